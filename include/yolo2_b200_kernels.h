@@ -1,0 +1,202 @@
+/*
+ * yolo2_b200_kernels.h — thin C-ABI over the sm_100a CUDA kernels of the
+ * YOLOv2 detection forward pass.  Plain pointers and sizes only; no C++ or
+ * torch types.  The C host runtime (darknet_b200.h) is written against this
+ * header exactly the way the reference's layer code is written against its
+ * own `*_ongpu` launchers.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to /root/reference/src_yolo2).
+ *
+ * Device tensor layout ("padded NHWC"): an activation tensor with valid
+ * extent H x W and C channels is stored as bf16 [B][H+1][W+1][CS] where CS is
+ * the channel stride of the buffer it lives in (CS >= C; CS > C when the
+ * tensor is a channel slice of a route/concat buffer).  Row H and column W of
+ * every image are zero.  With that single zero row/column, the 3x3 "same"
+ * convolution becomes a sum of nine GEMMs over *flat* positions
+ * p = (b*(H+1) + y)*(W+1) + x, tap (r,s) reading position
+ * p + (r-1)*(W+1) + (s-1); every halo read lands on a zero.
+ *
+ * All functions return 0 on success, a negative Y2_E* code otherwise, and
+ * never fall back to a CPU path.
+ */
+#ifndef YOLO2_B200_KERNELS_H
+#define YOLO2_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Y2_OK 0
+#define Y2_EINVAL (-1)
+#define Y2_ECUDA (-2)
+#define Y2_ENOMEM (-3)
+
+/* Opaque CUDA stream handle (cudaStream_t).  NULL = legacy default stream. */
+typedef void *y2_stream_t;
+
+const char *y2_last_error(void);
+
+/* ---- device runtime (replaces cuda.c:12-158 cuda_set_device / cuda_make_array /
+ *      cuda_push_array / cuda_pull_array / cuda_free) -------------------------------- */
+int y2_device_count(int *count);
+int y2_set_device(int dev);
+int y2_malloc(void **dptr, size_t bytes);
+int y2_free(void *dptr);
+int y2_memset(void *dptr, int value, size_t bytes, y2_stream_t s);
+int y2_host_alloc(void **hptr, size_t bytes);           /* pinned */
+int y2_host_free(void *hptr);
+int y2_memcpy_h2d(void *dst, const void *src, size_t bytes, y2_stream_t s);
+int y2_memcpy_d2h(void *dst, const void *src, size_t bytes, y2_stream_t s);
+int y2_stream_create(y2_stream_t *s);
+int y2_stream_destroy(y2_stream_t s);
+int y2_stream_sync(y2_stream_t s);
+int y2_device_sync(void);
+
+/* CUDA-graph capture of a layer schedule (replaces the host loop of
+ * network_kernels.cu:43-56 forward_network_gpu). */
+typedef void *y2_graph_t;
+int y2_graph_begin(y2_stream_t s);
+int y2_graph_end(y2_stream_t s, y2_graph_t *g);
+int y2_graph_launch(y2_graph_t g, y2_stream_t s);
+int y2_graph_destroy(y2_graph_t g);
+
+/* Events for device-side timing. */
+typedef void *y2_event_t;
+int y2_event_create(y2_event_t *e);
+int y2_event_record(y2_event_t e, y2_stream_t s);
+int y2_event_elapsed_ms(y2_event_t a, y2_event_t b, float *ms);
+int y2_event_destroy(y2_event_t e);
+
+/* ---- convolution (replaces convolutional_kernels.cu:77-131
+ *      forward_convolutional_layer_gpu = fill + im2col_ongpu + gemm_ongpu +
+ *      normalize_gpu + scale_bias_gpu + add_bias_gpu + activate_array_ongpu) ---------- */
+
+#define Y2_ACT_LINEAR 0
+#define Y2_ACT_LEAKY 1
+#define Y2_ACT_LOGISTIC 2
+
+#define Y2_OUT_BF16_PADDED 0 /* bf16 [B][H+1][W+1][out_cs], pads written as 0 */
+#define Y2_OUT_F32_FLAT 1    /* fp32 [B][H*W][out_cs] (the reference's "flatten"ed NHWC) */
+
+typedef struct y2_conv_desc {
+    const void *in;   /* bf16 padded NHWC, already offset to the first input channel */
+    int in_cs;        /* channel stride of `in` (elements) */
+    int cin;          /* channels read per tap; multiple of block_k */
+    int batch, h, w;  /* valid extent (stride-1 'same' conv: output extent is identical) */
+    int ksize;        /* 1 or 3 */
+    const void *wt;   /* bf16 [npad][ksize*ksize*cin], K index = (r*ksize+s)*cin + c */
+    int cout;         /* real filters */
+    int npad;         /* rows in wt, multiple of block_n */
+    int block_n;      /* 32, 64, 128 or 256 */
+    int block_k;      /* 64 (128-byte swizzle) or 32 (64-byte swizzle) */
+    const float *alpha; /* [npad]  scale_f / (sqrt(var_f) + 1e-6)  (1 when no batchnorm) */
+    const float *beta;  /* [npad]  bias_f - mean_f * alpha_f */
+    int act;          /* Y2_ACT_* */
+    void *out;        /* already offset to the first output channel */
+    int out_cs;       /* channel stride of `out` (elements) */
+    int out_mode;     /* Y2_OUT_* */
+} y2_conv_desc;
+
+typedef struct y2_conv_plan y2_conv_plan; /* tensor maps + launch geometry */
+
+int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **plan);
+int y2_conv_plan_launch(const y2_conv_plan *plan, y2_stream_t s);
+void y2_conv_plan_destroy(y2_conv_plan *plan);
+/* algorithmic flops of one launch: 2*cout*ksize^2*cin_real*B*H*W is the caller's
+ * business; this returns the number of MMA tiles for diagnostics. */
+int y2_conv_plan_tiles(const y2_conv_plan *plan);
+
+/* ---- layout / packing kernels ------------------------------------------------------ */
+
+/* fp32 NCHW [B][C][H][W] -> bf16 padded NHWC [B][H+1][W+1][cs] (channels >= C zeroed up
+ * to cpad).  Replaces the cuda_make_array upload of network_kernels.cu:399. */
+int y2_pack_nchw_f32(const float *src, void *dst, int batch, int c, int h, int w,
+                     int cpad, int cs, y2_stream_t s);
+
+/* First-layer patch gather: fp32 NCHW [B][C][H][W] -> bf16 [B][H+1][W+1][kpad] where
+ * channel k = c*ksize*ksize + r*ksize + s holds in[c][y+r-pad][x+s-pad] (0 outside),
+ * the K ordering of im2col.c:16-39.  k >= C*ksize*ksize zeroed. */
+int y2_pack_patches_f32(const float *src, void *dst, int batch, int c, int h, int w,
+                        int ksize, int kpad, y2_stream_t s);
+
+/* bf16 padded NHWC slice -> fp32 NCHW [B][C][H][W] (host-visible l.output layout). */
+int y2_unpack_to_nchw_f32(const void *src, float *dst, int batch, int c, int h, int w,
+                          int cs, y2_stream_t s);
+
+/* fp32 flat NHWC [B][H*W][cs] -> fp32 NCHW [B][C][H][W]. */
+int y2_flat_to_nchw_f32(const float *src, float *dst, int batch, int c, int hw, int cs,
+                        y2_stream_t s);
+
+/* fp32 NCHW -> fp32 flat NHWC (blas_kernels.cu:550-572 flatten_kernel, forward=1). */
+int y2_nchw_to_flat_f32(const float *src, float *dst, int batch, int c, int hw,
+                        y2_stream_t s);
+
+/* ---- maxpool (replaces maxpool_layer_kernels.cu:10-48,87-97) ------------------------ */
+int y2_maxpool(const void *in, int in_cs, void *out, int out_cs, int batch, int c,
+               int h, int w, int out_h, int out_w, int size, int stride, int pad,
+               y2_stream_t s);
+
+/* ---- reorg (replaces blas_kernels.cu:332-362 reorg_kernel, forward=0 as called by
+ *      reorg_layer.c:97-104) --------------------------------------------------------- */
+int y2_reorg(const void *in, int in_cs, void *out, int out_cs, int batch, int c, int h,
+             int w, int stride, y2_stream_t s);
+
+/* ---- route fallback copy (replaces route_layer.c:104-117 copy_ongpu loop); the
+ *      planner normally aliases producers into the concat buffer instead ------------- */
+int y2_copy_channels(const void *in, int in_cs, void *out, int out_cs, int batch, int c,
+                     int h, int w, y2_stream_t s);
+
+/* ---- region layer forward (replaces region_layer.c:383-422 + 144-177:
+ *      flatten + softmax + D2H + CPU logistic) ---------------------------------------- */
+/* in: fp32 flat [B][hw][n*(5+classes)] raw conv output; out: same shape, tx..th raw,
+ * objectness logistic'd, classes softmax'd (flat or per tree group). */
+int y2_region_forward(const float *in, float *out, int batch, int hw, int n, int classes,
+                      int softmax, int n_groups, const int *d_group_size,
+                      const int *d_group_offset, y2_stream_t s);
+
+/* ---- get_region_boxes (replaces region_layer.c:328-379, flat softmax and
+ *      tree-without-map / tree-with-map variants) ------------------------------------- */
+/* pred: [B][hw*n][5+classes] (mutated in the tree case, like the reference);
+ * boxes: [B][hw*n][4]; probs: [B][hw*n][classes_out]. */
+int y2_region_boxes(float *pred, const float *d_biases, float *boxes, float *probs,
+                    int batch, int lw, int lh, int n, int classes, float img_w,
+                    float img_h, float thresh, int only_objectness, int classfix,
+                    int tree_n, const int *d_tree_parent, const int *d_map, int map_n,
+                    y2_stream_t s);
+
+/* ---- do_nms_sort (replaces box.c:249-277) ------------------------------------------- */
+/* boxes [B][total][4], probs [B][total][classes] updated in place. */
+int y2_nms_sort(const float *boxes, float *probs, int batch, int total, int classes,
+                float thresh, y2_stream_t s);
+
+/* ---- final pick (replaces yolo_v2_class.cpp:221-239): per box max_index over classes,
+ *      keep prob > thresh; compacts to det[B][max_det] + count[B] --------------------- */
+typedef struct y2_det {
+    float x, y, w, h; /* box centre / size, relative units (as box.h:4-6) */
+    float prob;
+    int obj_id;
+    int box_index;
+} y2_det;
+int y2_collect(const float *boxes, const float *probs, int batch, int total, int classes,
+               float thresh, y2_det *det, int *count, int max_det, y2_stream_t s);
+
+/* ---- classifier tail (config 5) ----------------------------------------------------- */
+int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs,
+                    y2_stream_t s);
+int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp,
+                    y2_stream_t s);
+int y2_shortcut(const void *add, int add_cs, int add_c, int add_h, int add_w,
+                void *out, int out_cs, int out_c, int out_h, int out_w, int batch,
+                int act, y2_stream_t s);
+
+/* library identity, for the loader tests */
+const char *y2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,364 @@
+// HBM-bound data-movement kernels on the padded-NHWC bf16 layout:
+// input packing, maxpool, reorg, route copy, export to the reference's NCHW fp32.
+// All are grid-stride kernels launched with a multiple of the SM count; channel-innermost
+// 16-byte accesses wherever the layout allows.
+#include "y2_common.cuh"
+
+#include <float.h>
+
+namespace y2 {
+
+static inline int grid_for(long long work_items, int threads)
+{
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------
+// fp32 NCHW -> bf16 padded NHWC
+// ---------------------------------------------------------------------------------
+__global__ void pack_nchw_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                 int batch, int c, int h, int w, int cpad, int cs)
+{
+    const int hp = h + 1, wp = w + 1;
+    const long long total = (long long)batch * hp * wp;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % wp);
+        const int y = (int)((p / wp) % hp);
+        const int b = (int)(p / ((long long)wp * hp));
+        __nv_bfloat16 *o = dst + p * cs;
+        const bool valid = (x < w) && (y < h);
+        const float *s = src + ((size_t)b * c * h + y) * w + x;
+        for (int k = 0; k < cpad; ++k) {
+            float v = (valid && k < c) ? __ldg(s + (size_t)k * h * w) : 0.f;
+            o[k] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// first-layer patch gather (K ordering of the reference's im2col.c:16-39)
+// ---------------------------------------------------------------------------------
+template <int KPAD>
+__global__ void pack_patches_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                    int batch, int c, int h, int w, int ksize)
+{
+    const int hp = h + 1, wp = w + 1;
+    const int pad = ksize / 2;
+    const int kk = ksize * ksize;
+    const long long total = (long long)batch * hp * wp;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % wp);
+        const int y = (int)((p / wp) % hp);
+        const int b = (int)(p / ((long long)wp * hp));
+        float v[KPAD];
+#pragma unroll
+        for (int k = 0; k < KPAD; ++k) v[k] = 0.f;
+        if (x < w && y < h) {
+            const float *s = src + (size_t)b * c * h * w;
+#pragma unroll
+            for (int k = 0; k < KPAD; ++k) {
+                if (k < c * kk) {
+                    const int ci = k / kk;
+                    const int r = (k % kk) / ksize;
+                    const int q = k % ksize;
+                    const int yy = y + r - pad, xx = x + q - pad;
+                    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                        v[k] = __ldg(s + ((size_t)ci * h + yy) * w + xx);
+                }
+            }
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(dst + p * KPAD);
+#pragma unroll
+        for (int g = 0; g < KPAD / 8; ++g) {
+            uint4 t;
+            t.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+            t.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+            t.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+            t.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+            o[g] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// bf16 padded NHWC slice -> fp32 NCHW (export of l.output).  32x32 smem transpose so
+// both sides are coalesced: reads run along channels, writes along x.
+// ---------------------------------------------------------------------------------
+__global__ void unpack_nchw_kernel(const __nv_bfloat16 *__restrict__ src, float *__restrict__ dst,
+                                   int batch, int c, int h, int w, int cs)
+{
+    __shared__ float tile[32][33];
+    const int wp = w + 1, hp = h + 1;
+    const int xt = (w + 31) / 32, ct = (c + 31) / 32;
+    const long long ntiles = (long long)batch * h * xt * ct;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int cti = (int)(t % ct);
+        const int xti = (int)((t / ct) % xt);
+        const int y = (int)((t / ((long long)ct * xt)) % h);
+        const int b = (int)(t / ((long long)ct * xt * h));
+        // load: threadIdx.x -> channel, threadIdx.y -> x
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int x = xti * 32 + j, ch = cti * 32 + threadIdx.x;
+            float v = 0.f;
+            if (x < w && ch < c)
+                v = __bfloat162float(src[(((size_t)b * hp + y) * wp + x) * cs + ch]);
+            tile[j][threadIdx.x] = v;
+        }
+        __syncthreads();
+        for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+            const int ch = cti * 32 + j, x = xti * 32 + threadIdx.x;
+            if (x < w && ch < c) dst[(((size_t)b * c + ch) * h + y) * w + x] = tile[threadIdx.x][j];
+        }
+        __syncthreads();
+    }
+}
+
+// fp32 flat NHWC [B][hw][cs] <-> fp32 NCHW [B][c][hw]
+__global__ void flat_to_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int batch,
+                                    int c, int hw, int cs)
+{
+    const long long total = (long long)batch * c * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i % hw);
+        const int ch = (int)((i / hw) % c);
+        const int b = (int)(i / ((long long)hw * c));
+        dst[i] = src[((size_t)b * hw + s) * cs + ch];
+    }
+}
+__global__ void nchw_to_flat_kernel(const float *__restrict__ src, float *__restrict__ dst, int batch,
+                                    int c, int hw)
+{
+    const long long total = (long long)batch * c * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const int s = (int)((i / c) % hw);
+        const int b = (int)(i / ((long long)hw * c));
+        dst[i] = src[((size_t)b * c + ch) * hw + s];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// maxpool: out[b,y,x,k] = max_{n,m<size} in[b, y*stride+n-pad, x*stride+m-pad, k], cells
+// outside the valid extent are skipped (== -FLT_MAX in maxpool_layer.c:95-105).
+// One thread per (output position, 8-channel group): 16-byte loads/stores, channel
+// innermost -> fully coalesced.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void bf16x8_max(uint4 &acc, const uint4 &v)
+{
+    __nv_bfloat162 *a = reinterpret_cast<__nv_bfloat162 *>(&acc);
+    const __nv_bfloat162 *b = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hmax2(a[i], b[i]);
+}
+
+__global__ void maxpool_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
+                               __nv_bfloat16 *__restrict__ out, int out_cs, int batch, int c8, int h,
+                               int w, int oh, int ow, int size, int stride, int pad)
+{
+    const int ohp = oh + 1, owp = ow + 1, hp = h + 1, wp = w + 1;
+    const long long total = (long long)batch * ohp * owp * c8;
+    // -FLT_MAX is not representable in bf16; the most negative finite bf16 plays its role
+    // (only reachable when a window has no valid cell, which the cfgs never produce).
+    const uint32_t neg = 0xFF7FFF7Fu;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % c8);
+        const long long p = i / c8;
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        if (ox < ow && oy < oh) {
+            acc = make_uint4(neg, neg, neg, neg);
+            for (int n = 0; n < size; ++n) {
+                const int yy = oy * stride + n - pad;
+                if (yy < 0 || yy >= h) continue;
+                for (int m = 0; m < size; ++m) {
+                    const int xx = ox * stride + m - pad;
+                    if (xx < 0 || xx >= w) continue;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(
+                        in + (((size_t)b * hp + yy) * wp + xx) * in_cs + g * 8));
+                    bf16x8_max(acc, v);
+                }
+            }
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// reorg, exactly the index map of reorg_cpu(..., forward=0) (blas.c:8-29) as invoked by
+// reorg_layer.c:78-85 with the INPUT dims: out[in_index] = x[out_index], both flat NCHW
+// indices, x re-read as [c/s^2][h*s][w*s].  Output reports (w/s, h/s, c*s^2).
+// One thread per output element, channel innermost on the write side.
+// ---------------------------------------------------------------------------------
+__global__ void reorg_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
+                             __nv_bfloat16 *__restrict__ out, int out_cs, int batch, int c, int h, int w,
+                             int stride)
+{
+    const int oc = c * stride * stride, oh = h / stride, ow = w / stride;
+    const int ohp = oh + 1, owp = ow + 1, hp = h + 1, wp = w + 1;
+    const int out_c = c / (stride * stride);
+    const long long total = (long long)batch * ohp * owp * oc;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % oc);
+        const long long p = t / oc;
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (ox < ow && oy < oh) {
+            // flat NCHW index of this output element inside its image
+            const int in_index = ox + ow * (oy + oh * ch);
+            // decompose as (k, j, i) over the INPUT dims (c, h, w)
+            const int i = in_index % w;
+            const int j = (in_index / w) % h;
+            const int k = in_index / (w * h);
+            const int c2 = k % out_c;
+            const int offset = k / out_c;
+            const int w2 = i * stride + offset % stride;
+            const int h2 = j * stride + offset / stride;
+            const int out_index = w2 + w * stride * (h2 + h * stride * c2);
+            // out_index is a flat NCHW index into the true input (c, h, w)
+            const int sx = out_index % w;
+            const int sy = (out_index / w) % h;
+            const int sc = out_index / (w * h);
+            v = in[(((size_t)b * hp + sy) * wp + sx) * in_cs + sc];
+        }
+        out[(size_t)p * out_cs + ch] = v;
+    }
+}
+
+// route fallback: copy a channel slice between padded buffers of equal extent
+__global__ void copy_channels_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
+                                     __nv_bfloat16 *__restrict__ out, int out_cs, long long positions,
+                                     int c8)
+{
+    const long long total = positions * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % c8);
+        const long long p = i / c8;
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) =
+            __ldg(reinterpret_cast<const uint4 *>(in + (size_t)p * in_cs + g * 8));
+    }
+}
+
+} // namespace y2
+
+using namespace y2;
+
+extern "C" int y2_pack_nchw_f32(const float *src, void *dst, int batch, int c, int h, int w, int cpad,
+                                int cs, y2_stream_t s)
+{
+    if (!src || !dst || batch <= 0 || c <= 0 || cpad < c || cs < cpad) return Y2_EINVAL;
+    const long long total = (long long)batch * (h + 1) * (w + 1);
+    pack_nchw_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(src, (__nv_bfloat16 *)dst, batch, c, h,
+                                                                     w, cpad, cs);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_pack_patches_f32(const float *src, void *dst, int batch, int c, int h, int w, int ksize,
+                                   int kpad, y2_stream_t s)
+{
+    if (!src || !dst || batch <= 0 || c * ksize * ksize > kpad) {
+        set_error("y2_pack_patches_f32: c*k*k=%d does not fit kpad=%d", c * ksize * ksize, kpad);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (h + 1) * (w + 1);
+    const int grid = grid_for(total, 128);
+    if (kpad == 32)
+        pack_patches_kernel<32><<<grid, 128, 0, to_stream(s)>>>(src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize);
+    else if (kpad == 64)
+        pack_patches_kernel<64><<<grid, 128, 0, to_stream(s)>>>(src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize);
+    else {
+        set_error("y2_pack_patches_f32: kpad must be 32 or 64");
+        return Y2_EINVAL;
+    }
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_unpack_to_nchw_f32(const void *src, float *dst, int batch, int c, int h, int w, int cs,
+                                     y2_stream_t s)
+{
+    if (!src || !dst || batch <= 0) return Y2_EINVAL;
+    const long long ntiles = (long long)batch * h * ((w + 31) / 32) * ((c + 31) / 32);
+    long long grid = ntiles;
+    const long long cap = (long long)sm_count() * 32;
+    if (grid > cap) grid = cap;
+    unpack_nchw_kernel<<<(int)grid, dim3(32, 8), 0, to_stream(s)>>>((const __nv_bfloat16 *)src, dst, batch, c, h,
+                                                                    w, cs);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_flat_to_nchw_f32(const float *src, float *dst, int batch, int c, int hw, int cs,
+                                   y2_stream_t s)
+{
+    if (!src || !dst) return Y2_EINVAL;
+    const long long total = (long long)batch * c * hw;
+    flat_to_nchw_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(src, dst, batch, c, hw, cs);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_nchw_to_flat_f32(const float *src, float *dst, int batch, int c, int hw, y2_stream_t s)
+{
+    if (!src || !dst) return Y2_EINVAL;
+    const long long total = (long long)batch * c * hw;
+    nchw_to_flat_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(src, dst, batch, c, hw);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_maxpool(const void *in, int in_cs, void *out, int out_cs, int batch, int c, int h, int w,
+                          int out_h, int out_w, int size, int stride, int pad, y2_stream_t s)
+{
+    if (!in || !out || c % 8 || in_cs % 8 || out_cs % 8) {
+        set_error("y2_maxpool: channel counts must be multiples of 8 (c=%d in_cs=%d out_cs=%d)", c, in_cs, out_cs);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (out_h + 1) * (out_w + 1) * (c / 8);
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, in_cs, (__nv_bfloat16 *)out, out_cs, batch, c / 8, h, w, out_h, out_w, size,
+        stride, pad);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_reorg(const void *in, int in_cs, void *out, int out_cs, int batch, int c, int h, int w,
+                        int stride, y2_stream_t s)
+{
+    if (!in || !out || stride <= 0 || c % (stride * stride) || h % stride || w % stride) {
+        set_error("y2_reorg: c=%d h=%d w=%d not divisible by stride=%d", c, h, w, stride);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (h / stride + 1) * (w / stride + 1) * c * stride * stride;
+    reorg_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>((const __nv_bfloat16 *)in, in_cs,
+                                                                 (__nv_bfloat16 *)out, out_cs, batch, c, h, w,
+                                                                 stride);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_copy_channels(const void *in, int in_cs, void *out, int out_cs, int batch, int c, int h,
+                                int w, y2_stream_t s)
+{
+    if (!in || !out || c % 8 || in_cs % 8 || out_cs % 8) return Y2_EINVAL;
+    const long long positions = (long long)batch * (h + 1) * (w + 1);
+    copy_channels_kernel<<<grid_for(positions * (c / 8), 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, in_cs, (__nv_bfloat16 *)out, out_cs, positions, c / 8);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}

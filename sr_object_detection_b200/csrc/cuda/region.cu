@@ -1,0 +1,417 @@
+// Region layer forward, box decoding and final pick on the GPU.
+// Compiled with -fmad=false -prec-div=true: every float expression below mirrors the
+// C expression types of the reference so that thresholds, ties and the keep set come out
+// bit-identical (SURVEY.md section 8 "numerical contract").
+//
+// Replaces: forward_region_layer_gpu / forward_region_layer (region_layer.c:383-422,
+// 144-177), softmax (blas.c:205-221), softmax_tree (softmax_layer.c:35-47),
+// get_region_boxes / get_region_box (region_layer.c:328-379, 73-85),
+// hierarchy_predictions (tree.c:37-51), max_index pick (yolo_v2_class.cpp:221-239).
+#include "y2_common.cuh"
+
+#include <float.h>
+
+namespace y2 {
+
+// activations.h:35  static inline float logistic_activate(float x){return 1./(1. + exp(-x));}
+__device__ __forceinline__ float logistic_ref(float x)
+{
+    return (float)(1. / (1. + exp((double)(-x))));
+}
+
+// ---------------------------------------------------------------------------------
+// region forward: one warp per softmax group of one box.
+//   out[0..3] = in[0..3];  out[4] = logistic(in[4]);
+//   out[5+g..] = softmax over the group (blas.c:205-221): the exps are evaluated by the
+//   lanes in parallel (double exp, rounded to float), the float sum is then accumulated in
+//   index order by shuffling the terms through lane 0's order, so it is the same sequence
+//   of roundings as the reference's serial loop.
+// ---------------------------------------------------------------------------------
+__global__ void region_forward_kernel(const float *in, float *out,
+                                      long long boxes, int classes, int softmax, int n_groups,
+                                      const int *__restrict__ group_size,
+                                      const int *__restrict__ group_offset)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int size = classes + 5;
+    const int groups = n_groups > 0 ? n_groups : 1;
+    const long long work = boxes * groups;
+    for (long long wi = warp_global; wi < work; wi += nwarps) {
+        const long long box = wi / groups;
+        const int g = (int)(wi - box * groups);
+        const float *x = in + box * size;
+        float *o = out + box * size;
+        if (g == 0 && lane < 5) o[lane] = (lane == 4) ? logistic_ref(x[4]) : x[lane];
+        int off = 0, n = classes;
+        if (n_groups > 0) {
+            off = group_offset[g];
+            n = group_size[g];
+        }
+        const float *xi = x + 5 + off;
+        float *oi = o + 5 + off;
+        if (!softmax) {
+            for (int i = lane; i < n; i += 32) oi[i] = xi[i];
+            continue;
+        }
+        float largest = -FLT_MAX;
+        for (int i = lane; i < n; i += 32) {
+            const float v = xi[i];
+            if (v > largest) largest = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+            if (other > largest) largest = other;
+        }
+        // temp == 1: input[i]/temp - largest/temp is a float expression
+        float sum = 0.f;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            float e = 0.f;
+            if (i < n) {
+                const float arg = xi[i] / 1.f - largest / 1.f;
+                e = (float)exp((double)arg);
+                oi[i] = e;
+            }
+            const int cnt = (n - base) < 32 ? (n - base) : 32;
+            for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
+        }
+        for (int i = lane; i < n; i += 32) oi[i] = oi[i] / sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// get_region_boxes, flat-softmax variant (region_layer.c:328-347, 367-377).
+// One thread per (box, class) element; the class-0 thread also decodes the box.
+// ---------------------------------------------------------------------------------
+__global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const float *__restrict__ biases,
+                                         float *__restrict__ boxes, float *__restrict__ probs, int batch,
+                                         int lw, int lh, int n, int classes, float img_w, float img_h,
+                                         float thresh, int only_objectness, int classfix)
+{
+    const int per_img = lw * lh * n;
+    const long long total = (long long)batch * per_img * classes;
+    const int size = classes + 5;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % classes);
+        const long long bi = t / classes; // b*per_img + index
+        const int index = (int)(bi % per_img);
+        const float *x = pred + bi * size;
+        float scale = x[4];
+        if (classfix == -1 && scale < .5) scale = 0;
+        const float prob = scale * x[5 + j];
+        float pv = (prob > thresh) ? prob : 0;
+        if (j == 0) {
+            if (only_objectness) pv = scale;
+            const int an = index % n;
+            const int cell = index / n;
+            const int row = cell / lw;
+            const int col = cell % lw;
+            // get_region_box, DOABS branch (region_layer.c:76-83)
+            float bx = (col + logistic_ref(x[0])) / lw;
+            float by = (row + logistic_ref(x[1])) / lh;
+            float bw = (float)(exp((double)x[2]) * (double)biases[2 * an] / (double)lw);
+            float bh = (float)(exp((double)x[3]) * (double)biases[2 * an + 1] / (double)lh);
+            bx *= img_w;
+            by *= img_h;
+            bw *= img_w;
+            bh *= img_h;
+            float4 bb = make_float4(bx, by, bw, bh);
+            *reinterpret_cast<float4 *>(boxes + bi * 4) = bb;
+        }
+        probs[t] = pv;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// get_region_boxes, softmax-tree variants (region_layer.c:349-366).  One block per box:
+// the class scores are staged in shared memory, hierarchy_predictions is evaluated per
+// node by walking to the root and multiplying back down (float multiply commutes, so
+// v(j) = x[j] * v(parent) is reproduced exactly), then either the coco9k map lookup or
+// the "highest index above .5" selection runs.  pred is mutated like the reference.
+// ---------------------------------------------------------------------------------
+__global__ void region_boxes_tree_kernel(float *__restrict__ pred, const float *__restrict__ biases,
+                                         float *__restrict__ boxes, float *__restrict__ probs, int batch,
+                                         int lw, int lh, int n, int classes, float img_w, float img_h,
+                                         float thresh, int only_objectness, int classfix,
+                                         const int *__restrict__ parent, const int *__restrict__ map, int map_n)
+{
+    extern __shared__ float sh[]; // [classes] raw, [classes] hierarchical
+    float *sx = sh;
+    float *hv = sh + classes;
+    __shared__ int s_found;
+    const int per_img = lw * lh * n;
+    const long long nboxes = (long long)batch * per_img;
+    const int size = classes + 5;
+    const int out_classes = map ? map_n : classes;
+    for (long long bi = blockIdx.x; bi < nboxes; bi += gridDim.x) {
+        float *x = pred + bi * size;
+        const int index = (int)(bi % per_img);
+        for (int j = threadIdx.x; j < classes; j += blockDim.x) sx[j] = x[5 + j];
+        if (threadIdx.x == 0) s_found = -1;
+        __syncthreads();
+        float scale = x[4];
+        if (classfix == -1 && scale < .5) scale = 0;
+        for (int j = threadIdx.x; j < classes; j += blockDim.x) {
+            int path[64];
+            int depth = 0;
+            int c = j;
+            while (c >= 0 && depth < 64) {
+                path[depth++] = c;
+                c = parent[c];
+            }
+            float v = sx[path[depth - 1]];
+            for (int d = depth - 2; d >= 0; --d) v = sx[path[d]] * v;
+            hv[j] = v;
+        }
+        __syncthreads();
+        float *pr = probs + bi * out_classes;
+        if (map) {
+            for (int j = threadIdx.x; j < classes; j += blockDim.x) x[5 + j] = hv[j];
+            for (int j = threadIdx.x; j < map_n; j += blockDim.x) {
+                const float prob = scale * hv[map[j]];
+                pr[j] = (prob > thresh) ? prob : 0;
+            }
+        } else {
+            int best = -1;
+            for (int j = threadIdx.x; j < classes; j += blockDim.x)
+                if (hv[j] > .5 && j > best) best = j;
+            if (best >= 0) atomicMax(&s_found, best);
+            __syncthreads();
+            const int found = s_found;
+            for (int j = threadIdx.x; j < classes; j += blockDim.x) {
+                const float v = (j == found) ? hv[j] : 0.f;
+                x[5 + j] = v;
+                pr[j] = (scale > thresh) ? v : 0;
+            }
+        }
+        if (threadIdx.x == 0) {
+            if (only_objectness) pr[0] = scale;
+            const int an = index % n;
+            const int cell = index / n;
+            const int row = cell / lw;
+            const int col = cell % lw;
+            float bx = (col + logistic_ref(x[0])) / lw;
+            float by = (row + logistic_ref(x[1])) / lh;
+            float bw = (float)(exp((double)x[2]) * (double)biases[2 * an] / (double)lw);
+            float bh = (float)(exp((double)x[3]) * (double)biases[2 * an + 1] / (double)lh);
+            bx *= img_w;
+            by *= img_h;
+            bw *= img_w;
+            bh *= img_h;
+            *reinterpret_cast<float4 *>(boxes + bi * 4) = make_float4(bx, by, bw, bh);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// final pick (yolo_v2_class.cpp:221-239 / utils.c:533-545 max_index): per box the first
+// maximum over classes; keep when prob > thresh; emit in box-index order.
+// One block per image, one warp per box, ordered compaction by a block scan.
+// ---------------------------------------------------------------------------------
+__global__ void collect_kernel(const float *__restrict__ boxes, const float *__restrict__ probs, int total,
+                               int classes, float thresh, y2_det *__restrict__ det, int *__restrict__ count,
+                               int max_det)
+{
+    extern __shared__ int s_flag[]; // [total] obj id or -1, then prefix
+    float *s_prob = reinterpret_cast<float *>(s_flag + total);
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float *pb = probs + (size_t)b * total * classes;
+    for (int i = warp; i < total; i += nw) {
+        const float *p = pb + (size_t)i * classes;
+        float best = -FLT_MAX;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < classes; j += 32) {
+            const float v = p[j];
+            if (v > best) { best = v; arg = j; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) {
+            // max_index starts from a[0] with strict >, so an all-equal row yields 0
+            if (arg == 0x7fffffff) arg = 0;
+            const float pv = p[arg];
+            s_flag[i] = (pv > thresh) ? arg : -1;
+            s_prob[i] = pv;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+        y2_det *d = det + (size_t)b * max_det;
+        const float4 *bx = reinterpret_cast<const float4 *>(boxes) + (size_t)b * total;
+        for (int i = 0; i < total; ++i) {
+            if (s_flag[i] >= 0) {
+                if (c < max_det) {
+                    const float4 q = bx[i];
+                    d[c].x = q.x; d[c].y = q.y; d[c].w = q.z; d[c].h = q.w;
+                    d[c].prob = s_prob[i];
+                    d[c].obj_id = s_flag[i];
+                    d[c].box_index = i;
+                }
+                ++c;
+            }
+        }
+        count[b] = c;
+    }
+}
+
+// classifier tail ------------------------------------------------------------------
+// avgpool_layer.c:40-55: sequential float sum over h*w, then / (h*w).  One thread per
+// (b, c) keeps the reference's summation order; reads are coalesced along c.
+__global__ void avgpool_flat_kernel(const float *__restrict__ in, float *__restrict__ out, int batch, int hw,
+                                    int c, int cs)
+{
+    const long long total = (long long)batch * c;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const int b = (int)(t / c);
+        const float *p = in + (size_t)b * hw * cs + ch;
+        float s = 0.f;
+        for (int i = 0; i < hw; ++i) s += p[(size_t)i * cs];
+        out[t] = s / hw;
+    }
+}
+
+// softmax_layer.c:49-61 -> softmax(blas.c:205-221) per row, warp per row
+__global__ void softmax_rows_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int n,
+                                    float temp)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp_global; r < rows; r += nwarps) {
+        const float *xi = in + r * n;
+        float *oi = out + r * n;
+        float largest = -FLT_MAX;
+        for (int i = lane; i < n; i += 32) {
+            const float v = xi[i];
+            if (v > largest) largest = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+            if (other > largest) largest = other;
+        }
+        float sum = 0.f;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            float e = 0.f;
+            if (i < n) {
+                const float arg = xi[i] / temp - largest / temp;
+                e = (float)exp((double)arg);
+                oi[i] = e;
+            }
+            const int cnt = (n - base) < 32 ? (n - base) : 32;
+            for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
+        }
+        for (int i = lane; i < n; i += 32) oi[i] = oi[i] / sum;
+    }
+}
+
+static inline int grid_cap(long long blocks, int per_sm)
+{
+    long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+} // namespace y2
+
+using namespace y2;
+
+extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw, int n, int classes,
+                                 int softmax, int n_groups, const int *d_group_size,
+                                 const int *d_group_offset, y2_stream_t s)
+{
+    if (!in || !out || batch <= 0 || hw <= 0 || n <= 0 || classes <= 0) return Y2_EINVAL;
+    if (n_groups > 0 && (!d_group_size || !d_group_offset)) return Y2_EINVAL;
+    const long long boxes = (long long)batch * hw * n;
+    const long long work = boxes * (n_groups > 0 ? n_groups : 1);
+    const int threads = 256;
+    const int grid = grid_cap((work * 32 + threads - 1) / threads, 8);
+    region_forward_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
+                                                              d_group_size, d_group_offset);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes, float *probs, int batch,
+                               int lw, int lh, int n, int classes, float img_w, float img_h, float thresh,
+                               int only_objectness, int classfix, int tree_n, const int *d_tree_parent,
+                               const int *d_map, int map_n, y2_stream_t s)
+{
+    if (!pred || !d_biases || !boxes || !probs || batch <= 0) return Y2_EINVAL;
+    const long long nboxes = (long long)batch * lw * lh * n;
+    if (tree_n > 0) {
+        if (!d_tree_parent || tree_n != classes) {
+            set_error("y2_region_boxes: tree size %d != classes %d", tree_n, classes);
+            return Y2_EINVAL;
+        }
+        const size_t smem = (size_t)classes * 2 * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done && smem > 48 * 1024) {
+            Y2_CUDA_CHECK(cudaFuncSetAttribute(region_boxes_tree_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        if (smem > 200 * 1024) {
+            set_error("y2_region_boxes: %d classes exceed the shared-memory staging", classes);
+            return Y2_EINVAL;
+        }
+        region_boxes_tree_kernel<<<grid_cap(nboxes, 4), 256, smem, to_stream(s)>>>(
+            pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh, only_objectness,
+            classfix, d_tree_parent, d_map, map_n);
+    } else {
+        const long long total = nboxes * classes;
+        region_boxes_flat_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, to_stream(s)>>>(
+            pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh, only_objectness,
+            classfix);
+    }
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int total, int classes,
+                          float thresh, y2_det *det, int *count, int max_det, y2_stream_t s)
+{
+    if (!boxes || !probs || !det || !count || batch <= 0 || total <= 0) return Y2_EINVAL;
+    const size_t smem = (size_t)total * 8;
+    if (smem > 48 * 1024) {
+        set_error("y2_collect: %d boxes per image exceed the staging buffer", total);
+        return Y2_EINVAL;
+    }
+    collect_kernel<<<batch, 256, smem, to_stream(s)>>>(boxes, probs, total, classes, thresh, det, count,
+                                                       max_det);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs, y2_stream_t s)
+{
+    if (!in || !out) return Y2_EINVAL;
+    const long long total = (long long)batch * c;
+    avgpool_flat_kernel<<<grid_cap((total + 127) / 128, 16), 128, 0, to_stream(s)>>>(in, out, batch, hw, c, cs);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp, y2_stream_t s)
+{
+    if (!in || !out) return Y2_EINVAL;
+    softmax_rows_kernel<<<grid_cap(((long long)rows * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(in, out, rows,
+                                                                                                   n, temp);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}

@@ -1,0 +1,256 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C-ABI.
+
+The convolution is a floating-point kernel, so it is compared with a plain PyTorch fp32
+convolution of the same bf16-rounded operands (tolerances stated per test); the byte/index
+kernels (maxpool, reorg, pack/unpack, route copy) must match bit for bit.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from sr_object_detection_b200 import _lib  # noqa: E402
+from tests import gpu_util as G  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+ACT_LINEAR, ACT_LEAKY = 0, 1
+OUT_BF16, OUT_F32 = 0, 1
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ref_conv(x, wt, alpha, beta, act, ksize):
+    xb = x.to(torch.bfloat16).float()
+    wb = wt.to(torch.bfloat16).float()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv2d(xb, wb, padding=ksize // 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    y = y * alpha.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    if act == ACT_LEAKY:
+        y = torch.where(y > 0, y, 0.1 * y)
+    return y
+
+
+CONV_CASES = [
+    # (batch, cin, h, w, cout, ksize, block_n, block_k, act)
+    (2, 64, 13, 13, 64, 1, 64, 64, ACT_LEAKY),
+    (2, 64, 13, 13, 128, 3, 128, 64, ACT_LEAKY),
+    (4, 128, 13, 13, 256, 3, 256, 64, ACT_LEAKY),
+    (3, 32, 20, 28, 64, 3, 64, 32, ACT_LEAKY),
+    (2, 256, 26, 26, 512, 3, 256, 64, ACT_LEAKY),
+    (2, 512, 13, 13, 1024, 3, 128, 64, ACT_LEAKY),
+    (1, 1024, 13, 13, 512, 1, 256, 64, ACT_LINEAR),
+    (2, 32, 52, 52, 32, 1, 32, 32, ACT_LEAKY),
+    (64, 64, 13, 13, 64, 3, 64, 64, ACT_LEAKY),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "b%d_c%d_%dx%d_n%d_k%d_bn%d_bk%d_a%d" % c)
+def test_conv_bf16_matches_fp32_reference(case):
+    batch, cin, h, w, cout, ksize, block_n, block_k, act = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(1234 + cin + cout)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev) * 2 - 1
+    s = (2.0 / (ksize * ksize * cin)) ** 0.5
+    wt = (torch.rand(cout, cin, ksize, ksize, generator=g).to(dev) * 2 - 1) * s
+    npad = ((cout + block_n - 1) // block_n) * block_n
+    alpha = torch.ones(npad, device=dev)
+    beta = torch.zeros(npad, device=dev)
+    alpha[:cout] = torch.rand(cout, generator=g).to(dev) + 0.5
+    beta[:cout] = torch.rand(cout, generator=g).to(dev) * 0.2 - 0.1
+
+    x_p = G.to_padded_nhwc(x)
+    wt_p = G.pack_weights(wt, cin, npad)
+    out = torch.full((batch, h + 1, w + 1, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    G.run_conv(x_p, cin, cin, batch, h, w, ksize, wt_p, cout, npad, block_n, block_k, alpha, beta, act,
+               out, cout, OUT_BF16)
+    got = G.from_padded_nhwc(out, cout, h, w)
+    ref = _ref_conv(x, wt, alpha[:cout], beta[:cout], act, ksize)
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item() / scale
+    # bf16 output rounding is 2^-9 relative; fp32 accumulate. Tolerance: 1e-2 of the layer max.
+    assert err <= 1e-2, f"max err / max|ref| = {err:.3e}"
+    # pad row / column must be written as zeros
+    assert out[:, h, :, :].abs().max().item() == 0
+    assert out[:, :, w, :].abs().max().item() == 0
+
+
+def test_conv_f32_flat_head_125():
+    """1x1 linear head with 125 filters written as fp32 [B][H*W][125] (region-layer input)."""
+    dev = torch.device("cuda:0")
+    batch, cin, h, w, cout = 3, 1024, 13, 13, 125
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev) * 2 - 1
+    wt = (torch.rand(cout, cin, 1, 1, generator=g).to(dev) * 2 - 1) * (2.0 / cin) ** 0.5
+    npad = 128
+    alpha = torch.ones(npad, device=dev)
+    beta = torch.zeros(npad, device=dev)
+    beta[:cout] = torch.rand(cout, generator=g).to(dev) - 0.5
+    x_p = G.to_padded_nhwc(x)
+    wt_p = G.pack_weights(wt, cin, npad)
+    out = torch.zeros(batch, h * w, cout, dtype=torch.float32, device=dev)
+    G.run_conv(x_p, cin, cin, batch, h, w, 1, wt_p, cout, npad, 128, 64, alpha, beta, ACT_LINEAR, out, cout,
+               OUT_F32)
+    ref = _ref_conv(x, wt, alpha[:cout], beta[:cout], ACT_LINEAR, 1)
+    got = out.view(batch, h, w, cout).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    # operands are identical bf16 values on both sides; only fp32 summation order differs
+    assert err <= 1e-4, f"max err / max|ref| = {err:.3e}"
+
+
+def test_conv_channel_slice_in_concat_buffer():
+    """Output written at a channel offset of a wider buffer (in-place route) and input read
+    from a channel slice; neighbouring channels must be untouched."""
+    dev = torch.device("cuda:0")
+    batch, cin, h, w, cout = 2, 64, 13, 13, 128
+    g = torch.Generator(device="cpu").manual_seed(99)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev) * 2 - 1
+    wt = (torch.rand(cout, cin, 3, 3, generator=g).to(dev) * 2 - 1) * (2.0 / (9 * cin)) ** 0.5
+    alpha = torch.ones(cout, device=dev)
+    beta = torch.zeros(cout, device=dev)
+    in_cs, in_off = 192, 64
+    buf_in = torch.full((batch, h + 1, w + 1, in_cs), 3.0, dtype=torch.bfloat16, device=dev)
+    buf_in[:, :, :, in_off:in_off + cin] = G.to_padded_nhwc(x)
+    out_cs, out_off = 320, 64
+    buf_out = torch.full((batch, h + 1, w + 1, out_cs), 5.0, dtype=torch.bfloat16, device=dev)
+    wt_p = G.pack_weights(wt, cin, cout)
+    lib = _lib.load()
+    d = _lib.ConvDesc()
+    d.in_ = buf_in.data_ptr() + in_off * 2; d.in_cs = in_cs; d.cin = cin
+    d.batch = batch; d.h = h; d.w = w; d.ksize = 3
+    d.wt = wt_p.data_ptr(); d.cout = cout; d.npad = cout; d.block_n = 128; d.block_k = 64
+    d.alpha = alpha.data_ptr(); d.beta = beta.data_ptr(); d.act = ACT_LEAKY
+    d.out = buf_out.data_ptr() + out_off * 2; d.out_cs = out_cs; d.out_mode = OUT_BF16
+    plan = C.c_void_p()
+    _lib.check(lib.y2_conv_plan_create(C.byref(d), C.byref(plan)))
+    _lib.check(lib.y2_conv_plan_launch(plan, _stream()))
+    torch.cuda.synchronize()
+    lib.y2_conv_plan_destroy(plan)
+    ref = _ref_conv(x, wt, alpha, beta, ACT_LEAKY, 3)
+    got = buf_out[:, :h, :w, out_off:out_off + cout].permute(0, 3, 1, 2).float()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-2
+    assert (buf_out[..., :out_off] == 5.0).all() and (buf_out[..., out_off + cout:] == 5.0).all()
+
+
+def test_first_layer_patches_path():
+    """3-channel stem: patch gather (K=27 -> 32) + 1x1 GEMM == 3x3 convolution."""
+    dev = torch.device("cuda:0")
+    batch, cin, h, w, cout = 2, 3, 32, 48, 32
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev)
+    wt = (torch.rand(cout, cin, 3, 3, generator=g).to(dev) * 2 - 1) * (2.0 / 27) ** 0.5
+    alpha = torch.rand(cout, generator=g).to(dev) + 0.5
+    beta = torch.rand(cout, generator=g).to(dev) * 0.2
+    lib = _lib.load()
+    patches = torch.empty(batch, h + 1, w + 1, 32, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_pack_patches_f32(x.data_ptr(), patches.data_ptr(), batch, cin, h, w, 3, 32, _stream()))
+    # reference patches from torch unfold: K index = c*9 + r*3 + s
+    unf = torch.nn.functional.unfold(x, 3, padding=1).view(batch, 27, h, w)
+    assert torch.equal(patches[:, :h, :w, :27].permute(0, 3, 1, 2), unf.to(torch.bfloat16))
+    assert patches[:, :h, :w, 27:].abs().max().item() == 0
+    wt_p = torch.zeros(cout, 32, dtype=torch.bfloat16, device=dev)
+    wt_p[:, :27] = wt.reshape(cout, 27).to(torch.bfloat16)
+    out = torch.zeros(batch, h + 1, w + 1, cout, dtype=torch.bfloat16, device=dev)
+    G.run_conv(patches, 32, 32, batch, h, w, 1, wt_p, cout, cout, 32, 32, alpha, beta, ACT_LEAKY, out, cout,
+               OUT_BF16)
+    ref = _ref_conv(x, wt, alpha, beta, ACT_LEAKY, 3)
+    got = G.from_padded_nhwc(out, cout, h, w)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-2
+
+
+def test_pack_unpack_roundtrip_bit_exact():
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, c, h, w, cpad, cs = 3, 20, 17, 23, 32, 64
+    x = torch.randn(batch, c, h, w, device=dev)
+    packed = torch.full((batch, h + 1, w + 1, cs), 9.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_pack_nchw_f32(x.data_ptr(), packed.data_ptr(), batch, c, h, w, cpad, cs, _stream()))
+    ref = G.to_padded_nhwc(x, cpad)
+    assert torch.equal(packed[..., :cpad], ref)
+    assert (packed[..., cpad:] == 9.0).all()
+    back = torch.empty(batch, c, h, w, device=dev)
+    _lib.check(lib.y2_unpack_to_nchw_f32(packed.data_ptr(), back.data_ptr(), batch, c, h, w, cs, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("size,stride,h,w", [(2, 2, 26, 26), (2, 1, 13, 13), (2, 2, 416, 416), (3, 2, 31, 30)])
+def test_maxpool_bit_exact(size, stride, h, w):
+    """maxpool_layer.c:79-114 semantics: padding=(size-1)/2, out=(w+2p)/stride, window starts
+    at -padding, cells outside the image are skipped."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, c = 2, 32
+    pad = (size - 1) // 2
+    oh, ow = (h + 2 * pad) // stride, (w + 2 * pad) // stride
+    x = torch.randn(batch, c, h, w, device=dev).to(torch.bfloat16).float()
+    x_p = G.to_padded_nhwc(x)
+    out = torch.full((batch, oh + 1, ow + 1, c), 3.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_maxpool(x_p.data_ptr(), c, out.data_ptr(), c, batch, c, h, w, oh, ow, size, stride, pad,
+                              _stream()))
+    torch.cuda.synchronize()
+    neg = torch.finfo(torch.float32).min
+    # window covers rows [i*stride - pad, i*stride - pad + size): pad left by `pad`, right generously
+    xp = torch.nn.functional.pad(x, (pad, size, pad, size), value=neg)
+    ref = torch.nn.functional.max_pool2d(xp, size, stride)[:, :, :oh, :ow]
+    got = G.from_padded_nhwc(out, c, oh, ow)
+    assert torch.equal(got, ref)
+    assert out[:, oh].abs().max().item() == 0 and out[:, :, ow].abs().max().item() == 0
+
+
+def _reorg_reference(x: np.ndarray, stride: int) -> np.ndarray:
+    """reorg_cpu(x, w, h, c, batch, stride, forward=0, out) of blas.c:8-29, vectorised:
+    out.flat[in_index] = x.flat[out_index] per image."""
+    b, c, h, w = x.shape
+    out_c = c // (stride * stride)
+    k, j, i = np.meshgrid(np.arange(c), np.arange(h), np.arange(w), indexing="ij")
+    in_index = i + w * (j + h * k)
+    c2 = k % out_c
+    offset = k // out_c
+    w2 = i * stride + offset % stride
+    h2 = j * stride + offset // stride
+    out_index = w2 + w * stride * (h2 + h * stride * c2)
+    out = np.empty_like(x).reshape(b, -1)
+    xf = x.reshape(b, -1)
+    out[:, in_index.ravel()] = xf[:, out_index.ravel()]
+    return out.reshape(b, c * stride * stride, h // stride, w // stride)
+
+
+def test_reorg_matches_reference_index_map():
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, c, h, w, stride = 3, 64, 26, 26, 2
+    x = torch.randn(batch, c, h, w, device=dev).to(torch.bfloat16).float()
+    x_p = G.to_padded_nhwc(x)
+    oc, oh, ow = c * stride * stride, h // stride, w // stride
+    out_cs, off = 1280, 0
+    out = torch.full((batch, oh + 1, ow + 1, out_cs), 2.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_reorg(x_p.data_ptr(), c, out.data_ptr() + off * 2, out_cs, batch, c, h, w, stride, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(_reorg_reference(x.cpu().numpy(), stride)).to(dev)
+    got = out[:, :oh, :ow, off:off + oc].permute(0, 3, 1, 2).float()
+    assert torch.equal(got, ref)
+    assert (out[..., oc:] == 2.0).all()
+
+
+def test_copy_channels_route_fallback():
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, c, h, w = 2, 64, 13, 13
+    src = torch.randn(batch, h + 1, w + 1, 96, device=dev).to(torch.bfloat16)
+    dst = torch.zeros(batch, h + 1, w + 1, 160, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_copy_channels(src.data_ptr() + 16 * 2, 96, dst.data_ptr() + 32 * 2, 160, batch, c, h, w,
+                                    _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(dst[..., 32:96], src[..., 16:80])
+    assert dst[..., :32].abs().max().item() == 0 and dst[..., 96:].abs().max().item() == 0
