@@ -1,0 +1,286 @@
+/*
+ * darknet_b200.h — the reference's C API for the YOLOv2 detection forward pass,
+ * re-implemented on hand-written sm_100a kernels (libyolo2_b200.so).
+ *
+ * Source-level drop-in for the callers of SURVEY.md section 8b: a caller written against the
+ * reference headers (network.h, parser.h, region_layer.h, box.h, cuda.h, option_list.h,
+ * tree.h, utils.h under /root/reference/src_yolo2) recompiles against this single header.
+ * Names, argument meaning, by-value struct passing, ownership and error behaviour follow the
+ * reference; each declaration cites the interface it replaces.  Struct layouts are NOT
+ * binary-compatible with a reference build (training-only fields are dropped, device state
+ * lives behind `network.b200`).
+ *
+ * There is no CPU execution path: with gpu_index < 0 parse_network_cfg only builds the host
+ * description (shapes, weights), and network_predict aborts through error().
+ */
+#ifndef DARKNET_B200_H
+#define DARKNET_B200_H
+
+#include <stddef.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- activations.h:6-8 ------------------------------------------------------------ */
+typedef enum {
+    LOGISTIC, RELU, RELIE, LINEAR, RAMP, TANH, PLSE, LEAKY, ELU, LOGGY, STAIR, HARDTAN, LHTAN
+} ACTIVATION;
+ACTIVATION get_activation(char *s);          /* activations.c:45-62 */
+char *get_activation_string(ACTIVATION a);   /* activations.c:9-43 */
+
+/* ---- layer.h:13-42 ---------------------------------------------------------------- */
+typedef enum {
+    CONVOLUTIONAL, DECONVOLUTIONAL, CONNECTED, MAXPOOL, SOFTMAX, DETECTION, DROPOUT, CROP,
+    ROUTE, COST, NORMALIZATION, AVGPOOL, LOCAL, SHORTCUT, ACTIVE, RNN, GRU, CRNN, BATCHNORM,
+    NETWORK, XNOR, REGION, REORG, BLANK
+} LAYER_TYPE;
+typedef enum { SSE, MASKED, SMOOTH } COST_TYPE;
+
+/* ---- tree.h:4-14 ------------------------------------------------------------------- */
+typedef struct {
+    int *leaf;
+    int n;
+    int *parent;
+    int *group;
+    char **name;
+    int groups;
+    int *group_size;
+    int *group_offset;
+} tree;
+tree *read_tree(char *filename);                                                   /* tree.c:53-103 */
+void hierarchy_predictions(float *predictions, int n, tree *hier, int only_leaves); /* tree.c:37-51 */
+float get_hierarchy_probability(float *x, tree *hier, int c);                      /* tree.c:26-35 */
+
+/* ---- box.h:4-6 ---------------------------------------------------------------------- */
+typedef struct { float x, y, w, h; } box;
+
+struct network_state;
+struct layer;
+typedef struct layer layer;
+
+/* ---- layer.h:44-264 (inference subset; same field names) ---------------------------- */
+struct layer {
+    LAYER_TYPE type;
+    ACTIVATION activation;
+    COST_TYPE cost_type;
+    void (*forward)(struct layer, struct network_state);      /* aborts: no CPU path */
+    void (*forward_gpu)(struct layer, struct network_state);
+    int batch_normalize;
+    int batch;
+    int flipped;
+    int inputs, outputs;
+    int h, w, c;
+    int out_h, out_w, out_c;
+    int n;            /* filters (conv) / anchors (region) / inputs (route) */
+    int groups;
+    int size, stride, pad, reverse;
+    int index;        /* shortcut source */
+    int binary, xnor;
+    int softmax, classes, coords;
+    int max_boxes, log, sqrt, rescore, bias_match, random, absolute, classfix;
+    float jitter, thresh;
+    float coord_scale, object_scale, noobject_scale, class_scale;
+    float temperature, dot;
+    int dontload, dontloadscales;
+    tree *softmax_tree;
+    int *map;
+    float *cost;
+    /* host parameter arrays, exactly as load_weights fills them (parser.c:963-1006) */
+    float *biases;
+    float *scales;
+    float *weights;
+    float *rolling_mean;
+    float *rolling_variance;
+    int *input_layers;
+    int *input_sizes;
+    /* host activations, fp32 NCHW (REGION: flattened [hw][n][5+classes]).  Always present for
+     * the network's output layer; for other layers it is filled on demand by
+     * get_network_output_layer(). */
+    float *output;
+    size_t workspace_size;
+    /* device side (opaque layouts, see yolo2_b200_kernels.h) */
+    float *output_gpu;
+    float *weights_gpu;
+    float *biases_gpu;
+    float *scales_gpu;
+    void *b200;       /* per-layer plan */
+};
+void free_layer(layer);                                                            /* layer.c:5-96 */
+
+/* ---- network.h:19-77 ---------------------------------------------------------------- */
+typedef enum { CONSTANT, STEP, EXP, POLY, STEPS, SIG, RANDOM } learning_rate_policy;
+
+typedef struct network {
+    float *workspace;
+    int n;
+    int batch;
+    int *seen;
+    float epoch;
+    int subdivisions;
+    float momentum, decay;
+    layer *layers;
+    int outputs;
+    float *output;
+    learning_rate_policy policy;
+    float learning_rate, gamma, scale, power;
+    int time_steps, step, max_batches;
+    float *scales;
+    int *steps;
+    int num_steps, burn_in;
+    int adam;
+    float B1, B2, eps;
+    int inputs;
+    int h, w, c;
+    int max_crop, min_crop;
+    float angle, aspect, exposure, saturation, hue;
+    int gpu_index;
+    tree *hierarchy;
+    float **input_gpu;
+    float **truth_gpu;
+    void *b200;       /* device arena, stream, layer schedule, CUDA graph */
+} network;
+
+typedef struct network_state {
+    float *truth;
+    float *input;
+    float *delta;
+    float *workspace;
+    int train;
+    int index;
+    network net;
+} network_state;
+
+/* ---- cuda.h:8,22-32 / cuda.c:1-158 --------------------------------------------------- */
+extern int gpu_index;
+#define BLOCK 512
+void cuda_set_device(int n);
+int cuda_get_device(void);
+void check_error_code(int status, const char *what); /* cuda.c:27-49 check_error: print, abort */
+float *cuda_make_array(float *x, size_t n);
+int *cuda_make_int_array(size_t n);
+void cuda_push_array(float *x_gpu, float *x, size_t n);
+void cuda_pull_array(float *x_gpu, float *x, size_t n);
+void cuda_free(float *x_gpu);
+
+/* ---- parser.h:5-11 -------------------------------------------------------------------- */
+network parse_network_cfg(char *filename);                         /* parser.c:585-700 */
+void load_weights(network *net, char *filename);                   /* parser.c:1084-1087 */
+void load_weights_upto(network *net, char *filename, int cutoff);  /* parser.c:1009-1082 */
+void save_weights(network net, char *filename);                    /* parser.c:879-882 */
+void save_weights_upto(network net, char *filename, int cutoff);   /* parser.c:822-878 */
+
+/* ---- network.h:79-131 ------------------------------------------------------------------ */
+network make_network(int n);                                       /* network.c:132-143 */
+void free_network(network net);                                    /* network.c:592-609 */
+float *network_predict(network net, float *input);                 /* network.c:458-474 */
+float *network_predict_gpu(network net, float *input);             /* network_kernels.cu:392-407 */
+void forward_network(network net, network_state state);            /* network.c:145-158: aborts */
+void forward_network_gpu(network net, network_state state);        /* network_kernels.cu:43-56 */
+float *get_network_output(network net);                            /* network.c:173-181 */
+float *get_network_output_gpu(network net);                        /* network_kernels.cu:378-390 */
+float *get_network_output_layer(network net, int i);               /* network.c:466 */
+float *get_network_output_gpu_layer(network net, int i);
+int get_network_output_size(network net);                          /* network.c:167-171 */
+int get_network_output_size_layer(network net, int i);
+int get_network_input_size(network net);
+void set_batch_network(network *net, int b);                       /* network.c:308-320 */
+int resize_network(network *net, int w, int h);                    /* network.c:322-388 */
+char *get_layer_string(LAYER_TYPE a);                              /* network.c:77-130 */
+
+/* ---- region_layer.h:9-18, box.h:12-20 -------------------------------------------------- */
+void forward_region_layer_gpu(const layer l, network_state state); /* region_layer.c:383-422 */
+void get_region_boxes(layer l, int w, int h, float thresh, float **probs, box *boxes,
+                      int only_objectness, int *map);              /* region_layer.c:328-379 */
+void do_nms_sort(box *boxes, float **probs, int total, int classes, float thresh); /* box.c:249-277 */
+void do_nms(box *boxes, float **probs, int total, int classes, float thresh);      /* box.c:279-297 */
+float box_iou(box a, box b);                                       /* box.c:94-97 */
+float box_intersection(box a, box b);
+float box_union(box a, box b);
+
+/* ---- option_list.h:12-21, list.h, utils.h --------------------------------------------- */
+typedef struct node { void *val; struct node *next; struct node *prev; } node;
+typedef struct list { int size; node *front; node *back; } list;
+list *make_list(void);
+void list_insert(list *, void *);
+void free_list(list *l);
+void free_list_contents(list *l);
+void **list_to_array(list *l);
+
+list *read_data_cfg(char *filename);                               /* option_list.c:7-33 */
+int read_option(char *s, list *options);                           /* option_list.c:35-51 */
+void option_insert(list *l, char *key, char *val);
+char *option_find(list *l, char *key);
+char *option_find_str(list *l, char *key, char *def);
+int option_find_int(list *l, char *key, int def);
+int option_find_int_quiet(list *l, char *key, int def);
+float option_find_float(list *l, char *key, float def);
+float option_find_float_quiet(list *l, char *key, float def);
+void option_unused(list *l);
+
+void error(const char *s);                                         /* utils.c:195-200 */
+void file_error(char *s);                                          /* utils.c:208-213 */
+char *fgetl(FILE *fp);                                             /* utils.c:263-293 */
+void strip(char *s);                                               /* utils.c:230-241 */
+int *read_map(char *filename);                                     /* utils.c:17-33 */
+int max_index(float *a, int n);                                    /* utils.c:533-545 */
+void mean_arrays(float **a, int n, int els, float *avg);           /* utils.c:420-433 */
+char *basecfg(char *cfgfile);                                      /* utils.c:136-153 */
+char **get_labels(char *filename);                                 /* data.c:474-480 */
+int find_arg(int argc, char *argv[], char *arg);
+int find_int_arg(int argc, char **argv, char *arg, int def);
+float find_float_arg(int argc, char **argv, char *arg, float def);
+char *find_char_arg(int argc, char **argv, char *arg, char *def);
+
+/* ---- image.h (the two calls Detector::detect needs) ------------------------------------ */
+typedef struct { int h, w, c; float *data; } image;
+image make_image(int w, int h, int c);                             /* image.c:1436-1441 */
+void free_image(image m);
+image resize_image(image im, int w, int h);                        /* image.c:1950-1993 */
+
+/* =========================================================================================
+ * B200 extensions (not in the reference): batched, device-resident detection.
+ * ========================================================================================= */
+
+typedef struct y2_detection {
+    float x, y, w, h;   /* centre/size in relative units, as `box` */
+    float prob;
+    int obj_id;
+    int box_index;      /* cell-major, anchor-minor index, as probs[] rows */
+} y2_detection;
+
+/* Upload `batch` images (fp32 planar CHW, [0,1]) into the network's device input buffer. */
+void network_upload_input(network net, const float *input);
+/* Pinned host staging buffer ([batch][c][h][w] fp32) that network_upload_input copies from;
+ * fill it directly and pass it (or NULL) to network_upload_input to skip the extra host copy. */
+float *network_input_staging(network net);
+/* Forward pass on the already-uploaded input; nothing is copied back. */
+void network_forward_device(network net);
+/* Region decode + NMS + final pick on the device for every image of the batch; copies only
+ * the compact per-image detection lists back.  dets: [batch][max_det], counts: [batch]. */
+void network_detect_device(network net, float thresh, float nms, y2_detection *dets, int *counts,
+                           int max_det);
+/* upload + forward + detect, one synchronisation */
+void network_detect_batch(network net, const float *input, float thresh, float nms,
+                          y2_detection *dets, int *counts, int max_det);
+/* Block until the network's stream is idle. */
+void network_sync(network net);
+/* Device stream the network runs on (cudaStream_t) — for timing with CUDA events. */
+void *network_stream(network net);
+/* Algorithmic conv FLOPs per image: sum 2*n*k*k*c*out_h*out_w (darknet.c:115-131 `operations`). */
+double network_conv_flops(network net);
+/* Number of kernel launches one forward issues (diagnostics / bench `gpu_launches`). */
+int network_launch_count(network net);
+/* Per-layer device time of the last profiled forward, in ms (NULL if never profiled). */
+int network_profile_layers(network net, float *ms_per_layer, int n);
+/* 1 -> run layers eagerly instead of replaying the captured CUDA graph */
+void network_set_eager(network net, int eager);
+/* sizeof(layer|network|network_state|y2_detection|box) for what = 0..4: lets a binding that
+ * passes these structs by value check its mirror against the library it loaded. */
+size_t y2_abi_sizeof(int what);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

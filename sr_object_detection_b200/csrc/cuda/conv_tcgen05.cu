@@ -320,19 +320,39 @@ struct y2_conv_plan {
 namespace y2 {
 
 template <int BN, int BK>
-static int launch_cfg(const y2_conv_plan *pl, cudaStream_t st)
+static int prepare_cfg()
 {
+    // raise the dynamic shared-memory limit once per device; done at plan time so that nothing
+    // but the launch itself happens inside a CUDA-graph capture
     static bool attr_done[64] = {false};
     int dev = 0;
-    cudaGetDevice(&dev);
+    Y2_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_tcgen05_kernel<BN, BK>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done[dev] = true;
     }
+    return Y2_OK;
+}
+
+template <int BN, int BK>
+static int launch_cfg(const y2_conv_plan *pl, cudaStream_t st)
+{
     conv_tcgen05_kernel<BN, BK><<<pl->grid, kThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->prm);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
+}
+
+#define Y2_FOR_EACH_CFG(X) X(256, 64) X(128, 64) X(64, 64) X(32, 64) X(128, 32) X(64, 32) X(32, 32)
+
+static int prepare(int block_n, int block_k)
+{
+#define Y2_CASE(BN, BK) \
+    if (block_n == BN && block_k == BK) return prepare_cfg<BN, BK>();
+    Y2_FOR_EACH_CFG(Y2_CASE)
+#undef Y2_CASE
+    set_error("no conv kernel for block_n=%d block_k=%d", block_n, block_k);
+    return Y2_EINVAL;
 }
 
 } // namespace y2
@@ -414,6 +434,11 @@ extern "C" int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **out_pla
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = sm_count();
     pl->grid = tiles < sms ? tiles : sms;
+    rc = prepare(d->block_n, d->block_k);
+    if (rc != Y2_OK) {
+        delete pl;
+        return rc;
+    }
     *out_plan = pl;
     return Y2_OK;
 }
@@ -425,13 +450,7 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
     cudaStream_t st = to_stream(s);
 #define Y2_CASE(BN, BK) \
     if (pl->block_n == BN && pl->block_k == BK) return launch_cfg<BN, BK>(pl, st);
-    Y2_CASE(256, 64)
-    Y2_CASE(128, 64)
-    Y2_CASE(64, 64)
-    Y2_CASE(32, 64)
-    Y2_CASE(128, 32)
-    Y2_CASE(64, 32)
-    Y2_CASE(32, 32)
+    Y2_FOR_EACH_CFG(Y2_CASE)
 #undef Y2_CASE
     set_error("y2_conv_plan_launch: no kernel for block_n=%d block_k=%d", pl->block_n, pl->block_k);
     return Y2_EINVAL;

@@ -1,0 +1,194 @@
+/*
+ * Post-processing entry points of the drop-in API and the batched device-resident detection
+ * extension.  The arithmetic runs in the region / NMS kernels; these functions only move the
+ * caller-owned host arrays (boxes[total], probs[total][classes]) across, as the reference's
+ * callers expect (detector.c:486-495, yolo_v2_class.cpp:71-73,215-216).
+ *
+ * Reference interfaces replaced: get_region_boxes (region_layer.c:328-379), do_nms_sort
+ * (box.c:249-277), box_iou & friends (box.c:67-97).
+ */
+#include "y2_host.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+_Static_assert(sizeof(y2_detection) == sizeof(y2_det), "y2_detection must mirror y2_det");
+
+/* ---- box helpers (box.c:67-97), plain float arithmetic for API users ------------------------- */
+static float overlap(float x1, float w1, float x2, float w2)
+{
+    float l1 = x1 - w1 / 2;
+    float l2 = x2 - w2 / 2;
+    float left = l1 > l2 ? l1 : l2;
+    float r1 = x1 + w1 / 2;
+    float r2 = x2 + w2 / 2;
+    float right = r1 < r2 ? r1 : r2;
+    return right - left;
+}
+
+float box_intersection(box a, box b)
+{
+    float w = overlap(a.x, a.w, b.x, b.w);
+    float h = overlap(a.y, a.h, b.y, b.h);
+    if (w < 0 || h < 0) return 0;
+    return w * h;
+}
+
+float box_union(box a, box b)
+{
+    float i = box_intersection(a, b);
+    return a.w * a.h + b.w * b.h - i;
+}
+
+float box_iou(box a, box b)
+{
+    return box_intersection(a, b) / box_union(a, b);
+}
+
+/* ---- scratch -------------------------------------------------------------------------------- */
+typedef struct {
+    void *dev;
+    size_t dev_bytes;
+    void *host;
+    size_t host_bytes;
+} scratch_t;
+
+static void scratch_reserve(scratch_t *s, size_t bytes)
+{
+    if (s->dev_bytes < bytes) {
+        y2_free(s->dev);
+        Y2_CHECK(y2_malloc(&s->dev, bytes));
+        s->dev_bytes = bytes;
+    }
+    if (s->host_bytes < bytes) {
+        y2_host_free(s->host);
+        Y2_CHECK(y2_host_alloc(&s->host, bytes));
+        s->host_bytes = bytes;
+    }
+}
+
+static __thread scratch_t g_pred, g_boxes, g_probs;
+
+/* region_layer.c:328-379.  Reads l.output on the HOST (callers may have replaced it, e.g. the
+ * 3-frame mean of yolo_v2_class.cpp:208-213), decodes on the device, writes the caller's arrays.
+ * In the tree case l.output is mutated exactly like the reference does. */
+void get_region_boxes(layer l, int w, int h, float thresh, float **probs, box *boxes, int only_objectness,
+                      int *map)
+{
+    y2_layer_rt *r = y2_lrt(l);
+    if (!r || l.type != REGION) error("get_region_boxes: not a planned region layer");
+    const int total = l.w * l.h * l.n;
+    const int out_classes = map ? 200 : l.classes;
+    const size_t pred_bytes = (size_t)l.outputs * sizeof(float);
+    scratch_reserve(&g_pred, pred_bytes);
+    scratch_reserve(&g_boxes, (size_t)total * 4 * sizeof(float));
+    scratch_reserve(&g_probs, (size_t)total * l.classes * sizeof(float));
+    memcpy(g_pred.host, l.output, pred_bytes);
+    Y2_CHECK(y2_memcpy_h2d(g_pred.dev, g_pred.host, pred_bytes, 0));
+    int *map_dev = 0;
+    if (map) {
+        if (map == l.map && r->map_dev) map_dev = r->map_dev;
+        else {
+            Y2_CHECK(y2_malloc((void **)&map_dev, 200 * sizeof(int)));
+            Y2_CHECK(y2_memcpy_h2d(map_dev, map, 200 * sizeof(int), 0));
+        }
+    }
+    Y2_CHECK(y2_region_boxes((float *)g_pred.dev, r->biases_dev, (float *)g_boxes.dev, (float *)g_probs.dev, 1,
+                             l.w, l.h, l.n, l.classes, (float)w, (float)h, thresh, only_objectness, l.classfix,
+                             l.softmax_tree ? l.softmax_tree->n : 0, r->tree_parent_dev, map_dev, map ? 200 : 0,
+                             0));
+    Y2_CHECK(y2_memcpy_d2h(g_boxes.host, g_boxes.dev, (size_t)total * 4 * sizeof(float), 0));
+    Y2_CHECK(y2_memcpy_d2h(g_probs.host, g_probs.dev, (size_t)total * out_classes * sizeof(float), 0));
+    if (l.softmax_tree) Y2_CHECK(y2_memcpy_d2h(g_pred.host, g_pred.dev, pred_bytes, 0));
+    Y2_CHECK(y2_stream_sync(0));
+    if (map_dev && map_dev != r->map_dev) y2_free(map_dev);
+    memcpy(boxes, g_boxes.host, (size_t)total * sizeof(box));
+    for (int j = 0; j < total; ++j)
+        memcpy(probs[j], (float *)g_probs.host + (size_t)j * out_classes, (size_t)out_classes * sizeof(float));
+    if (l.softmax_tree) memcpy(l.output, g_pred.host, pred_bytes);
+}
+
+/* box.c:249-277 */
+void do_nms_sort(box *boxes, float **probs, int total, int classes, float thresh)
+{
+    if (total <= 0 || classes <= 0) return;
+    scratch_reserve(&g_boxes, (size_t)total * 4 * sizeof(float));
+    scratch_reserve(&g_probs, (size_t)total * classes * sizeof(float));
+    memcpy(g_boxes.host, boxes, (size_t)total * sizeof(box));
+    for (int j = 0; j < total; ++j)
+        memcpy((float *)g_probs.host + (size_t)j * classes, probs[j], (size_t)classes * sizeof(float));
+    Y2_CHECK(y2_memcpy_h2d(g_boxes.dev, g_boxes.host, (size_t)total * 4 * sizeof(float), 0));
+    Y2_CHECK(y2_memcpy_h2d(g_probs.dev, g_probs.host, (size_t)total * classes * sizeof(float), 0));
+    Y2_CHECK(y2_nms_sort((const float *)g_boxes.dev, (float *)g_probs.dev, 1, total, classes, thresh, 0));
+    Y2_CHECK(y2_memcpy_d2h(g_probs.host, g_probs.dev, (size_t)total * classes * sizeof(float), 0));
+    Y2_CHECK(y2_stream_sync(0));
+    for (int j = 0; j < total; ++j)
+        memcpy(probs[j], (float *)g_probs.host + (size_t)j * classes, (size_t)classes * sizeof(float));
+}
+
+/* box.c:279-297 is only reached from demo.c / validate_detector_recall, outside the hot path */
+void do_nms(box *boxes, float **probs, int total, int classes, float thresh)
+{
+    (void)boxes;
+    (void)probs;
+    (void)total;
+    (void)classes;
+    (void)thresh;
+    error("do_nms (unsorted variant) is outside the B200 hot path; use do_nms_sort");
+}
+
+/* ---- batched, device-resident detection (extension) -------------------------------------------- */
+static layer *region_of(network net)
+{
+    layer *l = &net.layers[net.n - 1];
+    if (l->type != REGION || !l->b200) error("network_detect: last layer is not a planned region layer");
+    return l;
+}
+
+void network_detect_device(network net, float thresh, float nms, y2_detection *dets, int *counts, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt) error("network_detect: network has no device plan");
+    Y2_CHECK(y2_set_device(rt->device));
+    layer *l = region_of(net);
+    y2_layer_rt *r = (y2_layer_rt *)l->b200;
+    const int B = net.batch;
+    const int total = l->w * l->h * l->n;
+    if (rt->det_cap < max_det || rt->det_batch < B) {
+        y2_free(rt->det_dev);
+        y2_host_free(rt->det_pinned);
+        y2_free(rt->cnt_dev);
+        y2_host_free(rt->cnt_pinned);
+        rt->det_cap = max_det;
+        rt->det_batch = B > rt->cap_batch ? B : rt->cap_batch;
+        const size_t nd = (size_t)rt->det_batch * rt->det_cap;
+        Y2_CHECK(y2_malloc((void **)&rt->det_dev, nd * sizeof(y2_det)));
+        Y2_CHECK(y2_host_alloc((void **)&rt->det_pinned, nd * sizeof(y2_det)));
+        Y2_CHECK(y2_malloc((void **)&rt->cnt_dev, (size_t)rt->det_batch * sizeof(int)));
+        Y2_CHECK(y2_host_alloc((void **)&rt->cnt_pinned, (size_t)rt->det_batch * sizeof(int)));
+    }
+    Y2_CHECK(y2_region_boxes((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
+                             l->classes, 1.f, 1.f, thresh, 0, l->classfix,
+                             l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0, rt->stream));
+    if (nms > 0)
+        Y2_CHECK(y2_nms_sort(r->boxes_dev, r->probs_dev, B, total, l->classes, nms, rt->stream));
+    Y2_CHECK(y2_collect(r->boxes_dev, r->probs_dev, B, total, l->classes, thresh, rt->det_dev, rt->cnt_dev,
+                        rt->det_cap, rt->stream));
+    Y2_CHECK(y2_memcpy_d2h(rt->cnt_pinned, rt->cnt_dev, (size_t)B * sizeof(int), rt->stream));
+    Y2_CHECK(y2_memcpy_d2h(rt->det_pinned, rt->det_dev, (size_t)B * rt->det_cap * sizeof(y2_det), rt->stream));
+    Y2_CHECK(y2_stream_sync(rt->stream));
+    for (int b = 0; b < B; ++b) {
+        int c = rt->cnt_pinned[b];
+        counts[b] = c;
+        if (c > max_det) c = max_det;
+        memcpy(dets + (size_t)b * max_det, rt->det_pinned + (size_t)b * rt->det_cap, (size_t)c * sizeof(y2_det));
+    }
+}
+
+void network_detect_batch(network net, const float *input, float thresh, float nms, y2_detection *dets,
+                          int *counts, int max_det)
+{
+    network_upload_input(net, input);
+    network_forward_device(net);
+    network_detect_device(net, thresh, nms, dets, counts, max_det);
+}

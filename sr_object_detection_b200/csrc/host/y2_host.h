@@ -1,0 +1,114 @@
+/* Internal header of the C host runtime (not installed). */
+#ifndef Y2_HOST_H
+#define Y2_HOST_H
+
+#include "darknet_b200.h"
+#include "yolo2_b200_kernels.h"
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* abort through the reference's fatal-exit convention when a kernel-ABI call fails */
+void y2_fatal(const char *where, int rc);
+#define Y2_CHECK(call)                                  \
+    do {                                                \
+        int _rc = (call);                               \
+        if (_rc != Y2_OK) y2_fatal(#call, _rc);         \
+    } while (0)
+
+enum { Y2_KIND_BF16_PADDED = 0, Y2_KIND_F32_FLAT = 1, Y2_KIND_F32_VEC = 2, Y2_KIND_NONE = 3 };
+
+/* per-layer device plan, owned by net.layers[i].b200 */
+typedef struct y2_layer_rt {
+    /* output view */
+    void *out;          /* first channel of this layer's output */
+    int out_cs;         /* channel stride (elements) */
+    int out_kind;       /* Y2_KIND_* */
+    int cpad;           /* channels stored (>= out_c) */
+    void *own_buf;      /* allocation owned by this layer, NULL when aliased / placed */
+    size_t own_bytes;
+    int placed_in;      /* route layer index whose concat buffer holds this output, or -1 */
+    int copy_needed;    /* route: bitmask of inputs that need an explicit copy */
+    /* convolution */
+    y2_conv_plan *plan;
+    void *wt_dev;       /* bf16 [npad][ktot] */
+    float *alpha_dev, *beta_dev;
+    int npad, block_n, block_k, cin_pad, ktot;
+    int use_patches, kpad;
+    void *patches;      /* bf16 [B][H+1][W+1][kpad] */
+    int wt_dirty;
+    /* input packing for a non-patch first layer */
+    void *packed_in;
+    /* region */
+    float *boxes_dev, *probs_dev;
+    float *biases_dev;
+    int *tree_parent_dev, *group_size_dev, *group_offset_dev, *map_dev;
+    int probs_classes;
+    /* profiling */
+    y2_event_t ev0, ev1;
+} y2_layer_rt;
+
+typedef struct y2_net_rt {
+    int device;
+    y2_stream_t stream;
+    int cap_batch;       /* batch the buffers were sized for */
+    int plan_batch;      /* batch the plans/tensor maps were built for */
+    int plan_w, plan_h;
+    float *in_dev;       /* fp32 NCHW input */
+    float *in_pinned;
+    size_t in_bytes;
+    float *out_pinned;   /* staging of the network output */
+    size_t out_bytes;
+    y2_graph_t graph;
+    int graph_valid;
+    int eager;
+    int launches;
+    int profile;
+    /* detection scratch */
+    y2_det *det_dev, *det_pinned;
+    int *cnt_dev, *cnt_pinned;
+    int det_cap, det_batch;
+    float *export_dev;   /* fp32 scratch for layer export */
+    size_t export_bytes;
+} y2_net_rt;
+
+static inline y2_net_rt *y2_rt(network net) { return (y2_net_rt *)net.b200; }
+static inline y2_layer_rt *y2_lrt(layer l) { return (y2_layer_rt *)l.b200; }
+
+/* y2_network.c */
+void y2_plan_network(network *net);
+void y2_unplan_network(network *net);
+void y2_push_convolutional_layer(layer *l);
+int y2_output_layer_index(network net);
+
+/* layer constructors (y2_layers.c) */
+layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, int stride, int padding,
+                               ACTIVATION activation, int batch_normalize, int binary, int xnor, int adam);
+layer make_maxpool_layer(int batch, int h, int w, int c, int size, int stride, int padding);
+layer make_reorg_layer(int batch, int w, int h, int c, int stride, int reverse);
+layer make_route_layer(int batch, int n, int *input_layers, int *input_sizes);
+layer make_region_layer(int batch, int w, int h, int n, int classes, int coords);
+layer make_shortcut_layer(int batch, int index, int w, int h, int c, int w2, int h2, int c2);
+layer make_avgpool_layer(int batch, int w, int h, int c);
+layer make_softmax_layer(int batch, int inputs, int groups);
+layer make_cost_layer(int batch, int inputs, COST_TYPE type, float scale);
+
+void forward_convolutional_layer_gpu(layer l, network_state state);
+void forward_maxpool_layer_gpu(layer l, network_state state);
+void forward_reorg_layer_gpu(layer l, network_state state);
+void forward_route_layer_gpu(layer l, network_state state);
+void forward_shortcut_layer_gpu(layer l, network_state state);
+void forward_avgpool_layer_gpu(layer l, network_state state);
+void forward_softmax_layer_gpu(layer l, network_state state);
+void forward_cost_layer_gpu(layer l, network_state state);
+void forward_no_cpu_path(layer l, network_state state);
+
+uint16_t y2_f32_to_bf16(float f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,277 @@
+"""Python mirror of the drop-in C API (include/darknet_b200.h), via ctypes.
+
+Same names, argument meaning and by-value struct passing as the C header, so the parity tests
+read like calls into the reference's own API:
+
+    net = dn.parse_network_cfg("yolo-voc.cfg"); dn.load_weights(net, "yolo-voc.weights")
+    out = dn.network_predict(net, images)           # numpy fp32 [B][outputs]
+    boxes, probs = dn.get_region_boxes(net, b, thresh)
+    dn.do_nms_sort(boxes, probs, nms)
+
+Everything executes in libyolo2_b200.so on the GPU; nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+class Tree(C.Structure):
+    _fields_ = [("leaf", _ip), ("n", C.c_int), ("parent", _ip), ("group", _ip),
+                ("name", C.POINTER(C.c_char_p)), ("groups", C.c_int), ("group_size", _ip),
+                ("group_offset", _ip)]
+
+
+class Box(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("w", C.c_float), ("h", C.c_float)]
+
+
+class Layer(C.Structure):
+    pass
+
+
+class NetworkState(C.Structure):
+    pass
+
+
+_FWD = C.c_void_p  # function pointers are opaque on the Python side
+
+Layer._fields_ = [
+    ("type", C.c_int), ("activation", C.c_int), ("cost_type", C.c_int),
+    ("forward", _FWD), ("forward_gpu", _FWD),
+    ("batch_normalize", C.c_int), ("batch", C.c_int), ("flipped", C.c_int),
+    ("inputs", C.c_int), ("outputs", C.c_int),
+    ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+    ("out_h", C.c_int), ("out_w", C.c_int), ("out_c", C.c_int),
+    ("n", C.c_int), ("groups", C.c_int),
+    ("size", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("reverse", C.c_int),
+    ("index", C.c_int), ("binary", C.c_int), ("xnor", C.c_int),
+    ("softmax", C.c_int), ("classes", C.c_int), ("coords", C.c_int),
+    ("max_boxes", C.c_int), ("log", C.c_int), ("sqrt", C.c_int), ("rescore", C.c_int),
+    ("bias_match", C.c_int), ("random", C.c_int), ("absolute", C.c_int), ("classfix", C.c_int),
+    ("jitter", C.c_float), ("thresh", C.c_float),
+    ("coord_scale", C.c_float), ("object_scale", C.c_float), ("noobject_scale", C.c_float),
+    ("class_scale", C.c_float), ("temperature", C.c_float), ("dot", C.c_float),
+    ("dontload", C.c_int), ("dontloadscales", C.c_int),
+    ("softmax_tree", C.POINTER(Tree)), ("map", _ip), ("cost", _fp),
+    ("biases", _fp), ("scales", _fp), ("weights", _fp), ("rolling_mean", _fp),
+    ("rolling_variance", _fp), ("input_layers", _ip), ("input_sizes", _ip),
+    ("output", _fp), ("workspace_size", C.c_size_t),
+    ("output_gpu", _fp), ("weights_gpu", _fp), ("biases_gpu", _fp), ("scales_gpu", _fp),
+    ("b200", C.c_void_p),
+]
+
+
+class Network(C.Structure):
+    _fields_ = [
+        ("workspace", _fp), ("n", C.c_int), ("batch", C.c_int), ("seen", _ip), ("epoch", C.c_float),
+        ("subdivisions", C.c_int), ("momentum", C.c_float), ("decay", C.c_float),
+        ("layers", C.POINTER(Layer)), ("outputs", C.c_int), ("output", _fp), ("policy", C.c_int),
+        ("learning_rate", C.c_float), ("gamma", C.c_float), ("scale", C.c_float), ("power", C.c_float),
+        ("time_steps", C.c_int), ("step", C.c_int), ("max_batches", C.c_int),
+        ("scales", _fp), ("steps", _ip), ("num_steps", C.c_int), ("burn_in", C.c_int),
+        ("adam", C.c_int), ("B1", C.c_float), ("B2", C.c_float), ("eps", C.c_float),
+        ("inputs", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+        ("max_crop", C.c_int), ("min_crop", C.c_int),
+        ("angle", C.c_float), ("aspect", C.c_float), ("exposure", C.c_float),
+        ("saturation", C.c_float), ("hue", C.c_float),
+        ("gpu_index", C.c_int), ("hierarchy", C.POINTER(Tree)),
+        ("input_gpu", C.POINTER(_fp)), ("truth_gpu", C.POINTER(_fp)),
+        ("b200", C.c_void_p),
+    ]
+
+
+NetworkState._fields_ = [("truth", _fp), ("input", _fp), ("delta", _fp), ("workspace", _fp),
+                         ("train", C.c_int), ("index", C.c_int), ("net", Network)]
+
+
+class Detection(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("w", C.c_float), ("h", C.c_float),
+                ("prob", C.c_float), ("obj_id", C.c_int), ("box_index", C.c_int)]
+
+
+class Image(C.Structure):
+    _fields_ = [("h", C.c_int), ("w", C.c_int), ("c", C.c_int), ("data", _fp)]
+
+
+# LAYER_TYPE values (layer.h:13-38)
+CONVOLUTIONAL, DECONVOLUTIONAL, CONNECTED, MAXPOOL, SOFTMAX, DETECTION, DROPOUT, CROP, ROUTE, COST, \
+    NORMALIZATION, AVGPOOL, LOCAL, SHORTCUT, ACTIVE, RNN, GRU, CRNN, BATCHNORM, NETWORK, XNOR, REGION, \
+    REORG, BLANK = range(24)
+
+_declared = False
+
+
+def lib() -> C.CDLL:
+    global _declared
+    l = _lib.load()
+    if _declared:
+        return l
+    fp, i, f = _fp, C.c_int, C.c_float
+    sig = {
+        "parse_network_cfg": (Network, [C.c_char_p]),
+        "load_weights": (None, [C.POINTER(Network), C.c_char_p]),
+        "load_weights_upto": (None, [C.POINTER(Network), C.c_char_p, i]),
+        "save_weights": (None, [Network, C.c_char_p]),
+        "free_network": (None, [Network]),
+        "network_predict": (fp, [Network, fp]),
+        "get_network_output": (fp, [Network]),
+        "get_network_output_layer": (fp, [Network, i]),
+        "get_network_output_size": (i, [Network]),
+        "get_network_input_size": (i, [Network]),
+        "set_batch_network": (None, [C.POINTER(Network), i]),
+        "resize_network": (i, [C.POINTER(Network), i, i]),
+        "get_region_boxes": (None, [Layer, i, i, f, C.POINTER(fp), C.POINTER(Box), i, _ip]),
+        "do_nms_sort": (None, [C.POINTER(Box), C.POINTER(fp), i, i, f]),
+        "box_iou": (f, [Box, Box]),
+        "cuda_set_device": (None, [i]),
+        "network_upload_input": (None, [Network, fp]),
+        "network_forward_device": (None, [Network]),
+        "network_detect_device": (None, [Network, f, f, C.POINTER(Detection), _ip, i]),
+        "network_detect_batch": (None, [Network, fp, f, f, C.POINTER(Detection), _ip, i]),
+        "network_sync": (None, [Network]),
+        "network_stream": (C.c_void_p, [Network]),
+        "network_conv_flops": (C.c_double, [Network]),
+        "network_launch_count": (i, [Network]),
+        "network_profile_layers": (i, [Network, fp, i]),
+        "network_set_eager": (None, [Network, i]),
+        "network_input_staging": (fp, [Network]),
+        "resize_image": (Image, [Image, i, i]),
+        "free_image": (None, [Image]),
+        "read_tree": (C.POINTER(Tree), [C.c_char_p]),
+        "max_index": (i, [fp, i]),
+        "y2_abi_sizeof": (C.c_size_t, [i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+    # the ctypes mirrors above must match the C structs exactly (by-value passing)
+    assert l.y2_abi_sizeof(0) == C.sizeof(Layer), (l.y2_abi_sizeof(0), C.sizeof(Layer))
+    assert l.y2_abi_sizeof(1) == C.sizeof(Network), (l.y2_abi_sizeof(1), C.sizeof(Network))
+    assert l.y2_abi_sizeof(2) == C.sizeof(NetworkState)
+    assert l.y2_abi_sizeof(3) == C.sizeof(Detection)
+    _declared = True
+    return l
+
+
+def _quiet_stderr():
+    """The parser prints the layer table on stderr like the reference; tests silence it."""
+    class _Ctx:
+        def __enter__(self):
+            if os.environ.get("Y2_VERBOSE"):
+                self.saved = None
+                return
+            import sys
+            sys.stderr.flush()
+            self.saved = os.dup(2)
+            self.null = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(self.null, 2)
+
+        def __exit__(self, *a):
+            if self.saved is not None:
+                os.dup2(self.saved, 2)
+                os.close(self.saved)
+                os.close(self.null)
+    return _Ctx()
+
+
+def gpu_index() -> int:
+    return C.c_int.in_dll(lib(), "gpu_index").value
+
+
+def set_gpu_index(v: int) -> None:
+    C.c_int.in_dll(lib(), "gpu_index").value = v
+
+
+def parse_network_cfg(path: str) -> Network:
+    with _quiet_stderr():
+        return lib().parse_network_cfg(str(path).encode())
+
+
+def load_weights(net: Network, path: str) -> None:
+    with _quiet_stderr():
+        lib().load_weights(C.byref(net), str(path).encode())
+
+
+def free_network(net: Network) -> None:
+    lib().free_network(net)
+
+
+def set_batch_network(net: Network, b: int) -> None:
+    lib().set_batch_network(C.byref(net), b)
+
+
+def resize_network(net: Network, w: int, h: int) -> int:
+    with _quiet_stderr():
+        return lib().resize_network(C.byref(net), w, h)
+
+
+def _as_fp(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_fp)
+
+
+def network_predict(net: Network, images: np.ndarray) -> np.ndarray:
+    """images: fp32 [B][C][H][W]; returns a copy of the borrowed output, [B][outputs]."""
+    assert images.size == net.batch * net.inputs, (images.shape, net.batch, net.inputs)
+    out = lib().network_predict(net, _as_fp(images))
+    n = lib().get_network_output_size(net)
+    return np.ctypeslib.as_array(out, shape=(net.batch, n)).copy()
+
+
+def get_network_output_layer(net: Network, i: int) -> np.ndarray:
+    out = lib().get_network_output_layer(net, i)
+    return np.ctypeslib.as_array(out, shape=(net.batch, net.layers[i].outputs)).copy()
+
+
+def region_layer(net: Network) -> Layer:
+    return net.layers[net.n - 1]
+
+
+def get_region_boxes(net: Network, b: int, thresh: float, only_objectness: int = 0, use_map: bool = False,
+                     w: int = 1, h: int = 1):
+    """get_region_boxes on batch element b (the reference reads element 0 of l.output; callers
+    advance the pointer per image, which is what this does)."""
+    l = Layer.from_buffer_copy(region_layer(net))
+    total = l.w * l.h * l.n
+    classes = 200 if use_map else l.classes
+    base = C.cast(l.output, C.c_void_p).value
+    l.output = C.cast(base + b * l.outputs * 4, _fp)
+    probs = np.zeros((total, classes), np.float32)
+    boxes = np.zeros((total, 4), np.float32)
+    rows = (_fp * total)(*[C.cast(probs.ctypes.data + j * classes * 4, _fp) for j in range(total)])
+    lib().get_region_boxes(l, w, h, thresh, rows, boxes.ctypes.data_as(C.POINTER(Box)), only_objectness,
+                           l.map if use_map else None)
+    return boxes, probs
+
+
+def do_nms_sort(boxes: np.ndarray, probs: np.ndarray, thresh: float) -> None:
+    total, classes = probs.shape
+    rows = (_fp * total)(*[C.cast(probs.ctypes.data + j * classes * 4, _fp) for j in range(total)])
+    lib().do_nms_sort(boxes.ctypes.data_as(C.POINTER(Box)), rows, total, classes, thresh)
+
+
+def network_detect_batch(net: Network, images: np.ndarray | None, thresh: float, nms: float,
+                         max_det: int = 256):
+    """Extension: batched forward + decode + NMS + pick; returns a list (per image) of
+    structured arrays with fields x,y,w,h,prob,obj_id,box_index."""
+    dets = (Detection * (net.batch * max_det))()
+    counts = (C.c_int * net.batch)()
+    if images is None:
+        lib().network_detect_device(net, thresh, nms, dets, counts, max_det)
+    else:
+        lib().network_detect_batch(net, _as_fp(images), thresh, nms, dets, counts, max_det)
+    arr = np.ctypeslib.as_array(dets)
+    out = []
+    for b in range(net.batch):
+        c = min(counts[b], max_det)
+        out.append(arr[b * max_det:b * max_det + c].copy())
+    return out, list(counts)

@@ -1,0 +1,215 @@
+"""Synthetic inputs for the benchmark and the parity tests: Darknet `.cfg` text for the
+north-star networks, seeded `.weights` files, seeded images and a WordTree.
+
+The network definitions are generated from compact specs (they describe the public
+YOLOv2 / Darknet-19 / ResNet-50 architectures; layer graphs are cross-checked against the
+reference's parser output in tests/test_oracle.py).  Nothing here touches a GPU.
+
+Weight statistics follow SURVEY.md section 8d: weights ~ U(-s, s), s = sqrt(2/(k*k*c))
+(the reference's own init scale, convolutional_layer.c:207-208), biases/means ~ U(-.1,.1),
+scales/variances ~ U(.5, 1.5) (the reference leaves rolling_variance = 0, which blows up
+without a weights file).
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+VOC_ANCHORS = "1.3221,1.73145, 3.19275,4.00944, 5.05587,8.09892, 9.47112,4.84053, 11.2364,10.0071"
+COCO_ANCHORS = "0.57273,0.677385, 1.87446,2.06253, 3.33843,5.47434, 7.88282,3.52778, 9.77052,9.16828"
+TINY_VOC_ANCHORS = "1.08,1.19, 3.42,4.41, 6.63,11.38, 9.42,5.11, 16.62,10.52"
+Y9K_ANCHORS = "0.77871,1.14074, 3.00525,4.31277, 9.22725,9.61974"
+
+
+def _net(batch, w, h, c=3):
+    return f"[net]\nbatch={batch}\nsubdivisions=1\nheight={h}\nwidth={w}\nchannels={c}\n\n"
+
+
+def _conv(filters, size, stride=1, bn=1, act="leaky", pad=1):
+    s = "[convolutional]\n"
+    if bn:
+        s += "batch_normalize=1\n"
+    return s + f"filters={filters}\nsize={size}\nstride={stride}\npad={pad}\nactivation={act}\n\n"
+
+
+def _maxpool(size=2, stride=2):
+    return f"[maxpool]\nsize={size}\nstride={stride}\n\n"
+
+
+def _region(anchors, classes, num, extra=""):
+    return (f"[region]\nanchors = {anchors}\nbias_match=1\nclasses={classes}\ncoords=4\nnum={num}\n"
+            f"softmax=1\njitter=.2\nrescore=1\nobject_scale=5\nnoobject_scale=1\nclass_scale=1\n"
+            f"coord_scale=1\nabsolute=1\nthresh = .6\nrandom=0\n{extra}\n")
+
+
+def _darknet19_trunk():
+    """Layers 0-22 of yolo-voc.cfg / yolo9000.cfg / darknet19_448.cfg."""
+    s = _conv(32, 3) + _maxpool() + _conv(64, 3) + _maxpool()
+    s += _conv(128, 3) + _conv(64, 1) + _conv(128, 3) + _maxpool()
+    s += _conv(256, 3) + _conv(128, 1) + _conv(256, 3) + _maxpool()
+    s += _conv(512, 3) + _conv(256, 1) + _conv(512, 3) + _conv(256, 1) + _conv(512, 3) + _maxpool()
+    s += _conv(1024, 3) + _conv(512, 1) + _conv(1024, 3) + _conv(512, 1) + _conv(1024, 3)
+    return s
+
+
+def tiny_yolo_voc_cfg(batch=1, w=416, h=416):
+    s = _net(batch, w, h)
+    for f in (16, 32, 64, 128, 256):
+        s += _conv(f, 3) + _maxpool()
+    s += _conv(512, 3) + _maxpool(2, 1)
+    s += _conv(1024, 3) + _conv(1024, 3) + _conv(125, 1, bn=0, act="linear")
+    return s + _region(TINY_VOC_ANCHORS, 20, 5)
+
+
+def _yolo2(batch, w, h, head, anchors, classes):
+    s = _net(batch, w, h) + _darknet19_trunk()
+    s += _conv(1024, 3) + _conv(1024, 3)
+    s += "[route]\nlayers=-9\n\n" + _conv(64, 1) + "[reorg]\nstride=2\n\n[route]\nlayers=-1,-4\n\n"
+    s += _conv(1024, 3) + _conv(head, 1, bn=0, act="linear")
+    return s + _region(anchors, classes, 5)
+
+
+def yolo_voc_cfg(batch=1, w=416, h=416):
+    return _yolo2(batch, w, h, 125, VOC_ANCHORS, 20)
+
+
+def yolo_coco_cfg(batch=1, w=608, h=608):
+    return _yolo2(batch, w, h, 425, COCO_ANCHORS, 80)
+
+
+def yolo9000_cfg(batch=1, w=544, h=544, tree="9k.tree", map_file=None, classes=9418):
+    s = _net(batch, w, h) + _darknet19_trunk()
+    s += _conv(3 * (classes + 5), 1, bn=0, act="linear")
+    extra = f"tree={tree}\n" + (f"map = {map_file}\n" if map_file else "")
+    return s + _region(Y9K_ANCHORS, classes, 3, extra)
+
+
+def darknet19_448_cfg(batch=1, w=448, h=448):
+    s = _net(batch, w, h) + _darknet19_trunk()
+    s += _conv(1000, 1, bn=0, act="linear")
+    return s + "[avgpool]\n\n[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
+
+
+def resnet50_cfg(batch=1, w=256, h=256):
+    s = _net(batch, w, h) + _conv(64, 7, stride=2) + _maxpool(2, 2)
+    for a, stride, blocks in ((64, 1, 3), (128, 2, 4), (256, 2, 6), (512, 2, 3)):
+        for b in range(blocks):
+            st = stride if b == 0 else 1
+            s += _conv(a, 1) + _conv(a, 3, stride=st) + _conv(4 * a, 1, act="linear")
+            s += "[shortcut]\nfrom=-4\nactivation=leaky\n\n"
+    s += _conv(1000, 1, bn=0, act="linear")
+    return s + "[avgpool]\n\n[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
+
+
+CFGS = {
+    "tiny-yolo-voc": tiny_yolo_voc_cfg,
+    "yolo-voc": yolo_voc_cfg,
+    "yolo": yolo_coco_cfg,
+    "yolo9000": yolo9000_cfg,
+    "darknet19_448": darknet19_448_cfg,
+    "resnet50": resnet50_cfg,
+}
+
+
+@dataclass
+class ConvSpec:
+    filters: int
+    size: int
+    channels: int
+    batch_normalize: bool
+
+
+def conv_specs_from_cfg(cfg_text: str) -> list[ConvSpec]:
+    """Walk a cfg the way parse_network_cfg does (parser.c:585-700), tracking channels only,
+    to know what a .weights file for it must contain."""
+    sections: list[tuple[str, dict]] = []
+    for raw in cfg_text.splitlines():
+        line = "".join(raw.split())
+        if not line or line[0] in "#;":
+            continue
+        if line.startswith("["):
+            sections.append((line, {}))
+        else:
+            k, _, v = line.partition("=")
+            sections[-1][1][k] = v
+    assert sections[0][0] == "[net]"
+    c = int(sections[0][1].get("channels", 3))
+    out_c: list[int] = []
+    specs: list[ConvSpec] = []
+    for idx, (name, opt) in enumerate(sections[1:]):
+        if name == "[convolutional]":
+            n = int(opt.get("filters", 1))
+            specs.append(ConvSpec(n, int(opt.get("size", 1)), c, bool(int(opt.get("batch_normalize", 0)))))
+            c = n
+        elif name == "[route]":
+            layers = [int(v) for v in opt["layers"].split(",")]
+            c = sum(out_c[(idx + l) if l < 0 else l] for l in layers)
+        elif name == "[reorg]":
+            st = int(opt.get("stride", 1))
+            c = c * st * st
+        # maxpool / shortcut / avgpool / softmax / cost / region keep or ignore c
+        out_c.append(c)
+    return specs
+
+
+def write_weights(path: str | Path, cfg_text: str, seed: int = 1234) -> int:
+    """Seeded synthetic `.weights` in the v0.1 layout read by load_weights_upto
+    (parser.c:1009-1082): int32 major, minor, revision, seen; per conv: biases, [scales,
+    rolling_mean, rolling_variance], weights[n][c][k][k]."""
+    specs = conv_specs_from_cfg(cfg_text)
+    total = 0
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiii", 0, 1, 0, 0))
+        for li, sp in enumerate(specs):
+            rng = np.random.default_rng(seed + li)
+            n, k, c = sp.filters, sp.size, sp.channels
+            biases = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+            f.write(biases.tobytes())
+            if sp.batch_normalize:
+                scales = rng.uniform(0.5, 1.5, n).astype(np.float32)
+                mean = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+                var = rng.uniform(0.5, 1.5, n).astype(np.float32)
+                f.write(scales.tobytes() + mean.tobytes() + var.tobytes())
+                total += 3 * n
+            s = np.sqrt(2.0 / (k * k * c))
+            w = rng.uniform(-s, s, n * c * k * k).astype(np.float32)
+            f.write(w.tobytes())
+            total += n + w.size
+    return total
+
+
+def images(batch: int, c: int, h: int, w: int, seed: int = 42) -> np.ndarray:
+    """U(0,1) fp32 planar CHW images, one generator per image (seed + index)."""
+    out = np.empty((batch, c, h, w), np.float32)
+    for b in range(batch):
+        out[b] = np.random.default_rng(seed + b).random((c, h, w), dtype=np.float32)
+    return out
+
+
+def write_tree(path: str | Path, n: int = 9418, fanout: int = 5, roots: int = 4) -> None:
+    """A well-formed WordTree in the `name parent` format of read_tree (tree.c:53-103):
+    `roots` top-level nodes, then parent = (i - roots) // fanout, so the children of a node
+    are contiguous and every parent precedes its children.  (cfg/9k.tree in the reference is
+    corrupt - SURVEY.md section 8c.)"""
+    with open(path, "w") as f:
+        for i in range(n):
+            parent = -1 if i < roots else (i - roots) // fanout
+            f.write(f"n{i:08d} {parent}\n")
+
+
+def region_inputs(batch: int, n: int, classes: int, h: int, w: int, seed: int = 7,
+                  hot_fraction: float = 0.05) -> np.ndarray:
+    """Seeded region-layer inputs [B][n*(5+classes)][h][w] (the conv output layout) with
+    objectness/class logits boosted on ~5% of boxes so that the keep set is non-trivial."""
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((batch, n, 5 + classes, h, w)) * 2).astype(np.float32)
+    hot = rng.random((batch, n, h, w)) < hot_fraction
+    x[:, :, 4][hot] += 6.0
+    x[:, :, 4][~hot] -= 3.0
+    cls = rng.integers(0, classes, (batch, n, h, w))
+    bi, ni, hi, wi = np.nonzero(hot)
+    x[bi, ni, 5 + cls[bi, ni, hi, wi], hi, wi] += 8.0
+    return x.reshape(batch, n * (5 + classes), h, w)

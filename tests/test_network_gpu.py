@@ -1,0 +1,122 @@
+"""End-to-end GPU parity: the drop-in C API (parse_network_cfg / load_weights / network_predict /
+get_region_boxes / do_nms_sort) on the B200 against the reference's own CPU implementation
+(oracle/_ref/darknet_ref, compiled from the reference sources) on the same seeded synthetic
+weights and images.
+
+Tolerances (north star): layer activations max|a-b| / max|b| <= 1e-2 (bf16 operands, fp32
+accumulate); box indices and the post-NMS keep set bit-exact on identical region inputs.
+"""
+import numpy as np
+import pytest
+
+from sr_object_detection_b200 import darknet as dn
+from sr_object_detection_b200 import synth
+from tests import ref_util as R
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-2
+
+
+def _setup(tmp_path, name, batch, w=416, h=416, **kw):
+    cfg_text = synth.CFGS[name](batch=batch, w=w, h=h, **kw)
+    cfg = tmp_path / f"{name}.cfg"
+    cfg.write_text(cfg_text)
+    weights = tmp_path / f"{name}.weights"
+    synth.write_weights(weights, cfg_text, seed=1234)
+    x = synth.images(batch, 3, h, w, seed=42)
+    inp = tmp_path / "input.f32"
+    x.tofile(inp)
+    return cfg, weights, x, inp
+
+
+@pytest.mark.parametrize("name,batch", [("tiny-yolo-voc", 2), ("yolo-voc", 2)])
+def test_layer_activations_match_reference(tmp_path, name, batch):
+    if not R.have_ref():
+        pytest.skip("oracle/_ref/darknet_ref not built")
+    cfg, weights, x, inp = _setup(tmp_path, name, batch)
+    ref_dir = tmp_path / "ref"
+    R.forward(R.REF_BIN, cfg, weights, inp, ref_dir, thresh=0.24, nms=0.4)
+
+    dn.set_gpu_index(0)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    out = dn.network_predict(net, x)
+    worst = (0.0, -1)
+    for i in range(net.n):
+        l = net.layers[i]
+        if l.type == dn.COST:
+            continue
+        ref = R.load(ref_dir, "layer_%03d.f32" % i, (batch, l.outputs))
+        got = dn.get_network_output_layer(net, i)
+        err = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+        worst = max(worst, (err, i))
+        assert err <= ACT_TOL, f"{name} layer {i} (type {l.type}): max err / max|ref| = {err:.3e}"
+    ref_out = R.load(ref_dir, "output.f32", out.shape)
+    err = float(np.abs(out - ref_out).max() / np.abs(ref_out).max())
+    assert err <= ACT_TOL, f"network output err {err:.3e}"
+    print(f"{name}: worst layer error {worst[0]:.3e} at layer {worst[1]}, output err {err:.3e}")
+    dn.free_network(net)
+
+
+@pytest.mark.parametrize("name,classes,n,side,thresh,nms", [
+    ("yolo-voc", 20, 5, 13, 0.24, 0.4),
+    ("yolo-voc", 20, 5, 13, 0.005, 0.45),
+    ("yolo", 80, 5, 19, 0.24, 0.4),
+])
+def test_decode_and_nms_bit_exact_on_identical_region_inputs(tmp_path, name, classes, n, side, thresh, nms):
+    """Region forward + get_region_boxes + do_nms_sort: device kernels vs the reference's C code
+    on the SAME region-layer input tensor."""
+    if not R.have_ref():
+        pytest.skip("oracle/_ref/darknet_ref not built")
+    import ctypes as C
+    import torch
+    from sr_object_detection_b200 import _lib
+    batch = 3
+    wh = side * 32
+    cfg_text = synth.CFGS[name](batch=batch, w=wh, h=wh)
+    cfg = tmp_path / "net.cfg"
+    cfg.write_text(cfg_text)
+    x = synth.region_inputs(batch, n, classes, side, side, seed=11)
+    rin = tmp_path / "region_in.f32"
+    x.tofile(rin)
+    ref_dir = tmp_path / "ref"
+    R.region(R.REF_BIN, cfg, rin, ref_dir, thresh=thresh, nms=nms)
+    total = side * side * n
+    size = classes + 5
+    ref_out = R.load(ref_dir, "region_out.f32", (batch, total, size))
+    ref_boxes = R.load(ref_dir, "boxes.f32", (batch, total, 4))
+    ref_pre = R.load(ref_dir, "probs_pre.f32", (batch, total, classes))
+    ref_post = R.load(ref_dir, "probs_post.f32", (batch, total, classes))
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    xin = torch.from_numpy(x).to(dev)
+    flat = torch.empty(batch, side * side, n * size, device=dev)
+    _lib.check(lib.y2_nchw_to_flat_f32(xin.data_ptr(), flat.data_ptr(), batch, n * size, side * side, st))
+    out = torch.empty_like(flat)
+    _lib.check(lib.y2_region_forward(flat.data_ptr(), out.data_ptr(), batch, side * side, n, classes, 1, 0,
+                                     None, None, st))
+    anchors = [float(v) for v in (synth.VOC_ANCHORS if classes == 20 else synth.COCO_ANCHORS).split(",")]
+    biases = torch.tensor(anchors, device=dev)
+    boxes = torch.empty(batch, total, 4, device=dev)
+    probs = torch.empty(batch, total, classes, device=dev)
+    _lib.check(lib.y2_region_boxes(out.data_ptr(), biases.data_ptr(), boxes.data_ptr(), probs.data_ptr(), batch,
+                                   side, side, n, classes, 1.0, 1.0, thresh, 0, 0, 0, None, None, 0, st))
+    pre = probs.clone()
+    _lib.check(lib.y2_nms_sort(boxes.data_ptr(), probs.data_ptr(), batch, total, classes, nms, st))
+    torch.cuda.synchronize()
+    got_out = out.view(batch, total, size).cpu().numpy()
+    got_boxes = boxes.cpu().numpy()
+    got_pre = pre.cpu().numpy()
+    got_post = probs.cpu().numpy()
+    # values: identical expressions, double exp on both sides -> expect bit equality
+    assert np.array_equal(got_out, ref_out), f"region output differs in {(got_out != ref_out).sum()} values"
+    assert np.array_equal(got_boxes, ref_boxes), f"boxes differ in {(got_boxes != ref_boxes).sum()} values"
+    assert np.array_equal(got_pre, ref_pre)
+    # the keep set, and the kept values
+    assert np.array_equal(got_post != 0, ref_post != 0), \
+        f"keep set differs in {((got_post != 0) != (ref_post != 0)).sum()} entries"
+    assert np.array_equal(got_post, ref_post)
+    assert (ref_pre != 0).sum() > (ref_post != 0).sum() > 0  # the case actually suppresses something
