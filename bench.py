@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Headline benchmark: YOLOv2-416 (yolo-voc.cfg) images/sec, batch 64 per GPU, on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+A step = one pass of the hot path over one batch of synthetic images: forward (23 tcgen05
+convolutions, 5 maxpools, reorg, in-place routes, region layer) + get_region_boxes + do_nms_sort +
+final pick.  `value` is measured with the batch resident in HBM, `e2e` through the public C API
+with host buffers (pinned H2D of the images and D2H of the detection lists inside the timed
+region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = "yolo-voc.cfg 416x416 batch 64 per GPU, forward + region decode + NMS"
+CFG_NAME = "yolo-voc"
+BATCH = 64
+SIDE = 416
+THRESH = 0.24   # detector.c:602 default -thresh
+NMS = 0.4       # detector.c:456 / yolo_v2_class.hpp:45
+MAX_DET = 256
+SEED_W, SEED_X = 1234, 42
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "tflops_burst": d["bf16_tflops"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for line in Path(self.path).read_text().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the power range
+        thr = (max(power) + min(power)) / 2
+        load = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _write_inputs(tmp: Path, batch: int):
+    from sr_object_detection_b200 import synth
+    cfg_text = synth.CFGS[CFG_NAME](batch=batch, w=SIDE, h=SIDE)
+    cfg = tmp / f"{CFG_NAME}_b{batch}.cfg"
+    cfg.write_text(cfg_text)
+    weights = tmp / f"{CFG_NAME}.weights"
+    if not weights.exists():
+        synth.write_weights(weights, cfg_text, seed=SEED_W)
+    return cfg, weights
+
+
+def cpu_baseline(tmp: Path, iters: int = 3, warmup: int = 1) -> dict:
+    """The reference's own CPU path (oracle/_ref, compiled from the reference sources) on the
+    host cores, bounded sample of the same workload: batch-1 forward + decode + NMS."""
+    from sr_object_detection_b200 import synth
+    ref = ROOT / "oracle" / "_ref" / "darknet_ref"
+    kind = "reference"
+    if not ref.exists():
+        ref = ROOT / "oracle" / "_build" / "y2_oracle"
+        kind = "port"
+    if not ref.exists():
+        return {"value": None, "unit": "images/s", "cores": 0, "kind": "unavailable",
+                "sample": "oracle binaries not built (run __graft_entry__.build())"}
+    cfg, weights = _write_inputs(tmp, 1)
+    inp = tmp / "cpu_input.f32"
+    synth.images(1, 3, SIDE, SIDE, seed=SEED_X).tofile(inp)
+    r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS), str(warmup),
+                        str(iters)], capture_output=True, text=True)
+    if r.returncode != 0:
+        return {"value": None, "unit": "images/s", "cores": 0, "kind": kind, "sample": "failed: " + r.stderr[-200:]}
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"value": round(d["images_per_s"], 4), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{iters} x batch-1 {CFG_NAME} {SIDE}x{SIDE} forward+decode+NMS after {warmup} warm-up, "
+                      f"OpenMP over all host threads ({d['seconds']:.1f} s)"}
+
+
+def run_reference(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    with tempfile.TemporaryDirectory(prefix="y2bench_") as t:
+        tmp = Path(t)
+        from sr_object_detection_b200 import synth
+        ref = ROOT / "oracle" / "_ref" / "darknet_ref"
+        kind = "reference"
+        if not ref.exists():
+            ref = ROOT / "oracle" / "_build" / "y2_oracle"
+            kind = "port"
+        cfg, weights = _write_inputs(tmp, 1)
+        inp = tmp / "cpu_input.f32"
+        synth.images(1, 3, SIDE, SIDE, seed=SEED_X).tofile(inp)
+        r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS),
+                            str(args.warmup), str(args.steps)], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-160:]}))
+            return 0
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        ips = d["images_per_s"]
+        line = {
+            "impl": "reference", "metric": "images/sec", "value": round(ips, 4), "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1000.0 * d["seconds"] / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "one image per step (batch 1), host CPU"},
+            "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+                             "sample": f"{args.steps} steps x 1 image, forward+decode+NMS"},
+            "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-layer timing table (json) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+
+    from sr_object_detection_b200 import _lib, synth
+    from sr_object_detection_b200 import darknet as dn
+
+    lib = dn.lib()
+    B = args.batch
+    tmpdir = tempfile.TemporaryDirectory(prefix=f"y2bench_r{rank}_")
+    tmp = Path(tmpdir.name)
+    cfg, weights = _write_inputs(tmp, B)
+    dn.set_gpu_index(local_rank)
+    lib.cuda_set_device(local_rank)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    images = synth.images(B, 3, SIDE, SIDE, seed=SEED_X + rank * B)
+    stream = C.c_void_p(lib.network_stream(net))
+
+    # stage the batch once in the pinned buffer; `value` keeps it resident in HBM
+    staging = lib.network_input_staging(net)
+    C.memmove(staging, images.ctypes.data, images.nbytes)
+    lib.network_upload_input(net, staging)
+    dets = (dn.Detection * (B * MAX_DET))()
+    counts = (C.c_int * B)()
+
+    def step_device():
+        lib.network_forward_device(net)
+        lib.network_detect_device(net, THRESH, NMS, dets, counts, MAX_DET)
+
+    def step_e2e():
+        lib.network_detect_batch(net, staging, THRESH, NMS, dets, counts, MAX_DET)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    ev = [C.c_void_p() for _ in range(2)]
+    for e in ev:
+        _lib.check(lib.y2_event_create(C.byref(e)))
+
+    def timed(fn, steps):
+        barrier()
+        _lib.check(lib.y2_event_record(ev[0], stream))
+        for _ in range(steps):
+            fn()
+        _lib.check(lib.y2_event_record(ev[1], stream))
+        torch.cuda.synchronize()
+        ms = C.c_float()
+        _lib.check(lib.y2_event_elapsed_ms(ev[0], ev[1], C.byref(ms)))
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms.value], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            return float(t.item())
+        return ms.value
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    launches_fwd = lib.network_launch_count(net)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-layer device times (eager pass with CUDA events on the network stream), for the
+    # roofline of the dominant kernel: the tcgen05 convolution
+    n_layers = net.n
+    layer_ms = np.zeros(n_layers, np.float32)
+    prof_steps = max(3, min(args.steps, 10))
+    buf = (C.c_float * n_layers)()
+    for _ in range(prof_steps):
+        lib.network_profile_layers(net, buf, n_layers)
+        layer_ms += np.ctypeslib.as_array(buf)
+    layer_ms /= prof_steps
+    conv_ms = 0.0
+    conv_launches = 0
+    table = []
+    flops_img = lib.network_conv_flops(net)
+    for i in range(n_layers):
+        l = net.layers[i]
+        fl = 2.0 * l.n * l.size * l.size * l.c * l.out_h * l.out_w * B if l.type == dn.CONVOLUTIONAL else 0.0
+        if l.type == dn.CONVOLUTIONAL:
+            conv_ms += float(layer_ms[i])
+            conv_launches += 1
+        table.append({"layer": i, "type": int(l.type), "ms": round(float(layer_ms[i]), 4),
+                      "tflops": round(float(fl / (float(layer_ms[i]) * 1e9)), 1) if fl and layer_ms[i] > 0 else None})
+
+    total_images = B * world * args.steps
+    value = total_images / (ms_dev / 1000.0)
+    e2e_value = total_images / (ms_e2e / 1000.0)
+    peaks = _peaks()
+    step_flops = flops_img * B
+    achieved_tf = step_flops / (conv_ms * 1e9) if conv_ms > 0 else 0.0
+    detect_launches = 6  # region_boxes, nms memset+count+mark+clear, collect
+    line = {
+        "metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cfg": "yolo-voc (YOLOv2-VOC)", "batch_per_gpu": B,
+                   "global_batch": B * world, "input": f"{SIDE}x{SIDE}x3 fp32", "parallelism": f"dp{world}",
+                   "thresh": THRESH, "nms": NMS,
+                   "l2": "inputs larger than L2 (133 MB fp32 batch, 2.5 GB activations per step)",
+                   "weights": "random-init synthetic .weights (seed 1234)", "schedule": "CUDA graph replay",
+                   "algorithmic_gflop_per_image": round(flops_img / 1e9, 3)},
+        "model_tflops": round(value / world * flops_img / 1e12, 1),
+        "model_frac_of_peak": round(value / world * flops_img / 1e12 / peaks["tflops"], 4),
+        "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel (23 launches per step)",
+                     "achieved": round(achieved_tf, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": round(achieved_tf / peaks["tflops"], 4), "peak_burst": peaks["tflops_burst"],
+                     "peak_source": peaks["source"], "traffic": None,
+                     "conv_ms_per_step": round(conv_ms, 4), "step_ms_eager": round(float(layer_ms.sum()), 4)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                "h2d_bytes_per_step": int(images.nbytes),
+                "d2h_bytes_per_step": int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4),
+                "api": "network_detect_batch(net, host_images, thresh, nms, dets, counts, max_det)"},
+        "gpu_launches": int((launches_fwd + detect_launches) * args.steps),
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(tmp)
+        print(json.dumps(line))
+        sys.stdout.flush()
+        if args.profile_out:
+            Path(args.profile_out).write_text(json.dumps({"batch": B, "layers": table, "line": line}, indent=1))
+    dn.free_network(net)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -202,14 +202,20 @@ def write_tree(path: str | Path, n: int = 9418, fanout: int = 5, roots: int = 4)
 
 def region_inputs(batch: int, n: int, classes: int, h: int, w: int, seed: int = 7,
                   hot_fraction: float = 0.05) -> np.ndarray:
-    """Seeded region-layer inputs [B][n*(5+classes)][h][w] (the conv output layout) with
-    objectness/class logits boosted on ~5% of boxes so that the keep set is non-trivial."""
+    """Seeded region-layer inputs [B][n*(5+classes)][h][w] (the conv output layout).  About
+    `hot_fraction` of the cells are "objects": all anchors of such a cell (and of its right
+    neighbour) get a boosted objectness and the same boosted class, so that several strongly
+    overlapping boxes compete in NMS and the keep set is non-trivial."""
     rng = np.random.default_rng(seed)
     x = (rng.standard_normal((batch, n, 5 + classes, h, w)) * 2).astype(np.float32)
-    hot = rng.random((batch, n, h, w)) < hot_fraction
-    x[:, :, 4][hot] += 6.0
-    x[:, :, 4][~hot] -= 3.0
-    cls = rng.integers(0, classes, (batch, n, h, w))
-    bi, ni, hi, wi = np.nonzero(hot)
-    x[bi, ni, 5 + cls[bi, ni, hi, wi], hi, wi] += 8.0
+    x[:, :, 4] -= 3.0
+    x[:, :, 2:4] *= 0.25  # keep exp(tw), exp(th) moderate so neighbouring boxes overlap
+    hot = rng.random((batch, h, w)) < hot_fraction
+    cls = rng.integers(0, classes, (batch, h, w))
+    bi, hi, wi = np.nonzero(hot)
+    for dx in (0, 1):
+        wj = np.minimum(wi + dx, w - 1)
+        for a in range(n):
+            x[bi, a, 4, hi, wj] += 6.0 + rng.random(len(bi)).astype(np.float32)
+            x[bi, a, 5 + cls[bi, hi, wi], hi, wj] += 8.0
     return x.reshape(batch, n * (5 + classes), h, w)
