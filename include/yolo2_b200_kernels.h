@@ -189,9 +189,12 @@ int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int c
                     y2_stream_t s);
 int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp,
                     y2_stream_t s);
-int y2_shortcut(const void *add, int add_cs, int add_c, int add_h, int add_w,
-                void *out, int out_cs, int out_c, int out_h, int out_w, int batch,
-                int act, y2_stream_t s);
+/* shortcut (replaces shortcut_layer.c:54-59 copy_ongpu + shortcut_gpu (blas_kernels.cu:618-651)
+ * + activate_array_ongpu): out = act(in + add sampled per blas.c:57-81).  in/out: bf16 padded
+ * NHWC of extent out_h x out_w, out_cpad stored channels (out_c real); add: the `from` layer. */
+int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_c, int add_h,
+                int add_w, void *out, int out_cs, int out_c, int out_cpad, int out_h, int out_w,
+                int batch, int act, y2_stream_t s);
 
 /* library identity, for the loader tests */
 const char *y2_version(void);

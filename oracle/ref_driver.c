@@ -13,6 +13,10 @@
  *   darknet_ref region  <cfg> <region_in.f32> <outdir> <thresh> <nms>
  *   darknet_ref time    <cfg> <weights> <input.f32> <thresh> <nms> <warmup> <iters>
  *   darknet_ref resize  <in.f32> <c> <h> <w> <out_h> <out_w> <out.f32>
+ *   darknet_ref layers  <cfg>                     (layer table as JSON, parser parity)
+ *
+ * Environment: Y2_USE_MAP=1 passes the region layer's `map` to get_region_boxes (the 200-class
+ * branch of region_layer.c:352-356, as validate_detector does, detector.c:344-347).
  *
  * <cfg> must carry batch=B subdivisions=1 (set_batch_network does not reallocate,
  * network.c:308-320); <input.f32> is raw float32 [B][C][H][W].
@@ -67,7 +71,7 @@ static void decode_and_nms(network net, const char *outdir, float thresh, float 
     layer l = net.layers[net.n - 1];
     if (l.type != REGION) return;
     int total = l.w * l.h * l.n, b, j;
-    int *map = 0;
+    int *map = (getenv("Y2_USE_MAP") && atoi(getenv("Y2_USE_MAP"))) ? l.map : 0;
     box *boxes = calloc(total, sizeof(box));
     float **probs = calloc(total, sizeof(float *));
     for (j = 0; j < total; ++j) probs[j] = calloc(l.classes, sizeof(float));
@@ -180,6 +184,23 @@ static int cmd_resize(int argc, char **argv)
     return 0;
 }
 
+static int cmd_layers(int argc, char **argv)
+{
+    if (argc < 3) return 1;
+    network net = parse_network_cfg(argv[2]);
+    int i;
+    printf("{\"batch\": %d, \"w\": %d, \"h\": %d, \"c\": %d, \"layers\": [", net.batch, net.w, net.h, net.c);
+    for (i = 0; i < net.n; ++i) {
+        layer l = net.layers[i];
+        printf("%s{\"type\": %d, \"w\": %d, \"h\": %d, \"c\": %d, \"out_w\": %d, \"out_h\": %d, \"out_c\": %d, "
+               "\"outputs\": %d, \"n\": %d, \"size\": %d, \"stride\": %d, \"pad\": %d}",
+               i ? ", " : "", (int)l.type, l.w, l.h, l.c, l.out_w, l.out_h, l.out_c, l.outputs, l.n, l.size,
+               l.stride, l.pad);
+    }
+    printf("]}\n");
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     gpu_index = -1;
@@ -188,6 +209,7 @@ int main(int argc, char **argv)
     if (!strcmp(argv[1], "region")) return cmd_region(argc, argv);
     if (!strcmp(argv[1], "time")) return cmd_time(argc, argv);
     if (!strcmp(argv[1], "resize")) return cmd_resize(argc, argv);
+    if (!strcmp(argv[1], "layers")) return cmd_layers(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 1;
 }

@@ -104,6 +104,7 @@ def _declare(lib: C.CDLL) -> None:
         "y2_collect": (i, [vp, vp, i, i, i, f, vp, vp, i, vp]),
         "y2_avgpool_flat": (i, [vp, vp, i, i, i, i, vp]),
         "y2_softmax_rows": (i, [vp, vp, i, i, f, vp]),
+        "y2_shortcut": (i, [vp, i, vp, i, i, i, i, vp, i, i, i, i, i, i, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name, None)

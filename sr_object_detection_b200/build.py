@@ -83,7 +83,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         o = OBJ / (src.stem + ".cpp.o")
         _run(["g++", *CXX_FLAGS, "-c", src, "-o", o], verbose)
         objs.append(o)
-    _run([NVCC, *GENCODE, "-shared", "-o", LIB, *objs, "-lcudart", "-lm", "-lpthread", "-lstdc++"], verbose)
+    # -Bsymbolic-functions: the drop-in API keeps the reference's unprefixed names (error, strip,
+    # free_list ...); calls between our own functions must not be interposed by a same-named
+    # symbol of the host process (glibc exports error(3)).
+    _run([NVCC, *GENCODE, "-shared", "-Xlinker", "-Bsymbolic-functions", "-o", LIB, *objs, "-lcudart", "-lm",
+          "-lpthread", "-lstdc++"], verbose)
     stamp.write_text(digest)
     return LIB
 

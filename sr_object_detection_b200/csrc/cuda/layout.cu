@@ -253,9 +253,84 @@ __global__ void copy_channels_kernel(const __nv_bfloat16 *__restrict__ in, int i
     }
 }
 
+// ---------------------------------------------------------------------------------
+// shortcut: out = act(in + add sampled), the fused form of shortcut_layer.c:39-44
+// (copy_cpu + shortcut_cpu + activate_array) with the index map of blas.c:57-81:
+//   out[b, j*sample, i*sample, k] += add[b, j*stride, i*stride, k]   for k < min(c1, c2),
+//   j < min(h1, h2), i < min(w1, w2), stride = w1/w2, sample = w2/w1 (each at least 1).
+// One thread per (output position, 8-channel group), 16-byte accesses.
+// ---------------------------------------------------------------------------------
+__global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
+                                const __nv_bfloat16 *__restrict__ add, int add_cs, int add_c, int add_h,
+                                int add_w, __nv_bfloat16 *__restrict__ out, int out_cs, int c8, int out_c,
+                                int out_h, int out_w, int batch, int act)
+{
+    const int ohp = out_h + 1, owp = out_w + 1, ahp = add_h + 1, awp = add_w + 1;
+    int stride = add_w / out_w, sample = out_w / add_w;
+    if (stride < 1) stride = 1;
+    if (sample < 1) sample = 1;
+    const int minw = add_w < out_w ? add_w : out_w, minh = add_h < out_h ? add_h : out_h;
+    const int minc = add_c < out_c ? add_c : out_c;
+    const long long total = (long long)batch * ohp * owp * c8;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % c8);
+        const long long p = t / c8;
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        uint4 res = make_uint4(0u, 0u, 0u, 0u);
+        if (ox < out_w && oy < out_h) {
+            const uint4 vi = __ldg(reinterpret_cast<const uint4 *>(in + (size_t)p * in_cs + g * 8));
+            const __nv_bfloat16 *hi = reinterpret_cast<const __nv_bfloat16 *>(&vi);
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __bfloat162float(hi[q]);
+            const int i = ox / sample, j = oy / sample;
+            if (ox % sample == 0 && oy % sample == 0 && i < minw && j < minh && g * 8 < minc) {
+                const uint4 va = __ldg(reinterpret_cast<const uint4 *>(
+                    add + (((size_t)b * ahp + (size_t)j * stride) * awp + (size_t)i * stride) * add_cs + g * 8));
+                const __nv_bfloat16 *ha = reinterpret_cast<const __nv_bfloat16 *>(&va);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (g * 8 + q < minc) f[q] += __bfloat162float(ha[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (act == Y2_ACT_LEAKY) f[q] = (f[q] > 0.f) ? f[q] : 0.1f * f[q];
+                else if (act == Y2_ACT_LOGISTIC) f[q] = 1.f / (1.f + __expf(-f[q]));
+                if (g * 8 + q >= out_c) f[q] = 0.f;
+            }
+            res.x = pack_bf16x2(f[0], f[1]);
+            res.y = pack_bf16x2(f[2], f[3]);
+            res.z = pack_bf16x2(f[4], f[5]);
+            res.w = pack_bf16x2(f[6], f[7]);
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) = res;
+    }
+}
+
 } // namespace y2
 
 using namespace y2;
+
+extern "C" int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_c, int add_h,
+                           int add_w, void *out, int out_cs, int out_c, int out_cpad, int out_h, int out_w,
+                           int batch, int act, y2_stream_t s)
+{
+    if (!in || !add || !out || out_cpad % 8 || in_cs % 8 || add_cs % 8 || out_cs % 8 || out_c > out_cpad ||
+        add_h <= 0 || add_w <= 0 || out_h <= 0 || out_w <= 0) {
+        set_error("y2_shortcut: invalid arguments (out_cpad=%d in_cs=%d add_cs=%d out_cs=%d)", out_cpad, in_cs,
+                  add_cs, out_cs);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (out_h + 1) * (out_w + 1) * (out_cpad / 8);
+    shortcut_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, in_cs, (const __nv_bfloat16 *)add, add_cs, add_c, add_h, add_w,
+        (__nv_bfloat16 *)out, out_cs, out_cpad / 8, out_c, out_h, out_w, batch, act);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
 
 extern "C" int y2_pack_nchw_f32(const float *src, void *dst, int batch, int c, int h, int w, int cpad,
                                 int cs, y2_stream_t s)

@@ -274,9 +274,7 @@ layer make_region_layer(int batch, int w, int h, int n, int classes, int coords)
     l.n = n;
     l.batch = batch;
     l.h = h;
-    l.w = w;
-    l.out_h = h;
-    l.out_w = w;
+    l.w = w; /* out_h / out_w stay 0, as region_layer.c:14-51 leaves them */
     l.classes = classes;
     l.coords = coords;
     l.cost = (float *)calloc(1, sizeof(float));
@@ -694,6 +692,17 @@ void y2_plan_network(network *net)
             }
             break;
         }
+        case SHORTCUT: {
+            y2_layer_rt *pr = i ? (y2_layer_rt *)net->layers[i - 1].b200 : 0;
+            y2_layer_rt *fr = (y2_layer_rt *)net->layers[l->index].b200;
+            if (!pr || pr->out_kind != Y2_KIND_BF16_PADDED || !fr || fr->out_kind != Y2_KIND_BF16_PADDED)
+                unsupported(i, "shortcut between non-tensor layers");
+            if (l->activation != LEAKY && l->activation != LINEAR && l->activation != LOGISTIC)
+                unsupported(i, "activation other than leaky/linear/logistic");
+            r->out_kind = Y2_KIND_BF16_PADDED;
+            r->cpad = pr->cpad;
+            break;
+        }
         case ROUTE: {
             r->out_kind = Y2_KIND_BF16_PADDED;
             int total = 0;
@@ -787,7 +796,8 @@ void y2_plan_network(network *net)
             r->own_bytes = padded_bytes(B, l->out_h, l->out_w, r->cpad);
             r->out_cs = r->cpad;
         } else if (r->out_kind == Y2_KIND_F32_FLAT) {
-            r->own_bytes = (size_t)B * l->out_h * l->out_w * r->cpad * sizeof(float);
+            const int oh = l->type == REGION ? l->h : l->out_h, ow = l->type == REGION ? l->w : l->out_w;
+            r->own_bytes = (size_t)B * oh * ow * r->cpad * sizeof(float);
             r->out_cs = r->cpad;
         } else {
             r->own_bytes = (size_t)B * r->cpad * sizeof(float);
@@ -946,9 +956,14 @@ void forward_softmax_layer_gpu(layer l, network_state state)
 
 void forward_shortcut_layer_gpu(layer l, network_state state)
 {
-    (void)l;
-    (void)state;
-    error("shortcut layers are not part of this round's hot path");
+    y2_layer_rt *r = y2_lrt(l);
+    y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
+    y2_layer_rt *fr = y2_lrt(state.net.layers[l.index]);
+    const int act = (l.activation == LEAKY) ? Y2_ACT_LEAKY : (l.activation == LOGISTIC) ? Y2_ACT_LOGISTIC : Y2_ACT_LINEAR;
+    /* (l.w, l.h, l.c) describe the `from` tensor, out_* the running one (shortcut_layer.c:7-34) */
+    Y2_CHECK(y2_shortcut(pr->out, pr->out_cs, fr->out, fr->out_cs, l.c, l.h, l.w, r->out, r->out_cs, l.out_c,
+                         r->cpad, l.out_h, l.out_w, l.batch, act, net_stream(state.net)));
+    count_launch(state.net, 1);
 }
 
 void forward_cost_layer_gpu(layer l, network_state state)
@@ -1216,8 +1231,6 @@ int resize_network(network *net, int w, int h)
         case REGION:
             l->w = w;
             l->h = h;
-            l->out_w = w;
-            l->out_h = h;
             l->outputs = h * w * l->n * (l->classes + l->coords + 1);
             l->inputs = l->outputs;
             break;
@@ -1236,9 +1249,6 @@ int resize_network(network *net, int w, int h)
                 else l->out_h = l->out_w = l->out_c = 0;
             }
             l->inputs = l->outputs;
-            l->w = l->out_w;
-            l->h = l->out_h;
-            l->c = l->out_c;
             break;
         }
         case REORG:

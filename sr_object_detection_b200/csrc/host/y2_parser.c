@@ -239,10 +239,7 @@ static layer parse_route(list *options, size_params params, network net)
         if (next.out_w == first.out_w && next.out_h == first.out_h) r.out_c += next.out_c;
         else r.out_h = r.out_w = r.out_c = 0;
     }
-    r.h = r.out_h;
-    r.w = r.out_w;
-    r.c = r.out_c;
-    return r;
+    return r; /* w/h/c stay 0 like the reference's route layer (route_layer.c:6-37) */
 }
 
 static layer parse_region(list *options, size_params params)

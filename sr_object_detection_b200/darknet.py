@@ -275,3 +275,94 @@ def network_detect_batch(net: Network, images: np.ndarray | None, thresh: float,
         c = min(counts[b], max_det)
         out.append(arr[b * max_det:b * max_det + c].copy())
     return out, list(counts)
+
+
+class _DevBuf:
+    """Device allocation through the kernel C-ABI (y2_malloc / y2_memcpy_*), freed on exit."""
+
+    def __init__(self, nbytes: int, host: np.ndarray | None = None):
+        self.lib = _lib.load()
+        self.ptr = C.c_void_p()
+        self.nbytes = int(nbytes)
+        _lib.check(self.lib.y2_malloc(C.byref(self.ptr), max(self.nbytes, 16)), "y2_malloc")
+        if host is not None:
+            host = np.ascontiguousarray(host)
+            _lib.check(self.lib.y2_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, None), "h2d")
+            _lib.check(self.lib.y2_stream_sync(None))
+
+    def get(self, dtype, shape) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        _lib.check(self.lib.y2_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes, None), "d2h")
+        _lib.check(self.lib.y2_stream_sync(None))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.lib.y2_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def decode_region_input(net: Network, region_in: np.ndarray, thresh: float, nms: float, use_map: bool = False) -> dict:
+    """Run the region layer + get_region_boxes + do_nms_sort kernels on a given region-layer INPUT
+    (fp32 [B][n*(5+classes)][h][w], the conv-head layout of the reference) for every image, through
+    the kernel C-ABI with the region layer's own parameters (anchors, tree, map).  Returns the
+    arrays the oracle drivers dump: region_out, boxes, probs_pre, probs_post, region_after_boxes.
+    Used by the parity tests to feed both sides identical region inputs."""
+    lib = _lib.load()
+    l = region_layer(net)
+    assert l.type == REGION
+    B = region_in.shape[0]
+    hw, n, classes = l.w * l.h, l.n, l.classes
+    size = classes + 5
+    total = hw * n
+    assert region_in.size == B * total * size
+    bufs = []
+
+    def dev(nbytes, host=None):
+        b = _DevBuf(nbytes, host)
+        bufs.append(b)
+        return b
+
+    try:
+        xin = dev(region_in.nbytes, region_in.astype(np.float32))
+        flat = dev(region_in.nbytes)
+        out = dev(region_in.nbytes)
+        biases = dev(n * 2 * 4, np.ctypeslib.as_array(l.biases, (n * 2,)).astype(np.float32))
+        _lib.check(lib.y2_nchw_to_flat_f32(xin.ptr, flat.ptr, B, n * size, hw, None), "nchw_to_flat")
+        groups, gs, go, parent, tree_n = 0, None, None, None, 0
+        if l.softmax_tree:
+            t = l.softmax_tree.contents
+            groups, tree_n = t.groups, t.n
+            gs = dev(groups * 4, np.ctypeslib.as_array(t.group_size, (groups,)).astype(np.int32)).ptr
+            go = dev(groups * 4, np.ctypeslib.as_array(t.group_offset, (groups,)).astype(np.int32)).ptr
+            parent = dev(t.n * 4, np.ctypeslib.as_array(t.parent, (t.n,)).astype(np.int32)).ptr
+        _lib.check(lib.y2_region_forward(flat.ptr, out.ptr, B, hw, n, classes, int(bool(l.softmax or l.softmax_tree)),
+                                         groups, gs, go, None), "region_forward")
+        region_out = out.get(np.float32, (B, total, size))
+        map_n, map_dev = 0, None
+        if use_map:
+            assert l.map, "region layer has no map"
+            map_n = 200
+            map_dev = dev(200 * 4, np.ctypeslib.as_array(l.map, (200,)).astype(np.int32)).ptr
+        out_classes = map_n or classes
+        boxes = dev(B * total * 4 * 4)
+        probs = dev(B * total * out_classes * 4)
+        _lib.check(lib.y2_region_boxes(out.ptr, biases.ptr, boxes.ptr, probs.ptr, B, l.w, l.h, n, classes, 1.0, 1.0,
+                                       thresh, 0, l.classfix, tree_n, parent, map_dev, map_n, None), "region_boxes")
+        pre = probs.get(np.float32, (B, total, out_classes))
+        if nms > 0:
+            _lib.check(lib.y2_nms_sort(boxes.ptr, probs.ptr, B, total, out_classes, nms, None), "nms_sort")
+        post = probs.get(np.float32, (B, total, out_classes))
+        res = {"region_out": region_out, "boxes": boxes.get(np.float32, (B, total, 4)),
+               "region_after_boxes": out.get(np.float32, (B, total, size))}
+        if out_classes != classes:  # the reference's probs rows are `classes` wide, only 200 are written
+            full_pre = np.zeros((B, total, classes), np.float32)
+            full_post = np.zeros((B, total, classes), np.float32)
+            full_pre[:, :, :out_classes] = pre
+            full_post[:, :, :out_classes] = post
+            pre, post = full_pre, full_post
+        res["probs_pre"], res["probs_post"] = pre, post
+        return res
+    finally:
+        for b in bufs:
+            b.free()

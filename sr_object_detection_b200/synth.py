@@ -104,7 +104,34 @@ def resnet50_cfg(batch=1, w=256, h=256):
     return s + "[avgpool]\n\n[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
 
 
+def mini_yolo_cfg(batch=2, w=32, h=32, classes=4, num=3, extra=""):
+    """A 17-layer detector with every layer kind and quirk of yolo-voc.cfg / tiny-yolo-voc.cfg at
+    toy size (golden-fixture network): 3x3 and 1x1 convs, 2/2 pools, the 2/1 pool with pad 0,
+    a single-input route, reorg, a two-input route, a linear head and a region layer."""
+    s = _net(batch, w, h)
+    s += _conv(8, 3) + _maxpool() + _conv(16, 3) + _maxpool() + _conv(16, 1) + _conv(32, 3)   # 0-5
+    s += _maxpool() + _conv(32, 3) + _maxpool(2, 1) + _conv(64, 3)                            # 6-9
+    s += "[route]\nlayers=-5\n\n" + _conv(8, 1) + "[reorg]\nstride=2\n\n[route]\nlayers=-1,-4\n\n"  # 10-13
+    s += _conv(32, 3) + _conv(num * (classes + 5), 1, bn=0, act="linear")                     # 14-15
+    anchors = ",".join(f"{0.6 + 0.7 * i:.2f},{0.8 + 0.5 * i:.2f}" for i in range(num))
+    return s + _region(anchors, classes, num, extra)
+
+
+def mini_resnet_cfg(batch=2, w=32, h=32):
+    """Toy version of resnet50.cfg (golden-fixture network): 7x7/2 stem, pool, two bottlenecks
+    whose shortcuts exercise the channel-mismatch and the stride-2 sampling branches of
+    shortcut_cpu (blas.c:57-81), then the classifier tail conv -> avgpool -> softmax -> cost."""
+    s = _net(batch, w, h) + _conv(16, 7, stride=2) + _maxpool(2, 2)
+    for a, st in ((8, 1), (16, 2)):
+        s += _conv(a, 1) + _conv(a, 3, stride=st) + _conv(4 * a, 1, act="linear")
+        s += "[shortcut]\nfrom=-4\nactivation=leaky\n\n"
+    s += _conv(10, 1, bn=0, act="linear")
+    return s + "[avgpool]\n\n[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
+
+
 CFGS = {
+    "mini-yolo": mini_yolo_cfg,
+    "mini-resnet": mini_resnet_cfg,
     "tiny-yolo-voc": tiny_yolo_voc_cfg,
     "yolo-voc": yolo_voc_cfg,
     "yolo": yolo_coco_cfg,
@@ -198,6 +225,13 @@ def write_tree(path: str | Path, n: int = 9418, fanout: int = 5, roots: int = 4)
         for i in range(n):
             parent = -1 if i < roots else (i - roots) // fanout
             f.write(f"n{i:08d} {parent}\n")
+
+
+def write_map(path: str | Path, classes: int, n: int = 200, seed: int = 5) -> None:
+    """A `map=` file as read by read_map (utils.c:17-33): n class indices, one per line."""
+    rng = np.random.default_rng(seed)
+    idx = rng.permutation(classes)[:n] if classes >= n else rng.integers(0, classes, n)
+    Path(path).write_text("".join(f"{int(i)}\n" for i in idx))
 
 
 def region_inputs(batch: int, n: int, classes: int, h: int, w: int, seed: int = 7,

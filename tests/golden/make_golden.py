@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures of tests/golden/*.npz by running the UNMODIFIED reference
+(oracle/_ref/darknet_ref = /root/reference/src_yolo2 compiled by oracle/Makefile) on seeded
+synthetic inputs.  The reference ships no golden vectors, weights or tests of its own
+(SURVEY.md section 4), so these reference outputs are what pins the oracle (and, through it,
+the CUDA path).  Run in the build container, where /root/reference exists:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Each .npz is self-contained: cfg text, weights bytes, inputs and every reference output.
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from sr_object_detection_b200 import synth  # noqa: E402
+
+REF = ROOT / "oracle" / "_ref" / "darknet_ref"
+OUT = Path(__file__).resolve().parent
+REF_CFG = Path("/root/reference/cfg")
+
+
+def run(args, cwd, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([str(REF), *map(str, args)], cwd=cwd, env=e, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise SystemExit(f"darknet_ref {args[0]} failed:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def f32(path):
+    return np.fromfile(path, np.float32)
+
+
+def forward_case(name, cfg_text, batch, side, thresh, nms, aux_files=None):
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        (t / "net.cfg").write_text(cfg_text)
+        for fn, text in (aux_files or {}).items():
+            (t / fn).write_text(text)
+        synth.write_weights(t / "net.weights", cfg_text, seed=1234)
+        x = synth.images(batch, 3, side, side, seed=42)
+        x.tofile(t / "in.f32")
+        (t / "out").mkdir()
+        run(["forward", "net.cfg", "net.weights", "in.f32", "out", thresh, nms, 1], cwd=t)
+        table = run(["layers", "net.cfg"], cwd=t)
+        d = {"cfg": np.array(cfg_text), "weights": np.frombuffer((t / "net.weights").read_bytes(), np.uint8),
+             "input": x, "thresh": np.float32(thresh), "nms": np.float32(nms), "layers": np.array(json.dumps(table))}
+        for fn, text in (aux_files or {}).items():
+            d["aux_" + fn.replace(".", "_")] = np.array(text)
+        for p in sorted((t / "out").iterdir()):
+            d[p.stem] = f32(p)
+        np.savez_compressed(OUT / f"{name}.npz", **d)
+        print(name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in d.items() if k.startswith(("output", "probs"))})
+
+
+def region_case(name, cfg_text, x, thresh, nms, aux_files=None, use_map=False):
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        (t / "net.cfg").write_text(cfg_text)
+        for fn, text in (aux_files or {}).items():
+            (t / fn).write_text(text)
+        x.tofile(t / "in.f32")
+        (t / "out").mkdir()
+        run(["region", "net.cfg", "in.f32", "out", thresh, nms], cwd=t, env={"Y2_USE_MAP": "1" if use_map else "0"})
+        d = {"cfg": np.array(cfg_text), "region_in": x, "thresh": np.float32(thresh), "nms": np.float32(nms),
+             "use_map": np.int32(use_map)}
+        for fn, text in (aux_files or {}).items():
+            d["aux_" + fn.replace(".", "_")] = np.array(text)
+        for p in sorted((t / "out").iterdir()):
+            d[p.stem] = f32(p)
+        np.savez_compressed(OUT / f"{name}.npz", **d)
+        pre, post = d["probs_pre"], d["probs_post"]
+        print(name, "nonzero probs pre/post NMS:", int((pre != 0).sum()), int((post != 0).sum()))
+
+
+def region_only_cfg(batch, side, n, classes, anchors, extra=""):
+    """[net] whose input already is the region layer's input (a region layer alone)."""
+    return (f"[net]\nbatch={batch}\nsubdivisions=1\nheight={side}\nwidth={side}\nchannels={n * (classes + 5)}\n\n"
+            + synth._region(anchors, classes, n, extra))
+
+
+def tree_text(n, fanout, roots):
+    with tempfile.NamedTemporaryFile("r", suffix=".tree") as f:
+        synth.write_tree(f.name, n=n, fanout=fanout, roots=roots)
+        return Path(f.name).read_text()
+
+
+def tree_region_inputs(batch, n, classes, side, fanout, roots, seed):
+    """Region inputs for a softmax tree: on hot cells boost one root-to-leaf path so that the
+    hierarchical product exceeds .5 somewhere below the root."""
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((batch, n, 5 + classes, side, side))).astype(np.float32)
+    x[:, :, 4] -= 2.0
+    x[:, :, 2:4] *= 0.25
+    hot = rng.random((batch, side, side)) < 0.2
+    bi, hi, wi = np.nonzero(hot)
+    for a in range(n):
+        x[bi, a, 4, hi, wi] += 6.0
+        node = rng.integers(roots + fanout * roots, classes, len(bi))
+        for _ in range(8):
+            x[bi, a, 5 + node, hi, wi] += 9.0
+            parent = np.where(node < roots, node, (node - roots) // fanout)
+            node = parent
+    return x.reshape(batch, n * (5 + classes), side, side)
+
+
+def parser_tables():
+    """Layer tables of the reference parser on its OWN cfg files, next to the tables of the
+    synthetic cfg text used everywhere else: they must agree (checked here, at generation
+    time, because /root/reference does not exist where the tests run)."""
+    out = {}
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        for name, real, kw in (("tiny-yolo-voc", "tiny-yolo-voc.cfg", {}), ("yolo-voc", "yolo-voc.cfg", {}),
+                               ("yolo", "yolo.cfg", {"w": 416, "h": 416}), ("darknet19_448", "darknet19_448.cfg", {}),
+                               ("resnet50", "resnet50.cfg", {})):
+            (t / "s.cfg").write_text(synth.CFGS[name](batch=1, **kw))
+            mine = run(["layers", "s.cfg"], cwd=t)
+            theirs = run(["layers", REF_CFG / real], cwd=t)
+            assert mine["layers"] == theirs["layers"], f"synthetic {name} cfg differs from the reference's {real}"
+            assert (mine["w"], mine["h"], mine["c"]) == (theirs["w"], theirs["h"], theirs["c"])
+            out[name] = mine
+        synth.write_tree(t / "9k.tree")
+        (t / "y9k.cfg").write_text(synth.yolo9000_cfg(batch=1, tree="9k.tree"))
+        out["yolo9000"] = run(["layers", "y9k.cfg"], cwd=t)
+        (t / "y608.cfg").write_text(synth.yolo_coco_cfg(batch=1, w=608, h=608))
+        out["yolo-608"] = run(["layers", "y608.cfg"], cwd=t)
+    (OUT / "parser_tables.json").write_text(json.dumps(out, indent=0))
+    print("parser tables:", {k: len(v["layers"]) for k, v in out.items()})
+
+
+def main():
+    if not REF.exists():
+        raise SystemExit("oracle/_ref/darknet_ref missing: run `make -C oracle ref` first")
+    # 1. whole networks, every layer's activations + decode + NMS
+    forward_case("mini_yolo", synth.mini_yolo_cfg(batch=2), 2, 32, 0.05, 0.4)
+    forward_case("mini_resnet", synth.mini_resnet_cfg(batch=2), 2, 32, 0.0, 0.0)
+    tt = tree_text(30, 3, 3)
+    forward_case("mini_yolo_tree", synth.mini_yolo_cfg(batch=1, classes=30, num=2, extra="tree=t.tree\n"), 1, 32, 0.05,
+                 0.4, aux_files={"t.tree": tt})
+    # 2. decode + NMS on crafted region inputs (non-trivial keep sets)
+    region_case("region_voc_13", region_only_cfg(1, 13, 5, 20, synth.VOC_ANCHORS),
+                synth.region_inputs(1, 5, 20, 13, 13, seed=11, hot_fraction=0.08), 0.24, 0.4)
+    region_case("region_voc_7_lowthresh", region_only_cfg(2, 7, 5, 20, synth.VOC_ANCHORS),
+                synth.region_inputs(2, 5, 20, 7, 7, seed=12, hot_fraction=0.1), 0.005, 0.45)
+    region_case("region_coco_9", region_only_cfg(1, 9, 5, 80, synth.COCO_ANCHORS),
+                synth.region_inputs(1, 5, 80, 9, 9, seed=13, hot_fraction=0.1), 0.24, 0.4)
+    tt = tree_text(220, 5, 4)
+    xt = tree_region_inputs(2, 3, 220, 5, 5, 4, seed=14)
+    region_case("region_tree_220", region_only_cfg(2, 5, 3, 220, synth.Y9K_ANCHORS, "tree=t.tree\n"), xt, 0.24, 0.4,
+                aux_files={"t.tree": tt})
+    with tempfile.NamedTemporaryFile("r", suffix=".map") as f:
+        synth.write_map(f.name, 220)
+        mt = Path(f.name).read_text()
+    region_case("region_tree_220_map", region_only_cfg(2, 5, 3, 220, synth.Y9K_ANCHORS, "tree=t.tree\nmap=t.map\n"), xt,
+                0.05, 0.4, aux_files={"t.tree": tt, "t.map": mt}, use_map=True)
+    # 3. resize_image
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        im = np.random.default_rng(3).random((3, 20, 30), dtype=np.float32)
+        im.tofile(t / "im.f32")
+        subprocess.run([str(REF), "resize", "im.f32", "3", "20", "30", "13", "17", "out.f32"], cwd=t, check=True)
+        np.savez_compressed(OUT / "resize.npz", image=im, resized=f32(t / "out.f32").reshape(3, 13, 17))
+    # 4. parser tables, incl. the reference's own cfg files
+    parser_tables()
+
+
+if __name__ == "__main__":
+    main()

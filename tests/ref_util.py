@@ -19,8 +19,30 @@ def have_oracle() -> bool:
     return ORACLE_BIN.exists()
 
 
-def _run(cmd, cwd=None, threads=None):
+def build_oracle() -> None:
+    """Compile oracle/y2_oracle.c (test infrastructure) if the binary is missing or stale."""
+    src = ROOT / "oracle" / "y2_oracle.c"
+    if ORACLE_BIN.exists() and ORACLE_BIN.stat().st_mtime >= src.stat().st_mtime:
+        return
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "oracle"], check=True, capture_output=True)
+
+
+def checker_bin():
+    """The CPU checker for the GPU parity tests: the compiled reference when it is present,
+    else the oracle port (pinned to the reference by tests/test_oracle_golden.py)."""
+    if REF_BIN.exists():
+        return REF_BIN
+    build_oracle()
+    return ORACLE_BIN
+
+
+def run_raw(cmd, cwd=None, env=None):
+    return _run(cmd, cwd=cwd, extra_env=env)
+
+
+def _run(cmd, cwd=None, threads=None, extra_env=None):
     env = dict(os.environ)
+    env.update(extra_env or {})
     if threads:
         env["OMP_NUM_THREADS"] = str(threads)
     r = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, cwd=cwd, env=env)

@@ -1,0 +1,191 @@
+"""CPU tests of the C host runtime (no GPU, gpu_index = -1: parse only): cfg parsing,
+.weights loading and the shape bookkeeping must agree with the reference's parser — checked
+against tests/golden/parser_tables.json, the tables printed by the reference's own parser
+(on its own cfg files too, see tests/golden/make_golden.py)."""
+import ctypes as C
+import json
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from sr_object_detection_b200 import darknet as dn
+from sr_object_detection_b200 import synth
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+FIELDS = ("type", "w", "h", "c", "out_w", "out_h", "out_c", "outputs", "n", "size", "stride", "pad")
+
+
+@pytest.fixture(autouse=True)
+def _host_only():
+    prev = dn.gpu_index()
+    dn.set_gpu_index(-1)
+    yield
+    dn.set_gpu_index(prev)
+
+
+def _table(net):
+    return [{f: int(getattr(net.layers[i], f)) for f in FIELDS} for i in range(net.n)]
+
+
+CASES = [("tiny-yolo-voc", {}, "tiny-yolo-voc"), ("yolo-voc", {}, "yolo-voc"), ("yolo", {"w": 416, "h": 416}, "yolo"),
+         ("yolo", {"w": 608, "h": 608}, "yolo-608"), ("darknet19_448", {}, "darknet19_448"), ("resnet50", {}, "resnet50")]
+
+
+@pytest.mark.parametrize("name,kw,key", CASES, ids=[c[2] for c in CASES])
+def test_layer_tables_match_reference_parser(tmp_path, name, kw, key):
+    tables = json.loads((GOLDEN / "parser_tables.json").read_text())
+    cfg = tmp_path / "net.cfg"
+    cfg.write_text(synth.CFGS[name](batch=1, **kw))
+    net = dn.parse_network_cfg(cfg)
+    assert net.n == len(tables[key]["layers"])
+    assert (net.w, net.h, net.c) == (tables[key]["w"], tables[key]["h"], tables[key]["c"])
+    got = _table(net)
+    for i, (g, w) in enumerate(zip(got, tables[key]["layers"])):
+        assert g == w, f"{key} layer {i}: {g} != {w}"
+    assert net.b200 is None  # no device plan without a GPU
+    dn.free_network(net)
+
+
+def test_yolo9000_table_with_synthetic_tree(tmp_path, monkeypatch):
+    tables = json.loads((GOLDEN / "parser_tables.json").read_text())
+    synth.write_tree(tmp_path / "9k.tree")
+    (tmp_path / "net.cfg").write_text(synth.yolo9000_cfg(batch=1, tree="9k.tree"))
+    monkeypatch.chdir(tmp_path)  # tree= is resolved against the CWD, as in the reference
+    net = dn.parse_network_cfg("net.cfg")
+    assert _table(net) == tables["yolo9000"]["layers"]
+    l = net.layers[net.n - 1]
+    t = l.softmax_tree.contents
+    assert t.n == 9418 and l.classes == 9418
+    # read_tree group bookkeeping (tree.c:53-103): groups are runs of equal parents
+    sizes = [t.group_size[i] for i in range(t.groups)]
+    assert sum(sizes) == t.n and sizes[0] == 4 and set(sizes[1:-1]) == {5}
+    dn.free_network(net)
+
+
+def test_cfg_reader_semantics(tmp_path):
+    """batch /= subdivisions; blanks stripped everywhere; '#' and ';' comments; pad=1 means
+    size/2; maxpool defaults (size=stride, padding=(size-1)/2); conv default activation is
+    logistic; anchors parsed with atof/strchr (parser.c:139-171, 236-284, 359-374, 504-577)."""
+    text = """[net]
+ batch = 64
+subdivisions=8
+height=32 ; trailing text is part of the value in the reference too
+width = 32
+channels=3
+# comment
+; comment
+
+[convolutional]
+filters = 10
+size=3
+stride=1
+pad=1
+
+[maxpool]
+stride=2
+
+[convolutional]
+filters=14
+size=1
+pad=1
+activation=linear
+
+[region]
+anchors = 1.5,2.5,  3.25,4.75
+classes=2
+num=2
+"""
+    cfg = tmp_path / "r.cfg"
+    cfg.write_text(text.replace("height=32 ; trailing text is part of the value in the reference too", "height=32"))
+    net = dn.parse_network_cfg(cfg)
+    assert net.batch == 8 and net.subdivisions == 8
+    c0, mp, c1, rg = (net.layers[i] for i in range(4))
+    assert (c0.pad, c0.out_w, c0.out_h, c0.activation) == (1, 32, 32, 0)  # LOGISTIC = 0
+    assert (mp.size, mp.stride, mp.pad, mp.out_w) == (2, 2, 0, 16)
+    assert (c1.pad, c1.out_w, c1.activation) == (0, 16, 3)  # 1x1 with pad=1 -> padding 0; LINEAR = 3
+    assert rg.type == dn.REGION and rg.outputs == 16 * 16 * 14
+    assert [rg.biases[i] for i in range(4)] == [1.5, 2.5, 3.25, 4.75]
+    dn.free_network(net)
+
+
+@pytest.mark.parametrize("major,minor", [(0, 1), (0, 2)])
+def test_weights_loader_layout(tmp_path, major, minor):
+    """parser.c:1009-1082: header int32 x3, `seen` int32 or (major*10+minor >= 2) 64-bit; per conv
+    biases, [scales, mean, variance], weights — BN arrays absent for non-BN layers."""
+    cfg_text = synth.mini_yolo_cfg(batch=1)
+    cfg = tmp_path / "net.cfg"
+    cfg.write_text(cfg_text)
+    w = tmp_path / "net.weights"
+    synth.write_weights(w, cfg_text, seed=77)
+    raw = w.read_bytes()
+    body = raw[16:]
+    header = struct.pack("<iii", major, minor, 0) + (struct.pack("<q", 5) if major * 10 + minor >= 2 else struct.pack("<i", 5))
+    w.write_bytes(header + body)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, w)
+    vals = np.frombuffer(body, np.float32)
+    off = 0
+    for i in range(net.n):
+        l = net.layers[i]
+        if l.type != dn.CONVOLUTIONAL:
+            continue
+        n, num = l.n, l.n * l.c * l.size * l.size
+        assert np.array_equal(np.ctypeslib.as_array(l.biases, (n,)), vals[off:off + n]); off += n
+        if l.batch_normalize:
+            for arr in (l.scales, l.rolling_mean, l.rolling_variance):
+                assert np.array_equal(np.ctypeslib.as_array(arr, (n,)), vals[off:off + n]); off += n
+        assert np.array_equal(np.ctypeslib.as_array(l.weights, (num,)), vals[off:off + num]); off += num
+    assert off == vals.size
+    dn.free_network(net)
+
+
+def test_resize_network_recomputes_shapes(tmp_path):
+    """resize_network (network.c:322-388): yolo.cfg says 416, the north star runs it at 608."""
+    tables = json.loads((GOLDEN / "parser_tables.json").read_text())
+    cfg = tmp_path / "net.cfg"
+    cfg.write_text(synth.yolo_coco_cfg(batch=1, w=416, h=416))
+    net = dn.parse_network_cfg(cfg)
+    assert dn.resize_network(net, 608, 608) == 0
+    assert _table(net) == tables["yolo-608"]["layers"]
+    assert (net.w, net.h, net.inputs) == (608, 608, 3 * 608 * 608)
+    assert dn.lib().get_network_output_size(net) == 19 * 19 * 425
+    dn.free_network(net)
+
+
+def test_predict_without_gpu_fails_loudly(tmp_path):
+    """No CPU fallback: network_predict on a host-only network aborts through error()
+    (utils.c:195-200 convention), it never computes on the CPU."""
+    import subprocess
+    import sys
+    cfg = tmp_path / "net.cfg"
+    cfg.write_text(synth.mini_yolo_cfg(batch=1))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from sr_object_detection_b200 import darknet as dn\n"
+        "dn.set_gpu_index(-1)\n"
+        "net = dn.parse_network_cfg(%r)\n"
+        "dn.network_predict(net, np.zeros((1, 3, 32, 32), np.float32))\n"
+        "print('COMPUTED')\n" % (str(Path(__file__).resolve().parents[1]), str(cfg)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "COMPUTED" not in r.stdout
+    assert "no CPU execution path" in r.stderr
+
+
+def test_host_helpers_match_reference_semantics():
+    lib = dn.lib()
+    a = np.array([0.1, 0.7, 0.7, -1.0], np.float32)
+    assert lib.max_index(a.ctypes.data_as(C.POINTER(C.c_float)), 4) == 1  # first max wins (utils.c:533-545)
+    b1, b2 = dn.Box(0.5, 0.5, 0.2, 0.2), dn.Box(0.55, 0.5, 0.2, 0.2)
+    inter = np.float32(np.float32(0.15) * np.float32(0.2))
+    # box.c:67-97 in float arithmetic
+    l1 = np.float32(0.5) - np.float32(0.2) / np.float32(2)
+    l2 = np.float32(0.55) - np.float32(0.2) / np.float32(2)
+    r1 = np.float32(0.5) + np.float32(0.2) / np.float32(2)
+    r2 = np.float32(0.55) + np.float32(0.2) / np.float32(2)
+    w = np.float32(min(r1, r2) - max(l1, l2))
+    hgt = np.float32(np.float32(0.6) - np.float32(0.4))
+    inter = np.float32(w * hgt)
+    union = np.float32(np.float32(np.float32(0.2) * np.float32(0.2) + np.float32(0.2) * np.float32(0.2)) - inter)
+    assert lib.box_iou(b1, b2) == pytest.approx(float(inter / union), rel=1e-6)
