@@ -655,6 +655,9 @@ void y2_plan_network(network *net)
             if (l->binary || l->xnor) unsupported(i, "binary/xnor convolution");
             r->out_kind = consumer_wants_f32(net, i) ? Y2_KIND_F32_FLAT : Y2_KIND_BF16_PADDED;
             r->cpad = (r->out_kind == Y2_KIND_F32_FLAT) ? l->n : storage_channels(l->n);
+            /* a reorg permutes flat NCHW indices, so its input must be stored without channel
+             * padding; 8-channel granularity keeps the 16-byte stores */
+            if (i + 1 < net->n && net->layers[i + 1].type == REORG && l->n % 8 == 0) r->cpad = l->n;
             r->block_n = pick_block_n(l->n);
             r->npad = round_up(l->n, r->block_n);
             if (r->cpad > r->npad) r->npad = round_up(r->cpad, r->block_n);
