@@ -110,6 +110,18 @@ void y2_conv_plan_destroy(y2_conv_plan *plan);
  * business; this returns the number of MMA tiles for diagnostics. */
 int y2_conv_plan_tiles(const y2_conv_plan *plan);
 
+/* ---- first layer (replaces, for a 3x3/1 'same' convolution over <= 3 input channels followed by a
+ *      2x2/2 maxpool: cuda_make_array of the input (network_kernels.cu:399) +
+ *      forward_convolutional_layer_gpu (convolutional_kernels.cu:77-131) +
+ *      forward_maxpool_layer_gpu (maxpool_layer_kernels.cu:87-97)) ------------------------------ */
+/* in: fp32 NCHW [B][c][h][w];  wt: bf16 [32][32] with K index c*9 + r*3 + s (im2col.c:16-39 order),
+ * rows >= filters zero;  alpha >= 0 (fold the sign into wt);  out: bf16 padded NHWC of the POOLED
+ * extent [B][h/2+1][w/2+1][out_cs], channels 0..31 written, pads left untouched (zero at plan time). */
+int y2_stem_prepare(void);
+int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w, const void *wt, int npad,
+                      const float *alpha, const float *beta, int act, void *out, int out_cs,
+                      y2_stream_t s);
+
 /* ---- layout / packing kernels ------------------------------------------------------ */
 
 /* fp32 NCHW [B][C][H][W] -> bf16 padded NHWC [B][H+1][W+1][cs] (channels >= C zeroed up

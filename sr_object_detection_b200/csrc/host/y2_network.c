@@ -520,6 +520,15 @@ void y2_push_convolutional_layer(layer *l)
             beta[f] = l->biases[f];
         }
     }
+    if (r->stem_fused) {
+        /* the fused conv+maxpool kernel takes the max before the affine map, which needs alpha >= 0:
+         * negate the filter and its alpha together (alpha*acc is unchanged bit for bit) */
+        for (int f = 0; f < l->n; ++f)
+            if (alpha[f] < 0) {
+                alpha[f] = -alpha[f];
+                for (int k = 0; k < r->ktot; ++k) w[(size_t)f * r->ktot + k] ^= 0x8000u;
+            }
+    }
     Y2_CHECK(y2_memcpy_h2d(r->wt_dev, w, elems * 2, 0));
     Y2_CHECK(y2_memcpy_h2d(r->alpha_dev, alpha, (size_t)r->npad * 4, 0));
     Y2_CHECK(y2_memcpy_h2d(r->beta_dev, beta, (size_t)r->npad * 4, 0));
@@ -536,6 +545,26 @@ static int pick_block_n(int cout)
     if (cout <= 64) return 64;
     if (cout <= 128) return 128;
     return 256;
+}
+
+/* layer 0 = 3x3/1 'same' conv over <= 3 channels with <= 32 filters, leaky/linear, feeding ONLY a
+ * 2x2/2 maxpool without padding: run both as the fused first-layer kernel */
+static int stem_fusable(network *net, int i)
+{
+    if (i != 0 || net->n < 2 || getenv("Y2_NO_STEM_FUSION")) return 0;
+    layer *l = &net->layers[0], *m = &net->layers[1];
+    if (l->size != 3 || l->stride != 1 || l->pad != 1 || l->c > 3 || l->n > 32) return 0;
+    if (l->activation != LEAKY && l->activation != LINEAR) return 0;
+    if (m->type != MAXPOOL || m->size != 2 || m->stride != 2 || m->pad != 0) return 0;
+    if (l->h < 2 || l->w < 2) return 0;
+    for (int j = 2; j < net->n; ++j) {
+        layer *lj = &net->layers[j];
+        if (lj->type == ROUTE)
+            for (int k = 0; k < lj->n; ++k)
+                if (lj->input_layers[k] == 0) return 0;
+        if (lj->type == SHORTCUT && lj->index == 0) return 0;
+    }
+    return 1;
 }
 
 /* view of the tensor a layer reads through state.input */
@@ -615,7 +644,8 @@ static void build_plans(network *net, int batch)
 {
     y2_net_rt *rt = (y2_net_rt *)net->b200;
     for (int i = 0; i < net->n; ++i)
-        if (net->layers[i].type == CONVOLUTIONAL) build_conv_plan(net, i, batch);
+        if (net->layers[i].type == CONVOLUTIONAL && !((y2_layer_rt *)net->layers[i].b200)->stem_fused)
+            build_conv_plan(net, i, batch);
     rt->plan_batch = batch;
     if (rt->graph) {
         y2_graph_destroy(rt->graph);
@@ -668,6 +698,7 @@ void y2_plan_network(network *net)
                 r->ktot = r->kpad;
                 r->block_k = r->kpad == 32 ? 32 : 64;
                 r->cin_pad = r->kpad;
+                r->stem_fused = stem_fusable(net, i);
             } else {
                 int cin_pad;
                 if (i == 0) cin_pad = storage_channels(l->c);
@@ -688,6 +719,7 @@ void y2_plan_network(network *net)
             if (!pr || pr->out_kind != Y2_KIND_BF16_PADDED) unsupported(i, "maxpool/reorg without a tensor input");
             if (l->type == REORG && l->reverse) unsupported(i, "reverse reorg");
             r->out_kind = Y2_KIND_BF16_PADDED;
+            if (l->type == MAXPOOL && pr->stem_fused) r->fused_into_prev = 1;
             if (l->type == MAXPOOL) r->cpad = pr->cpad;
             else {
                 if (pr->cpad != l->c) unsupported(i, "reorg of a channel-padded tensor");
@@ -785,6 +817,11 @@ void y2_plan_network(network *net)
         layer *l = &net->layers[i];
         y2_layer_rt *r = (y2_layer_rt *)l->b200;
         if (l->type == ROUTE || r->out_kind == Y2_KIND_NONE) continue;
+        if (r->stem_fused) { /* the full-resolution activation is never materialised */
+            r->out = 0;
+            r->out_cs = r->cpad;
+            continue;
+        }
         if (r->placed_in >= 0) {
             layer *rl = &net->layers[r->placed_in];
             y2_layer_rt *rr = (y2_layer_rt *)rl->b200;
@@ -832,7 +869,8 @@ void y2_plan_network(network *net)
             l->weights_gpu = (float *)r->wt_dev;
             l->biases_gpu = r->beta_dev;
             l->scales_gpu = r->alpha_dev;
-            if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->kpad));
+            if (r->stem_fused) Y2_CHECK(y2_stem_prepare());
+            else if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->kpad));
             else if (i == 0) r->packed_in = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->cin_pad));
             y2_push_convolutional_layer(l);
         } else if (l->type == REGION) {
@@ -880,6 +918,14 @@ void forward_convolutional_layer_gpu(layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_stream_t s = net_stream(state.net);
+    if (r->stem_fused) {
+        y2_layer_rt *mr = y2_lrt(state.net.layers[state.index + 1]);
+        const int act = (l.activation == LEAKY) ? Y2_ACT_LEAKY : Y2_ACT_LINEAR;
+        Y2_CHECK(y2_stem_conv_pool(state.input, l.batch, l.c, l.h, l.w, r->wt_dev, r->npad, r->alpha_dev,
+                                   r->beta_dev, act, mr->out, mr->out_cs, s));
+        count_launch(state.net, 1);
+        return;
+    }
     if (r->use_patches) {
         Y2_CHECK(y2_pack_patches_f32(state.input, r->patches, l.batch, l.c, l.h, l.w, l.size, r->kpad, s));
         count_launch(state.net, 1);
@@ -895,6 +941,7 @@ void forward_maxpool_layer_gpu(layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
+    if (r->fused_into_prev) return; /* the first-layer kernel already wrote this layer's output */
     Y2_CHECK(y2_maxpool(pr->out, pr->out_cs, r->out, r->out_cs, l.batch, r->cpad, l.h, l.w, l.out_h, l.out_w,
                         l.size, l.stride, l.pad, net_stream(state.net)));
     count_launch(state.net, 1);
@@ -1001,7 +1048,7 @@ void forward_network_gpu(network net, network_state state)
         }
         l.forward_gpu(l, state);
         if (rt->profile && r) Y2_CHECK(y2_event_record(r->ev1, rt->stream));
-        state.input = l.output_gpu;
+        if (l.output_gpu) state.input = l.output_gpu;
     }
 }
 
@@ -1130,7 +1177,30 @@ static float *export_layer(network net, int i)
         Y2_CHECK(y2_malloc((void **)&rt->export_dev, rt->export_bytes));
     }
     const float *src = rt->export_dev;
-    if (r->out_kind == Y2_KIND_BF16_PADDED) {
+    if (r->stem_fused) {
+        /* inspection path: the fused kernel never stores this activation, so recompute it with the
+         * generic patch-gather + convolution kernels into scratch buffers */
+        void *patches = dev_alloc_zero(padded_bytes(net.batch, l->h, l->w, r->kpad));
+        void *full = dev_alloc_zero(padded_bytes(net.batch, l->out_h, l->out_w, r->cpad));
+        y2_conv_desc d;
+        memset(&d, 0, sizeof(d));
+        d.in = patches; d.in_cs = r->kpad; d.cin = r->kpad; d.ksize = 1;
+        d.batch = net.batch; d.h = l->out_h; d.w = l->out_w;
+        d.wt = r->wt_dev; d.cout = r->cpad; d.npad = r->npad; d.block_n = r->block_n; d.block_k = r->block_k;
+        d.alpha = r->alpha_dev; d.beta = r->beta_dev;
+        d.act = (l->activation == LEAKY) ? Y2_ACT_LEAKY : Y2_ACT_LINEAR;
+        d.out = full; d.out_cs = r->cpad; d.out_mode = Y2_OUT_BF16_PADDED;
+        y2_conv_plan *plan = 0;
+        Y2_CHECK(y2_conv_plan_create(&d, &plan));
+        Y2_CHECK(y2_pack_patches_f32(rt->in_dev, patches, net.batch, l->c, l->h, l->w, l->size, r->kpad, rt->stream));
+        Y2_CHECK(y2_conv_plan_launch(plan, rt->stream));
+        Y2_CHECK(y2_unpack_to_nchw_f32(full, rt->export_dev, net.batch, l->out_c, l->out_h, l->out_w, r->cpad,
+                                       rt->stream));
+        Y2_CHECK(y2_stream_sync(rt->stream));
+        y2_conv_plan_destroy(plan);
+        y2_free(patches);
+        y2_free(full);
+    } else if (r->out_kind == Y2_KIND_BF16_PADDED) {
         Y2_CHECK(y2_unpack_to_nchw_f32(r->out, rt->export_dev, net.batch, l->out_c, l->out_h, l->out_w, r->out_cs,
                                        rt->stream));
     } else if (r->out_kind == Y2_KIND_F32_FLAT && l->type == CONVOLUTIONAL) {

@@ -254,3 +254,35 @@ def test_copy_channels_route_fallback():
     torch.cuda.synchronize()
     assert torch.equal(dst[..., 32:96], src[..., 16:80])
     assert dst[..., :32].abs().max().item() == 0 and dst[..., 96:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("batch,c,h,w,n", [(2, 3, 50, 38, 32), (3, 3, 64, 96, 16), (1, 1, 33, 35, 8), (4, 3, 416, 416, 32)])
+def test_stem_conv_pool_matches_fp32_reference(batch, c, h, w, n):
+    """Fused first layer: conv3x3 + affine + leaky + 2x2/2 maxpool from fp32 NCHW, vs PyTorch fp32 on
+    the same bf16-rounded operands.  Tolerance 1e-2 of the tensor max (bf16 output rounding)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(99 + h + n)
+    x = torch.rand(batch, c, h, w, generator=g).to(dev)
+    s = (2.0 / (9 * c)) ** 0.5
+    wt = ((torch.rand(n, c, 3, 3, generator=g) * 2 - 1) * s).to(dev)
+    alpha = torch.zeros(32, device=dev)
+    beta = torch.zeros(32, device=dev)
+    alpha[:n] = torch.rand(n, generator=g).to(dev) + 0.5
+    beta[:n] = torch.rand(n, generator=g).to(dev) * 0.4 - 0.2
+    wt_p = torch.zeros(32, 32, dtype=torch.bfloat16, device=dev)
+    wt_p[:n, :c * 9] = wt.reshape(n, c * 9).to(torch.bfloat16)
+    oh, ow = h // 2, w // 2
+    out = torch.zeros(batch, oh + 1, ow + 1, 32, dtype=torch.bfloat16, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.y2_stem_conv_pool(x.data_ptr(), batch, c, h, w, wt_p.data_ptr(), 32, alpha.data_ptr(),
+                                     beta.data_ptr(), ACT_LEAKY, out.data_ptr(), 32, _stream()), "stem")
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, wt, alpha[:n], beta[:n], ACT_LEAKY, 3)
+    ref = torch.nn.functional.max_pool2d(ref, 2, 2)
+    got = G.from_padded_nhwc(out, n, oh, ow)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-2, f"max err / max|ref| = {err:.3e}"
+    # pads and unused channels stay zero
+    assert out[:, oh, :, :].abs().max().item() == 0 and out[:, :, ow, :].abs().max().item() == 0
+    if n < 32:
+        assert out[..., n:].abs().max().item() == 0
