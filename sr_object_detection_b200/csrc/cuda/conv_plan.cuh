@@ -1,0 +1,76 @@
+// Shared definition of a convolution plan: tensor maps + launch geometry of one of the two
+// tcgen05 implicit-GEMM kernels (conv_slab.cu: halo slab + dual accumulators; conv_tcgen05.cu:
+// one TMA load per tap, the general fallback).
+#pragma once
+#include "y2_common.cuh"
+
+namespace y2 {
+
+constexpr int kBlockM = 128;
+
+// ---- per-tap kernel (conv_tcgen05.cu) ------------------------------------------------
+struct ConvParams {
+    int taps;        // 1 or 9
+    int ksize;       // 1 or 3
+    int cblocks;     // cin / BLOCK_K
+    int wp, hp;      // padded row pitch / rows per image
+    int h, w;
+    int total_pos;   // B * hp * wp
+    int tiles_m, tiles_n;
+    int cout;        // channels stored
+    int act;
+    int out_mode;
+    int out_cs;
+    int stages;
+    const float *alpha;
+    const float *beta;
+    void *out;
+};
+
+// ---- slab kernel (conv_slab.cu) ------------------------------------------------------
+struct SlabParams {
+    int cblocks;           // cin / BLOCK_K
+    int wp, hp, h, w;
+    int total_pos;
+    int tiles_m, tiles_n;  // tiles_m counts tiles of ACCS x 128 positions
+    int halo;              // rows of the slab before the tile's first position (wp + 1)
+    int slab_loads;        // TMA loads per slab
+    int box_rows;          // rows per TMA load
+    int slab_bytes;        // bytes per slab stage
+    int stages_a, stages_b;
+    int cout, act, out_mode, out_cs;
+    const float *alpha;
+    const float *beta;
+    void *out;
+};
+
+enum { kVariantPerTap = 0, kVariantSlab = 1 };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+// 2-D bf16 tensor map (dim0 = channels, contiguous; dim1 = rows), swizzle = box0 bytes
+int encode_2d_bf16(CUtensorMap *tm, const void *base, uint64_t dim0, uint64_t dim1,
+                   uint64_t stride1_bytes, uint32_t box0, uint32_t box1, int block_k);
+
+} // namespace y2
+
+struct y2_conv_plan {
+    CUtensorMap tm_a;
+    CUtensorMap tm_b;
+    int variant;
+    y2::ConvParams prm;
+    y2::SlabParams slab;
+    int block_n, block_k;
+    int grid;
+    size_t smem_bytes;
+};
+
+namespace y2 {
+// conv_slab.cu: returns Y2_OK and fills the plan when the layer fits the slab kernel, Y2_EINVAL
+// (without touching the error string) when it does not and the per-tap kernel must be used
+int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d);
+int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
+} // namespace y2

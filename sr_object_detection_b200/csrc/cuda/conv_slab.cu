@@ -1,0 +1,454 @@
+// Implicit-GEMM 3x3 convolution, "halo slab" variant.
+//
+// Replaces forward_convolutional_layer_gpu (reference convolutional_kernels.cu:77-131) for 3x3
+// stride-1 'same' layers; 1x1 layers and shapes that do not fit use conv_tcgen05.cu.
+//
+// Why a second kernel.  In the per-tap kernel (conv_tcgen05.cu) every one of the nine taps TMA-loads
+// its own shifted copy of the same activations.  Shared-memory bandwidth (TMA fill + tensor-core
+// operand reads, ~128 B/clk/SM) is what bounds these layers on B200, so here
+//   * the activations of a tile are loaded ONCE per channel block as a slab of consecutive flat
+//     positions  [p0 - (W+1) - 1,  p0 + M + (W+1) + 1)  (padded-NHWC flat positions, see
+//     yolo2_b200_kernels.h); the nine taps are nine tcgen05.mma A-descriptors whose start address
+//     is shifted by  r*(W+1) + s  rows inside that slab.  The swizzle XOR is a function of the
+//     absolute shared-memory address, so a row-shifted descriptor reads exactly what TMA wrote
+//     (verified on B200 for SWIZZLE_128B and SWIZZLE_64B, experiments/shifted_desc_test.cu);
+//   * narrow layers (<= 128 filters) use a tile of 256 positions held in TWO TMEM accumulators, so
+//     every weight tile that arrives in shared memory feeds two MMAs; wide layers keep one
+//     128 x 256 accumulator (the A read of an MMA is amortised over 256 filters);
+//   * small weight tiles travel 3 or 9 taps per pipeline stage: the MMA-issuing thread is a single
+//     latency-bound thread, one mbarrier round trip (~100 clk) per 128 tensor-pipe clocks would
+//     starve the pipe;
+//   * accumulators are double buffered in TMEM: the epilogue (8 warps) of tile i overlaps the MMAs
+//     of tile i+1.
+// The nine taps are fully unrolled and every descriptor is "base + compile-time multiple of two
+// registers", so the issue loop is a few uniform-datapath adds per UTCHMMA.
+//
+// Warp roles (352 threads): 0 slab producer, 1 MMA issuer (+ TMEM alloc), 2 weight producer,
+// 3..10 epilogue (TMEM lane quarter = warp & 3; warps 3-6 take the first half of the tile's
+// accumulator columns, warps 7-10 the second half).  Producer / MMA warps run converged and
+// elect one lane per issue (see elect_one_sync in y2_common.cuh).
+#include "conv_plan.cuh"
+
+#include <stdlib.h>
+
+namespace y2 {
+
+constexpr int kSlabThreads = 352;
+constexpr int kSlabEpiThreads = 256;
+constexpr int kSlabMaxStagesA = 4;
+constexpr int kSlabMaxStagesB = 8;
+
+template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS>
+struct SlabCfg {
+    static constexpr int kTileM = ACCS * kBlockM;
+    static constexpr int kRowBytes = BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kBStageBytes = TPS * kBBytes;
+    static constexpr int kTmemCols = (2 * ACCS * BLOCK_N <= 128) ? 128 : (2 * ACCS * BLOCK_N <= 256) ? 256 : 512;
+    static_assert(2 * ACCS * BLOCK_N <= 512, "accumulators exceed TMEM");
+    static_assert(TPS == 1 || TPS == 3 || TPS == 9, "taps per stage");
+    static_assert(ACCS * BLOCK_N >= 64, "each epilogue half owns whole 32-column chunks");
+    static constexpr uint32_t kSBO = 8 * BLOCK_K * 2;
+    static constexpr uint32_t kLayout = (BLOCK_K == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+    // high word of a K-major smem descriptor: SBO>>4 at [32,46), version 1 at [46,48), swizzle [61,64)
+    static constexpr uint32_t kDescHi = (kSBO >> 4) | (1u << 14) | (kLayout << 29);
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                                       ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                       ((uint32_t)(kBlockM >> 4) << 24);
+};
+
+__device__ __forceinline__ uint64_t slab_desc(uint32_t hi, uint32_t lo)
+{
+    return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+
+// one 32-column chunk of one accumulator row: affine + activation + store
+__device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const uint32_t (&v)[32], const float2 *sab,
+                                                    int c0, int n0, int p, int b, int y, int x, bool in_range,
+                                                    bool valid)
+{
+    float f[32];
+    const float4 *ab4 = reinterpret_cast<const float4 *>(sab + c0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 q = ab4[j];  // (alpha, beta) of two filters
+        float t0 = fmaf(__uint_as_float(v[2 * j]), q.x, q.y);
+        float t1 = fmaf(__uint_as_float(v[2 * j + 1]), q.z, q.w);
+        if (prm.act == Y2_ACT_LEAKY) {
+            t0 = (t0 > 0.f) ? t0 : 0.1f * t0;
+            t1 = (t1 > 0.f) ? t1 : 0.1f * t1;
+        } else if (prm.act == Y2_ACT_LOGISTIC) {
+            t0 = 1.f / (1.f + __expf(-t0));
+            t1 = 1.f / (1.f + __expf(-t1));
+        }
+        f[2 * j] = t0;
+        f[2 * j + 1] = t1;
+    }
+    const int ch0 = n0 + c0;
+    if (prm.out_mode == Y2_OUT_BF16_PADDED) {
+        if (in_range) {
+            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(prm.out) + (size_t)p * prm.out_cs + ch0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (ch0 + q * 8 < prm.cout) {
+                    uint4 w;
+                    if (valid) {
+                        w.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+                        w.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+                        w.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+                        w.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+                    } else {
+                        w = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    *reinterpret_cast<uint4 *>(o + q * 8) = w;
+                }
+            }
+        }
+    } else {  // Y2_OUT_F32_FLAT: [B][h*w][out_cs]
+        if (valid) {
+            float *o = reinterpret_cast<float *>(prm.out) +
+                       ((size_t)b * prm.h * prm.w + (size_t)y * prm.w + x) * prm.out_cs + ch0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (ch0 + j < prm.cout) o[j] = f[j];
+        }
+    }
+}
+
+template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS>
+__global__ void __launch_bounds__(kSlabThreads, 1)
+conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const SlabParams prm)
+{
+    using Cfg = SlabCfg<BLOCK_N, BLOCK_K, ACCS, TPS>;
+    constexpr int kTileM = Cfg::kTileM;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int stages_a = prm.stages_a, stages_b = prm.stages_b;
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + (size_t)stages_a * prm.slab_bytes;
+    uint8_t *aux = smem_b + (size_t)stages_b * Cfg::kBStageBytes;
+    float2 *s_ab = reinterpret_cast<float2 *>(aux);  // [2 buf][BLOCK_N] (alpha, beta)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + 2 * BLOCK_N * 8);
+    uint64_t *a_full = bars;
+    uint64_t *a_empty = bars + kSlabMaxStagesA;
+    uint64_t *b_full = bars + 2 * kSlabMaxStagesA;
+    uint64_t *b_empty = b_full + kSlabMaxStagesB;
+    uint64_t *tfull_bar = b_empty + kSlabMaxStagesB;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = prm.tiles_m * prm.tiles_n;
+    const int cblocks = prm.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        for (int i = 0; i < stages_a; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < stages_b; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], kSlabEpiThreads);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== slab producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * Cfg::kRowBytes;
+        const uint32_t load_bytes = (uint32_t)prm.box_rows * Cfg::kRowBytes;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / prm.tiles_n;
+            const int row0 = m_tile * kTileM - prm.halo;
+            for (int cb = 0; cb < cblocks; ++cb) {
+                mbar_wait(&a_empty[stage], phase ^ 1, 1);
+                if (elect_one_sync()) {
+                    uint8_t *sa = smem_a + (size_t)stage * prm.slab_bytes;
+                    mbar_expect_tx(&a_full[stage], slab_tx);
+                    for (int i = 0; i < prm.slab_loads; ++i)
+                        tma_load_2d(&tm_a, &a_full[stage], sa + i * load_bytes, cb * BLOCK_K,
+                                    row0 + i * prm.box_rows);
+                }
+                __syncwarp();
+                if (++stage == stages_a) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== weight producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / prm.tiles_n;
+            const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
+            for (int cb = 0; cb < cblocks; ++cb) {
+#pragma unroll 1
+                for (int g = 0; g < 9 / TPS; ++g) {
+                    mbar_wait(&b_empty[stage], phase ^ 1, 2);
+                    if (elect_one_sync()) {
+                        uint8_t *sb = smem_b + (size_t)stage * Cfg::kBStageBytes;
+                        mbar_expect_tx(&b_full[stage], (uint32_t)Cfg::kBStageBytes);
+#pragma unroll
+                        for (int t = 0; t < TPS; ++t)
+                            tma_load_2d(&tm_b, &b_full[stage], sb + t * Cfg::kBBytes,
+                                        ((g * TPS + t) * cblocks + cb) * BLOCK_K, n0);
+                    }
+                    __syncwarp();
+                    if (++stage == stages_b) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        // descriptor low words (address >> 4, LBO field = 1) and their strides, all in 16-byte units
+        const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t slab16 = (uint32_t)prm.slab_bytes >> 4;
+        constexpr uint32_t kRow16 = Cfg::kRowBytes >> 4;        // one position (row) of the slab
+        const uint32_t wp16 = (uint32_t)prm.wp * kRow16;        // one image row of the slab
+        constexpr uint32_t kAcc16 = kBlockM * kRow16;           // second accumulator: +128 positions
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t buf_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[buf], buf_phase ^ 1, 3);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)(buf * ACCS * BLOCK_N);
+            for (int cb = 0; cb < cblocks; ++cb) {
+                mbar_wait(&a_full[sa_i], pa, 4);
+                const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
+                const uint32_t acc_first = cb != 0;  // tap 0, k 0 of block 0 overwrites the accumulator
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    if (tap % TPS == 0) {
+                        mbar_wait(&b_full[sb_i], pb, 5);
+                        tc_fence_after();
+                    }
+                    if (elect_one_sync()) {
+                        const uint32_t b_lo = b_lo0 + (uint32_t)sb_i * (Cfg::kBStageBytes >> 4) +
+                                              (uint32_t)(tap % TPS) * (Cfg::kBBytes >> 4);
+                        const uint32_t a_tap = a_lo + (uint32_t)(tap / 3) * wp16 + (uint32_t)(tap % 3) * kRow16;
+#pragma unroll
+                        for (int a = 0; a < ACCS; ++a) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k)
+                                umma_bf16(d0 + (uint32_t)(a * BLOCK_N),
+                                          slab_desc(Cfg::kDescHi, a_tap + (uint32_t)a * kAcc16 + (uint32_t)(k * 2)),
+                                          slab_desc(Cfg::kDescHi, b_lo + (uint32_t)(k * 2)), Cfg::kIdesc,
+                                          (tap == 0 && k == 0) ? acc_first : 1u);
+                        }
+                        if (tap % TPS == TPS - 1) umma_commit(&b_empty[sb_i]);
+                        if (tap == 8) {
+                            umma_commit(&a_empty[sa_i]);
+                            if (cb == cblocks - 1) umma_commit(&tfull_bar[buf]);
+                        }
+                    }
+                    __syncwarp();
+                    if (tap % TPS == TPS - 1) {
+                        if (++sb_i == stages_b) { sb_i = 0; pb ^= 1; }
+                    }
+                }
+                if (++sa_i == stages_a) { sa_i = 0; pa ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 3..10) =====================
+        const int quarter = warp & 3;
+        const int half = (warp - 3) >> 2;
+        const int et = threadIdx.x - 96;  // 0..255
+        // accumulator columns [0, ACCS*BLOCK_N) of the tile: this warp owns [cbeg, cbeg + kSpan)
+        constexpr int kSpan = ACCS * BLOCK_N / 2;
+        const int cbeg = half * kSpan;
+        const int img_pos = prm.hp * prm.wp;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t buf_phase = (it >> 1) & 1;
+            const int m_tile = tile / prm.tiles_n;
+            const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
+            float2 *sab = s_ab + buf * BLOCK_N;
+            if (et < BLOCK_N) sab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+
+            mbar_wait(&tfull_bar[buf], buf_phase, 6);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = cbeg; cc < cbeg + kSpan; cc += 64) {
+                const int acc = cc / BLOCK_N;
+                const int col = cc - acc * BLOCK_N;
+                const int p = m_tile * kTileM + acc * kBlockM + quarter * 32 + lane;
+                const bool in_range = p < prm.total_pos;
+                const int b = p / img_pos;
+                const int rem = p - b * img_pos;
+                const int y = rem / prm.wp;
+                const int x = rem - y * prm.wp;
+                const bool valid = in_range && (y < prm.h) && (x < prm.w);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                       (uint32_t)((buf * ACCS + acc) * BLOCK_N + col);
+                if constexpr (BLOCK_N >= 64) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(taddr, v0);
+                    tmem_ld32(taddr + 32u, v1);
+                    tmem_ld_wait();
+                    slab_epilogue_chunk(prm, v0, sab, col, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk(prm, v1, sab, col + 32, n0, p, b, y, x, in_range, valid);
+                } else {  // BLOCK_N == 32 (kSpan == 32): one chunk of one accumulator
+                    uint32_t v0[32];
+                    tmem_ld32(taddr, v0);
+                    tmem_ld_wait();
+                    slab_epilogue_chunk(prm, v0, sab, col, n0, p, b, y, x, in_range, valid);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)Cfg::kTmemCols)
+                     : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------
+// (BLOCK_N, BLOCK_K, ACCS, TPS): weight stages of 16-36 KB
+#define Y2_FOR_EACH_SLAB_CFG(X) \
+    X(256, 64, 1, 1) X(128, 64, 2, 1) X(64, 64, 2, 3) X(32, 64, 2, 9) X(256, 32, 1, 1) X(128, 32, 2, 3) \
+    X(64, 32, 2, 9) X(32, 32, 2, 9)
+
+static int slab_tps(int bn, int bk)
+{
+#define Y2_CASE(BN, BK, ACCS, TPS) \
+    if (bn == BN && bk == BK) return TPS;
+    Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
+#undef Y2_CASE
+    return 0;
+}
+
+template <int BN, int BK, int ACCS, int TPS>
+static int slab_prepare_cfg()
+{
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    Y2_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<BN, BK, ACCS, TPS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[dev] = true;
+    }
+    return Y2_OK;
+}
+
+int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
+{
+    if (d->ksize != 3) return Y2_EINVAL;
+    const int bn = d->block_n;
+    const int accs = bn == 256 ? 1 : 2;
+    const int tile_m = accs * kBlockM;
+    const int bk = d->block_k;
+    const int tps = slab_tps(bn, bk);
+    if (!tps || d->npad % bn) return Y2_EINVAL;
+    const int hp = d->h + 1, wp = d->w + 1;
+    const long long total = (long long)d->batch * hp * wp;
+    const int row_bytes = bk * 2;
+    const int halo = wp + 1;
+    const int slab_rows = tile_m + 2 * halo;
+    const int loads = (slab_rows + 255) / 256;
+    int box_rows = (slab_rows + loads - 1) / loads;
+    box_rows = (box_rows + 15) / 16 * 16;
+    if (box_rows > 256) return Y2_EINVAL;
+    const int slab_bytes = loads * box_rows * row_bytes;  // multiple of 1024
+    const int b_stage = tps * bn * bk * 2;
+    const int aux = 2 * bn * 8 + 512;
+    const int budget = 227 * 1024 - 1024 - aux;
+    const int stages_a = 2;
+    int stages_b = (budget - stages_a * slab_bytes) / b_stage;
+    if (stages_b > kSlabMaxStagesB) stages_b = kSlabMaxStagesB;
+    if (stages_b < 2 || (tps == 1 && stages_b < 3)) return Y2_EINVAL;
+    const int ktot = 9 * d->cin;
+    int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
+                            (uint32_t)bk, (uint32_t)box_rows, bk);
+    if (rc == Y2_OK)
+        rc = encode_2d_bf16(&pl->tm_b, d->wt, (uint64_t)ktot, (uint64_t)d->npad, (uint64_t)ktot * 2, (uint32_t)bk,
+                            (uint32_t)bn, bk);
+    if (rc != Y2_OK) return rc;
+    SlabParams &p = pl->slab;
+    p.cblocks = d->cin / bk;
+    p.wp = wp;
+    p.hp = hp;
+    p.h = d->h;
+    p.w = d->w;
+    p.total_pos = (int)total;
+    p.tiles_m = (int)((total + tile_m - 1) / tile_m);
+    p.tiles_n = d->npad / bn;
+    p.halo = halo;
+    p.slab_loads = loads;
+    p.box_rows = box_rows;
+    p.slab_bytes = slab_bytes;
+    p.stages_a = stages_a;
+    p.stages_b = stages_b;
+    p.cout = d->cout;
+    p.act = d->act;
+    p.out_mode = d->out_mode;
+    p.out_cs = d->out_cs;
+    p.alpha = d->alpha;
+    p.beta = d->beta;
+    p.out = d->out;
+    pl->variant = kVariantSlab;
+    pl->block_n = bn;
+    pl->block_k = bk;
+    pl->smem_bytes = (size_t)stages_a * slab_bytes + (size_t)stages_b * b_stage + aux + 1024;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int sms = sm_count();
+    pl->grid = tiles < sms ? tiles : sms;
+#define Y2_CASE(BN, BK, ACCS, TPS) \
+    if (bn == BN && bk == BK) return slab_prepare_cfg<BN, BK, ACCS, TPS>();
+    Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
+#undef Y2_CASE
+    return Y2_EINVAL;
+}
+
+int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
+{
+#define Y2_CASE(BN, BK, ACCS, TPS)                                                                        \
+    if (pl->block_n == BN && pl->block_k == BK) {                                                         \
+        conv_slab_kernel<BN, BK, ACCS, TPS><<<pl->grid, kSlabThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, \
+                                                                                            pl->slab);    \
+        Y2_LAUNCH_CHECK();                                                                                \
+        return Y2_OK;                                                                                     \
+    }
+    Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
+#undef Y2_CASE
+    set_error("slab_plan_launch: no kernel for block_n=%d block_k=%d", pl->block_n, pl->block_k);
+    return Y2_EINVAL;
+}
+
+} // namespace y2

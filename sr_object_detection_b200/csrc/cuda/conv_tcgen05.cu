@@ -16,34 +16,17 @@
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue.
 // Tile = 128 positions x BLOCK_N filters, accumulators double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-#include "y2_common.cuh"
+#include "conv_plan.cuh"
 
 #include <mutex>
 #include <new>
+#include <stdlib.h>
+#include <string.h>
 
 namespace y2 {
 
-constexpr int kBlockM = 128;
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
-
-struct ConvParams {
-    int taps;        // 1 or 9
-    int ksize;       // 1 or 3
-    int cblocks;     // cin / BLOCK_K
-    int wp, hp;      // padded row pitch / rows per image
-    int h, w;
-    int total_pos;   // B * hp * wp
-    int tiles_m, tiles_n;
-    int cout;        // channels stored
-    int act;
-    int out_mode;
-    int out_cs;
-    int stages;
-    const float *alpha;
-    const float *beta;
-    void *out;
-};
 
 template <int BLOCK_N, int BLOCK_K>
 struct ConvCfg {
@@ -114,46 +97,53 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / prm.tiles_n;
-                const int n_tile = tile - m_tile * prm.tiles_n;
-                const int p0 = m_tile * kBlockM;
-                const int n0 = n_tile * BLOCK_N;
-                int kb = 0;
-                for (int tap = 0; tap < prm.taps; ++tap) {
-                    int shift = 0;
-                    if (prm.ksize == 3) shift = (tap / 3 - 1) * prm.wp + (tap % 3 - 1);
-                    for (int cb = 0; cb < prm.cblocks; ++cb, ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        // ===================== TMA producer (whole warp waits, one elected lane issues) ==========
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = tile / prm.tiles_n;
+            const int n_tile = tile - m_tile * prm.tiles_n;
+            const int p0 = m_tile * kBlockM;
+            const int n0 = n_tile * BLOCK_N;
+            int kb = 0;
+            for (int tap = 0; tap < prm.taps; ++tap) {
+                int shift = 0;
+                if (prm.ksize == 3) shift = (tap / 3 - 1) * prm.wp + (tap % 3 - 1);
+                for (int cb = 0; cb < prm.cblocks; ++cb, ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    if (elect_one_sync()) {
                         uint8_t *sa = smem + (size_t)stage * Cfg::kStageBytes;
                         uint8_t *sb = sa + Cfg::kABytes;
                         mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                         tma_load_2d(&tm_a, &full_bar[stage], sa, cb * BLOCK_K, p0 + shift);
                         tma_load_2d(&tm_b, &full_bar[stage], sb, kb * BLOCK_K, n0);
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        uint32_t tok = 0;  // early try_wait on the next stage (its latency overlaps the MMA issue)
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const bool last_tile = tile + (int)gridDim.x >= total_tiles;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                if (!tok) mbar_wait(&full_bar[stage], phase, 3);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase, 3);
-                    tc_fence_after();
+                int ns = stage + 1;
+                uint32_t np = phase;
+                if (ns == stages) { ns = 0; np ^= 1; }
+                tok = (last_tile && kb == kblocks - 1) ? 0u : mbar_test_wait(&full_bar[ns], np);
+                if (elect_one_sync()) {
                     const uint32_t sa = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
                     const uint32_t sb = sa + Cfg::kABytes;
                     const uint64_t adesc = make_kmajor_desc(sa, Cfg::kSBO, Cfg::kLayout);
@@ -165,9 +155,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
                                   Cfg::kIdesc, (uint32_t)((kb | k) != 0));
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
                 }
-                umma_commit(&tfull_bar[acc]);
+                __syncwarp();
+                stage = ns;
+                phase = np;
             }
         }
     } else {
@@ -263,12 +255,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
 // -------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
+EncodeTiledFn get_encode_fn()
 {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
@@ -281,7 +268,7 @@ static EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-static int encode_2d_bf16(CUtensorMap *tm, const void *base, uint64_t dim0, uint64_t dim1,
+int encode_2d_bf16(CUtensorMap *tm, const void *base, uint64_t dim0, uint64_t dim1,
                           uint64_t stride1_bytes, uint32_t box0, uint32_t box1, int block_k)
 {
     EncodeTiledFn fn = get_encode_fn();
@@ -307,15 +294,6 @@ static int encode_2d_bf16(CUtensorMap *tm, const void *base, uint64_t dim0, uint
 }
 
 } // namespace y2
-
-struct y2_conv_plan {
-    CUtensorMap tm_a;
-    CUtensorMap tm_b;
-    y2::ConvParams prm;
-    int block_n, block_k;
-    int grid;
-    size_t smem_bytes;
-};
 
 namespace y2 {
 
@@ -391,6 +369,15 @@ extern "C" int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **out_pla
     }
     const int taps = d->ksize * d->ksize;
     const int ktot = taps * d->cin;
+    // the halo-slab kernel serves every layer it fits; Y2_CONV_VARIANT=pertap forces this file's kernel
+    const char *forced = getenv("Y2_CONV_VARIANT");
+    if (!(forced && !strcmp(forced, "pertap")) && d->block_n <= 256) {
+        if (slab_plan_init(pl, d) == Y2_OK) {
+            *out_plan = pl;
+            return Y2_OK;
+        }
+    }
+    pl->variant = kVariantPerTap;
     int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
                             (uint32_t)d->block_k, kBlockM, d->block_k);
     if (rc == Y2_OK)
@@ -448,6 +435,7 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
     using namespace y2;
     if (!pl) return Y2_EINVAL;
     cudaStream_t st = to_stream(s);
+    if (pl->variant == kVariantSlab) return slab_plan_launch(pl, st);
 #define Y2_CASE(BN, BK) \
     if (pl->block_n == BN && pl->block_k == BK) return launch_cfg<BN, BK>(pl, st);
     Y2_FOR_EACH_CFG(Y2_CASE)
@@ -460,5 +448,6 @@ extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl) { delete pl; }
 
 extern "C" int y2_conv_plan_tiles(const y2_conv_plan *pl)
 {
-    return pl ? pl->prm.tiles_m * pl->prm.tiles_n : 0;
+    if (!pl) return 0;
+    return pl->variant == y2::kVariantSlab ? pl->slab.tiles_m * pl->slab.tiles_n : pl->prm.tiles_m * pl->prm.tiles_n;
 }

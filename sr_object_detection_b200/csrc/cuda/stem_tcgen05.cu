@@ -179,16 +179,16 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv_pool_kernel(const S
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == 4) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint64_t bdesc = make_kmajor_desc(smem_u32(sm.w), 512, 4);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&sm.t_empty[s], ph ^ 1, 11);
-                mbar_wait(&sm.a_full[s], ph, 12);
-                tc_fence_after();
+        // ===================== MMA issuer (whole warp waits, one elected lane issues) ===========
+        const uint64_t bdesc = make_kmajor_desc(smem_u32(sm.w), 512, 4);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(&sm.t_empty[s], ph ^ 1, 11);
+            mbar_wait(&sm.a_full[s], ph, 12);
+            tc_fence_after();
+            if (elect_one_sync()) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint64_t adesc = make_kmajor_desc(smem_u32(sm.a[s][q]), 512, 4);
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_conv_pool_kernel(const S
                 umma_commit(&sm.a_empty[s]);
                 umma_commit(&sm.t_full[s]);
             }
+            __syncwarp();
         }
     } else {
         // ===================== epilogue: max over the window, affine, leaky, store =====================

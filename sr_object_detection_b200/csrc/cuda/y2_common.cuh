@@ -69,6 +69,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity
         : "memory");
     return ok;
 }
+// Non-blocking probe (never suspends the thread, unlike try_wait).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag)
 {
@@ -81,6 +94,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
             __trap();
         }
     }
+}
+
+// One lane of the (converged) warp gets 1.  Unlike `lane == 0`, ptxas knows a single thread is active
+// under this predicate, so the uniform-datapath instructions behind it (UTCHMMA, UTMALDG, UTCBAR)
+// are emitted straight-line instead of inside a per-active-thread ELECT/BRA.U.ANY loop.
+__device__ __forceinline__ uint32_t elect_one_sync()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred;
 }
 
 __device__ __forceinline__ void fence_barrier_init()

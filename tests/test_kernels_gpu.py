@@ -50,11 +50,27 @@ CONV_CASES = [
     (1, 1024, 13, 13, 512, 1, 256, 64, ACT_LINEAR),
     (2, 32, 52, 52, 32, 1, 32, 32, ACT_LEAKY),
     (64, 64, 13, 13, 64, 3, 64, 64, ACT_LEAKY),
+    # wide rows: the halo slab spans several TMA loads (104 -> 2 loads, 208 -> 3 loads of 64-byte rows)
+    (2, 64, 104, 104, 128, 3, 128, 64, ACT_LEAKY),
+    (1, 32, 208, 208, 64, 3, 64, 32, ACT_LEAKY),
+    (3, 128, 52, 52, 256, 3, 256, 64, ACT_LEAKY),
+    (5, 128, 17, 23, 64, 1, 64, 64, ACT_LINEAR),
 ]
 
 
+@pytest.fixture(params=["slab", "pertap"])
+def conv_variant(request, monkeypatch):
+    """Both implicit-GEMM kernels stay under test: the halo-slab kernel (default) and the per-tap
+    fallback (Y2_CONV_VARIANT=pertap is read at plan creation)."""
+    if request.param == "pertap":
+        monkeypatch.setenv("Y2_CONV_VARIANT", "pertap")
+    else:
+        monkeypatch.delenv("Y2_CONV_VARIANT", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "b%d_c%d_%dx%d_n%d_k%d_bn%d_bk%d_a%d" % c)
-def test_conv_bf16_matches_fp32_reference(case):
+def test_conv_bf16_matches_fp32_reference(case, conv_variant):
     batch, cin, h, w, cout, ksize, block_n, block_k, act = case
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(1234 + cin + cout)
@@ -83,7 +99,7 @@ def test_conv_bf16_matches_fp32_reference(case):
     assert out[:, :, w, :].abs().max().item() == 0
 
 
-def test_conv_f32_flat_head_125():
+def test_conv_f32_flat_head_125(conv_variant):
     """1x1 linear head with 125 filters written as fp32 [B][H*W][125] (region-layer input)."""
     dev = torch.device("cuda:0")
     batch, cin, h, w, cout = 3, 1024, 13, 13, 125
@@ -106,7 +122,7 @@ def test_conv_f32_flat_head_125():
     assert err <= 1e-4, f"max err / max|ref| = {err:.3e}"
 
 
-def test_conv_channel_slice_in_concat_buffer():
+def test_conv_channel_slice_in_concat_buffer(conv_variant):
     """Output written at a channel offset of a wider buffer (in-place route) and input read
     from a channel slice; neighbouring channels must be untouched."""
     dev = torch.device("cuda:0")
