@@ -157,6 +157,13 @@ int y2_maxpool(const void *in, int in_cs, void *out, int out_cs, int batch, int 
 int y2_reorg(const void *in, int in_cs, void *out, int out_cs, int batch, int c, int h,
              int w, int stride, y2_stream_t s);
 
+/* The same permutation through a lookup table built once per layer (the index map costs ~15 integer
+ * divisions per element): y2_reorg_table fills table[(h/s)*(w/s)*(c*s*s)] with the element offset of
+ * every output element's source inside one padded input image; y2_reorg_gather applies it. */
+int y2_reorg_table(int *table, int in_cs, int c, int h, int w, int stride, y2_stream_t s);
+int y2_reorg_gather(const void *in, int in_cs, void *out, int out_cs, const int *table, int batch,
+                    int c, int h, int w, int stride, y2_stream_t s);
+
 /* ---- route fallback copy (replaces route_layer.c:104-117 copy_ongpu loop); the
  *      planner normally aliases producers into the concat buffer instead ------------- */
 int y2_copy_channels(const void *in, int in_cs, void *out, int out_cs, int batch, int c,

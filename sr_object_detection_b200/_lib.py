@@ -99,6 +99,8 @@ def _declare(lib: C.CDLL) -> None:
         "y2_nchw_to_flat_f32": (i, [vp, vp, i, i, i, vp]),
         "y2_maxpool": (i, [vp, i, vp, i, i, i, i, i, i, i, i, i, i, vp]),
         "y2_reorg": (i, [vp, i, vp, i, i, i, i, i, i, vp]),
+        "y2_reorg_table": (i, [vp, i, i, i, i, i, vp]),
+        "y2_reorg_gather": (i, [vp, i, vp, i, vp, i, i, i, i, i, vp]),
         "y2_copy_channels": (i, [vp, i, vp, i, i, i, i, i, vp]),
         "y2_region_forward": (i, [vp, vp, i, i, i, i, i, i, vp, vp, vp]),
         "y2_region_boxes": (i, [vp, vp, vp, vp, i, i, i, i, i, f, f, f, i, i, i, vp, vp, i, vp]),

@@ -39,6 +39,7 @@ struct SlabParams {
     int slab_bytes;        // bytes per slab stage
     int stages_a, stages_b;
     int cout, act, out_mode, out_cs;
+    int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
     const float *alpha;
     const float *beta;
     void *out;

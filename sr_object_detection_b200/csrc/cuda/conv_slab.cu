@@ -63,6 +63,7 @@ __device__ __forceinline__ uint64_t slab_desc(uint32_t hi, uint32_t lo)
 }
 
 // one 32-column chunk of one accumulator row: affine + activation + store
+template <int ACT>
 __device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const uint32_t (&v)[32], const float2 *sab,
                                                     int c0, int n0, int p, int b, int y, int x, bool in_range,
                                                     bool valid)
@@ -74,10 +75,10 @@ __device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const
         const float4 q = ab4[j];  // (alpha, beta) of two filters
         float t0 = fmaf(__uint_as_float(v[2 * j]), q.x, q.y);
         float t1 = fmaf(__uint_as_float(v[2 * j + 1]), q.z, q.w);
-        if (prm.act == Y2_ACT_LEAKY) {
-            t0 = (t0 > 0.f) ? t0 : 0.1f * t0;
-            t1 = (t1 > 0.f) ? t1 : 0.1f * t1;
-        } else if (prm.act == Y2_ACT_LOGISTIC) {
+        if (ACT == Y2_ACT_LEAKY) {  // max(t, 0.1 t) == (t > 0 ? t : 0.1 t) for every finite t
+            t0 = fmaxf(t0, 0.1f * t0);
+            t1 = fmaxf(t1, 0.1f * t1);
+        } else if (ACT == Y2_ACT_LOGISTIC) {
             t0 = 1.f / (1.f + __expf(-t0));
             t1 = 1.f / (1.f + __expf(-t1));
         }
@@ -279,51 +280,82 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int quarter = warp & 3;
         const int half = (warp - 3) >> 2;
         const int et = threadIdx.x - 96;  // 0..255
-        // accumulator columns [0, ACCS*BLOCK_N) of the tile: this warp owns [cbeg, cbeg + kSpan)
+        // this warp's share of the tile: with two accumulators, warps 3-6 drain the first and warps
+        // 7-10 the second; with one, each group drains half of its columns
         constexpr int kSpan = ACCS * BLOCK_N / 2;
-        const int cbeg = half * kSpan;
+        const int acc = (ACCS == 2) ? half : 0;
+        const int col0 = (ACCS == 2) ? 0 : half * kSpan;
         const int img_pos = prm.hp * prm.wp;
+        const bool ab_lane = et < BLOCK_N;
         int it = 0;
+        // (alpha, beta) of the first tile; later tiles are prefetched one tile ahead
+        if ((int)blockIdx.x < total_tiles && ab_lane) {
+            const int n0 = ((int)blockIdx.x % prm.tiles_n) * BLOCK_N;
+            s_ab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
             const int m_tile = tile / prm.tiles_n;
             const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
-            float2 *sab = s_ab + buf * BLOCK_N;
-            if (et < BLOCK_N) sab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float2 *sab = s_ab + (prm.tiles_n > 1 ? buf * BLOCK_N : 0);
+            // one filter block per layer: (alpha, beta) never change and the epilogue warps stay decoupled
+            const bool reload = prm.tiles_n > 1 || it == 0 || prm.couple;
+            if (reload) asm volatile("bar.sync 1, 256;" ::: "memory");  // sab[buf] written, sab[buf^1] free
+            const int next = tile + (int)gridDim.x;
+            float2 ab_next = make_float2(1.f, 0.f);
+            if (prm.tiles_n > 1 && next < total_tiles && ab_lane) {
+                const int nn = (next % prm.tiles_n) * BLOCK_N;
+                ab_next = make_float2(__ldg(prm.alpha + nn + et), __ldg(prm.beta + nn + et));
+            }
+            const int p = m_tile * kTileM + acc * kBlockM + quarter * 32 + lane;
+            const bool in_range = p < prm.total_pos;
+            const int b = p / img_pos;
+            const int rem = p - b * img_pos;
+            const int y = rem / prm.wp;
+            const int x = rem - y * prm.wp;
+            const bool valid = in_range && (y < prm.h) && (x < prm.w);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                   (uint32_t)((buf * ACCS + acc) * BLOCK_N + col0);
 
             mbar_wait(&tfull_bar[buf], buf_phase, 6);
             tc_fence_after();
+            if constexpr (kSpan >= 64) {
 #pragma unroll 1
-            for (int cc = cbeg; cc < cbeg + kSpan; cc += 64) {
-                const int acc = cc / BLOCK_N;
-                const int col = cc - acc * BLOCK_N;
-                const int p = m_tile * kTileM + acc * kBlockM + quarter * 32 + lane;
-                const bool in_range = p < prm.total_pos;
-                const int b = p / img_pos;
-                const int rem = p - b * img_pos;
-                const int y = rem / prm.wp;
-                const int x = rem - y * prm.wp;
-                const bool valid = in_range && (y < prm.h) && (x < prm.w);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                       (uint32_t)((buf * ACCS + acc) * BLOCK_N + col);
-                if constexpr (BLOCK_N >= 64) {
+                for (int c = 0; c < kSpan; c += 64) {
                     uint32_t v0[32], v1[32];
-                    tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + 32u, v1);
+                    tmem_ld32(taddr + (uint32_t)c, v0);
+                    tmem_ld32(taddr + (uint32_t)(c + 32), v1);
                     tmem_ld_wait();
-                    slab_epilogue_chunk(prm, v0, sab, col, n0, p, b, y, x, in_range, valid);
-                    slab_epilogue_chunk(prm, v1, sab, col + 32, n0, p, b, y, x, in_range, valid);
-                } else {  // BLOCK_N == 32 (kSpan == 32): one chunk of one accumulator
-                    uint32_t v0[32];
-                    tmem_ld32(taddr, v0);
-                    tmem_ld_wait();
-                    slab_epilogue_chunk(prm, v0, sab, col, n0, p, b, y, x, in_range, valid);
+                    if (c + 64 >= kSpan) {  // accumulator drained into registers: hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[buf]);
+                    }
+                    if (prm.act == Y2_ACT_LEAKY) {
+                        slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                        slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    } else if (prm.act == Y2_ACT_LINEAR) {
+                        slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                        slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    } else {
+                        slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                        slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    }
                 }
+            } else {  // BLOCK_N == 32, two accumulators: one 32-column chunk per warp
+                uint32_t v0[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[buf]);
+                if (prm.act == Y2_ACT_LEAKY)
+                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0, n0, p, b, y, x, in_range, valid);
+                else if (prm.act == Y2_ACT_LINEAR)
+                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v0, sab, col0, n0, p, b, y, x, in_range, valid);
+                else
+                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v0, sab, col0, n0, p, b, y, x, in_range, valid);
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[buf]);
+            if (prm.tiles_n > 1 && next < total_tiles && ab_lane) s_ab[(buf ^ 1) * BLOCK_N + et] = ab_next;
         }
     }
 
@@ -422,6 +454,9 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.alpha = d->alpha;
     p.beta = d->beta;
     p.out = d->out;
+    // measured on B200: lock-stepped epilogue warps write 128-byte rows (<= 64 filters) 10% faster, wider
+    // rows prefer free-running warps
+    p.couple = bn <= 64;
     pl->variant = kVariantSlab;
     pl->block_n = bn;
     pl->block_k = bk;

@@ -238,6 +238,64 @@ __global__ void reorg_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
     }
 }
 
+// The same permutation through a per-layer lookup table (built once at plan time): the index map
+// costs ~15 integer divisions per element, the table makes the layer a plain gather.
+// table[(oy*ow + ox)*oc + ch] = element offset of the source inside one padded input image.
+__global__ void reorg_table_kernel(int *__restrict__ table, int in_cs, int c, int h, int w, int stride)
+{
+    const int oc = c * stride * stride, oh = h / stride, ow = w / stride;
+    const int wp = w + 1;
+    const int out_c = c / (stride * stride);
+    const int total = oh * ow * oc;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ch = t % oc;
+        const int pos = t / oc;
+        const int ox = pos % ow, oy = pos / ow;
+        const int in_index = ox + ow * (oy + oh * ch);
+        const int i = in_index % w;
+        const int j = (in_index / w) % h;
+        const int k = in_index / (w * h);
+        const int c2 = k % out_c;
+        const int offset = k / out_c;
+        const int w2 = i * stride + offset % stride;
+        const int h2 = j * stride + offset / stride;
+        const int out_index = w2 + w * stride * (h2 + h * stride * c2);
+        const int sx = out_index % w;
+        const int sy = (out_index / w) % h;
+        const int sc = out_index / (w * h);
+        table[t] = (sy * wp + sx) * in_cs + sc;
+    }
+}
+
+// one thread per 8 output channels: 8 table entries, 8 two-byte gathers, one 16-byte store
+__global__ void reorg_gather_kernel(const __nv_bfloat16 *__restrict__ in, size_t in_img_elems,
+                                    __nv_bfloat16 *__restrict__ out, int out_cs, const int *__restrict__ table,
+                                    int batch, int oc, int oh, int ow)
+{
+    const int ohp = oh + 1, owp = ow + 1;
+    const int c8 = oc / 8;
+    const long long total = (long long)batch * ohp * owp * c8;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % c8);
+        const long long p = t / c8;
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ox < ow && oy < oh) {
+            const int4 *tp = reinterpret_cast<const int4 *>(table + ((size_t)(oy * ow + ox) * oc + g * 8));
+            const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+            const unsigned short *src = reinterpret_cast<const unsigned short *>(in) + (size_t)b * in_img_elems;
+            v.x = (uint32_t)__ldg(src + t0.x) | ((uint32_t)__ldg(src + t0.y) << 16);
+            v.y = (uint32_t)__ldg(src + t0.z) | ((uint32_t)__ldg(src + t0.w) << 16);
+            v.z = (uint32_t)__ldg(src + t1.x) | ((uint32_t)__ldg(src + t1.y) << 16);
+            v.w = (uint32_t)__ldg(src + t1.z) | ((uint32_t)__ldg(src + t1.w) << 16);
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) = v;
+    }
+}
+
 // route fallback: copy a channel slice between padded buffers of equal extent
 __global__ void copy_channels_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
                                      __nv_bfloat16 *__restrict__ out, int out_cs, long long positions,
@@ -423,6 +481,36 @@ extern "C" int y2_reorg(const void *in, int in_cs, void *out, int out_cs, int ba
     reorg_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>((const __nv_bfloat16 *)in, in_cs,
                                                                  (__nv_bfloat16 *)out, out_cs, batch, c, h, w,
                                                                  stride);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_reorg_table(int *table, int in_cs, int c, int h, int w, int stride, y2_stream_t s)
+{
+    if (!table || stride <= 0 || c % (stride * stride) || h % stride || w % stride) {
+        set_error("y2_reorg_table: c=%d h=%d w=%d not divisible by stride=%d", c, h, w, stride);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)(h / stride) * (w / stride) * c * stride * stride;
+    reorg_table_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(table, in_cs, c, h, w, stride);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_reorg_gather(const void *in, int in_cs, void *out, int out_cs, const int *table, int batch, int c,
+                               int h, int w, int stride, y2_stream_t s)
+{
+    const int oc = c * stride * stride;
+    if (!in || !out || !table || stride <= 0 || c % (stride * stride) || h % stride || w % stride || oc % 8 ||
+        out_cs % 8 || ((uintptr_t)out & 15) || ((uintptr_t)table & 15)) {
+        set_error("y2_reorg_gather: invalid arguments (c=%d h=%d w=%d stride=%d out_cs=%d)", c, h, w, stride, out_cs);
+        return Y2_EINVAL;
+    }
+    const int oh = h / stride, ow = w / stride;
+    const long long total = (long long)batch * (oh + 1) * (ow + 1) * (oc / 8);
+    reorg_gather_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, (size_t)(h + 1) * (w + 1) * in_cs, (__nv_bfloat16 *)out, out_cs, table, batch, oc,
+        oh, ow);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

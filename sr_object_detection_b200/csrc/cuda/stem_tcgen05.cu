@@ -90,7 +90,7 @@ __device__ __forceinline__ void stem_issue_loads(const StemParams &p, float *sta
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kStemThreads, 1) stem_conv_pool_kernel(const StemParams p)
+__global__ void __launch_bounds__(kStemThreads, 2) stem_conv_pool_kernel(const StemParams p)
 {
     extern __shared__ uint8_t stem_raw[];
     StemSmem &sm = *reinterpret_cast<StemSmem *>(stem_raw + ((1024u - (smem_u32(stem_raw) & 1023u)) & 1023u));
@@ -317,7 +317,9 @@ extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w
     int rc = y2_stem_prepare();
     if (rc != Y2_OK) return rc;
     const int sms = sm_count();
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    // two co-resident CTAs per SM (83 KB smem, 256 TMEM columns, <= 112 registers each): the producer warps
+    // of one CTA are latency-bound, a second CTA fills the bubbles
+    const int grid = p.total_tiles < 2 * sms ? p.total_tiles : 2 * sms;
     stem_conv_pool_kernel<<<grid, kStemThreads, smem, to_stream(s)>>>(p);
     Y2_LAUNCH_CHECK();
     return Y2_OK;

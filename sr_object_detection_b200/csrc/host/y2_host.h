@@ -45,6 +45,8 @@ typedef struct y2_layer_rt {
     int wt_dirty;
     /* input packing for a non-patch first layer */
     void *packed_in;
+    /* reorg */
+    int *reorg_table;   /* gather table of the layer (y2_reorg_table) */
     /* region */
     float *boxes_dev, *probs_dev;
     float *biases_dev;

@@ -443,6 +443,7 @@ static void free_layer_rt(layer *l)
     y2_free(r->beta_dev);
     y2_free(r->patches);
     y2_free(r->packed_in);
+    y2_free(r->reorg_table);
     y2_free(r->boxes_dev);
     y2_free(r->probs_dev);
     y2_free(r->biases_dev);
@@ -873,6 +874,12 @@ void y2_plan_network(network *net)
             else if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->kpad));
             else if (i == 0) r->packed_in = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->cin_pad));
             y2_push_convolutional_layer(l);
+        } else if (l->type == REORG) {
+            y2_layer_rt *pr = (y2_layer_rt *)net->layers[i - 1].b200;
+            if (l->out_c % 8 == 0 && r->out_cs % 8 == 0) {
+                Y2_CHECK(y2_malloc((void **)&r->reorg_table, (size_t)l->out_h * l->out_w * l->out_c * sizeof(int)));
+                Y2_CHECK(y2_reorg_table(r->reorg_table, pr->out_cs, l->c, l->h, l->w, l->stride, 0));
+            }
         } else if (l->type == REGION) {
             const size_t total = (size_t)l->w * l->h * l->n;
             r->probs_classes = l->map ? 200 : l->classes;
@@ -951,8 +958,12 @@ void forward_reorg_layer_gpu(layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
-    Y2_CHECK(y2_reorg(pr->out, pr->out_cs, r->out, r->out_cs, l.batch, l.c, l.h, l.w, l.stride,
-                      net_stream(state.net)));
+    if (r->reorg_table)
+        Y2_CHECK(y2_reorg_gather(pr->out, pr->out_cs, r->out, r->out_cs, r->reorg_table, l.batch, l.c, l.h, l.w,
+                                 l.stride, net_stream(state.net)));
+    else
+        Y2_CHECK(y2_reorg(pr->out, pr->out_cs, r->out, r->out_cs, l.batch, l.c, l.h, l.w, l.stride,
+                          net_stream(state.net)));
     count_launch(state.net, 1);
 }
 

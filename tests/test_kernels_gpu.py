@@ -257,6 +257,14 @@ def test_reorg_matches_reference_index_map():
     got = out[:, :oh, :ow, off:off + oc].permute(0, 3, 1, 2).float()
     assert torch.equal(got, ref)
     assert (out[..., oc:] == 2.0).all()
+    # the table-driven gather the network schedule uses must produce the same bytes
+    table = torch.zeros(oh * ow * oc, dtype=torch.int32, device=dev)
+    out2 = torch.full((batch, oh + 1, ow + 1, out_cs), 2.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_reorg_table(table.data_ptr(), c, c, h, w, stride, _stream()))
+    _lib.check(lib.y2_reorg_gather(x_p.data_ptr(), c, out2.data_ptr() + off * 2, out_cs, table.data_ptr(), batch, c, h,
+                                   w, stride, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
 
 
 def test_copy_channels_route_fallback():
