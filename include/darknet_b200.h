@@ -264,6 +264,17 @@ void network_detect_device(network net, float thresh, float nms, y2_detection *d
 /* upload + forward + detect, one synchronisation */
 void network_detect_batch(network net, const float *input, float thresh, float nms,
                           y2_detection *dets, int *counts, int max_det);
+/* Two-deep pipeline over the same work: network_detect_submit queues the H2D copy of a batch on a
+ * copy stream and its forward + decode + NMS + D2H behind it on the network's stream, then returns;
+ * network_detect_wait blocks for the OLDEST submitted batch and hands out its detections.  With two
+ * batches in flight the upload of batch i+1 overlaps the forward pass of batch i.  Both return the
+ * slot (0/1) the batch used.  network_pipeline_staging(net, slot) is the slot's pinned input buffer
+ * (slots alternate 0,1,0,... starting at the oldest free one); passing any other pointer costs a
+ * host-side copy into it.  Not to be mixed with the synchronous calls while batches are in flight. */
+float *network_pipeline_staging(network net, int slot);
+int network_pipeline_next_slot(network net); /* slot the next network_detect_submit will use */
+int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det);
+int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det);
 /* Block until the network's stream is idle. */
 void network_sync(network net);
 /* Device stream the network runs on (cudaStream_t) — for timing with CUDA events. */

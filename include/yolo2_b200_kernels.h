@@ -69,6 +69,8 @@ typedef void *y2_event_t;
 int y2_event_create(y2_event_t *e);
 int y2_event_record(y2_event_t e, y2_stream_t s);
 int y2_event_elapsed_ms(y2_event_t a, y2_event_t b, float *ms);
+int y2_event_sync(y2_event_t e);                       /* host blocks until the event has fired */
+int y2_stream_wait_event(y2_stream_t s, y2_event_t e);  /* later work of s waits for e on the device */
 int y2_event_destroy(y2_event_t e);
 
 /* ---- convolution (replaces convolutional_kernels.cu:77-131

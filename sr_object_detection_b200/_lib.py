@@ -85,6 +85,8 @@ def _declare(lib: C.CDLL) -> None:
         "y2_event_create": (i, [C.POINTER(vp)]),
         "y2_event_record": (i, [vp, vp]),
         "y2_event_elapsed_ms": (i, [vp, vp, C.POINTER(f)]),
+        "y2_event_sync": (i, [vp]),
+        "y2_stream_wait_event": (i, [vp, vp]),
         "y2_event_destroy": (i, [vp]),
         "y2_conv_plan_create": (i, [C.POINTER(ConvDesc), C.POINTER(vp)]),
         "y2_conv_plan_launch": (i, [vp, vp]),

@@ -163,6 +163,16 @@ extern "C" int y2_event_elapsed_ms(y2_event_t a, y2_event_t b, float *ms)
     Y2_CUDA_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
     return Y2_OK;
 }
+extern "C" int y2_event_sync(y2_event_t e)
+{
+    Y2_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)e));
+    return Y2_OK;
+}
+extern "C" int y2_stream_wait_event(y2_stream_t s, y2_event_t e)
+{
+    Y2_CUDA_CHECK(cudaStreamWaitEvent(to_stream(s), (cudaEvent_t)e, 0));
+    return Y2_OK;
+}
 extern "C" int y2_event_destroy(y2_event_t e)
 {
     if (e) Y2_CUDA_CHECK(cudaEventDestroy((cudaEvent_t)e));

@@ -192,3 +192,116 @@ void network_detect_batch(network net, const float *input, float thresh, float n
     network_forward_device(net);
     network_detect_device(net, thresh, nms, dets, counts, max_det);
 }
+
+/* ---- two-deep pipeline: the H2D copy of batch i+1 overlaps the forward pass of batch i ---------- */
+static void pipe_init(network net)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (rt->pipe_ready) return;
+    Y2_CHECK(y2_set_device(rt->device));
+    Y2_CHECK(y2_stream_create(&rt->copy_stream));
+    rt->pipe[0].in_dev = rt->in_dev;
+    rt->pipe[0].in_pinned = rt->in_pinned;
+    Y2_CHECK(y2_malloc((void **)&rt->pipe[1].in_dev, rt->in_bytes));
+    Y2_CHECK(y2_host_alloc((void **)&rt->pipe[1].in_pinned, rt->in_bytes));
+    for (int s = 0; s < 2; ++s) {
+        Y2_CHECK(y2_event_create(&rt->pipe[s].ev_h2d));
+        Y2_CHECK(y2_event_create(&rt->pipe[s].ev_done));
+        rt->pipe[s].busy = 0;
+    }
+    rt->pipe_head = 0;
+    rt->pipe_inflight = 0;
+    rt->pipe_ready = 1;
+}
+
+static void pipe_reserve_dets(y2_net_rt *rt, int s, int batch, int max_det)
+{
+    struct y2_pipe_slot *ps = &rt->pipe[s];
+    if (ps->det_cap >= max_det && ps->det_dev) return;
+    y2_free(ps->det_dev);
+    y2_host_free(ps->det_pinned);
+    y2_free(ps->cnt_dev);
+    y2_host_free(ps->cnt_pinned);
+    const int cap_b = batch > rt->cap_batch ? batch : rt->cap_batch;
+    const size_t nd = (size_t)cap_b * max_det;
+    Y2_CHECK(y2_malloc((void **)&ps->det_dev, nd * sizeof(y2_det)));
+    Y2_CHECK(y2_host_alloc((void **)&ps->det_pinned, nd * sizeof(y2_det)));
+    Y2_CHECK(y2_malloc((void **)&ps->cnt_dev, (size_t)cap_b * sizeof(int)));
+    Y2_CHECK(y2_host_alloc((void **)&ps->cnt_pinned, (size_t)cap_b * sizeof(int)));
+    ps->det_cap = max_det;
+}
+
+float *network_pipeline_staging(network net, int slot)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt || slot < 0 || slot > 1) error("network_pipeline_staging: bad slot or unplanned network");
+    pipe_init(net);
+    return rt->pipe[slot].in_pinned;
+}
+
+int network_pipeline_next_slot(network net)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt) error("network_pipeline_next_slot: network has no device plan");
+    pipe_init(net);
+    return (rt->pipe_head + rt->pipe_inflight) & 1;
+}
+
+int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt) error("network_detect_submit: network has no device plan");
+    if (net.batch != rt->plan_batch) error("network batch changed without set_batch_network");
+    pipe_init(net);
+    if (rt->pipe_inflight >= 2) error("network_detect_submit: two batches already in flight, call network_detect_wait");
+    Y2_CHECK(y2_set_device(rt->device));
+    const int s = (rt->pipe_head + rt->pipe_inflight) & 1;
+    struct y2_pipe_slot *ps = &rt->pipe[s];
+    layer *l = region_of(net);
+    y2_layer_rt *r = (y2_layer_rt *)l->b200;
+    const int B = net.batch;
+    const int total = l->w * l->h * l->n;
+    const size_t bytes = (size_t)B * net.inputs * sizeof(float);
+    pipe_reserve_dets(rt, s, B, max_det);
+    /* pageable caller memory is staged through the slot's pinned buffer (a host copy; fill
+     * network_pipeline_staging(net, slot) directly to avoid it) */
+    if (input && input != ps->in_pinned) memcpy(ps->in_pinned, input, bytes);
+    Y2_CHECK(y2_memcpy_h2d(ps->in_dev, ps->in_pinned, bytes, rt->copy_stream));
+    Y2_CHECK(y2_event_record(ps->ev_h2d, rt->copy_stream));
+    Y2_CHECK(y2_stream_wait_event(rt->stream, ps->ev_h2d));
+    if (s == 0) y2_run_forward_from(net, ps->in_dev, &rt->graph, &rt->graph_valid);
+    else y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
+    Y2_CHECK(y2_region_boxes((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
+                             l->classes, 1.f, 1.f, thresh, 0, l->classfix,
+                             l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0, rt->stream));
+    if (nms > 0) Y2_CHECK(y2_nms_sort(r->boxes_dev, r->probs_dev, B, total, l->classes, nms, rt->stream));
+    Y2_CHECK(y2_collect(r->boxes_dev, r->probs_dev, B, total, l->classes, thresh, ps->det_dev, ps->cnt_dev,
+                        ps->det_cap, rt->stream));
+    Y2_CHECK(y2_memcpy_d2h(ps->cnt_pinned, ps->cnt_dev, (size_t)B * sizeof(int), rt->stream));
+    Y2_CHECK(y2_memcpy_d2h(ps->det_pinned, ps->det_dev, (size_t)B * ps->det_cap * sizeof(y2_det), rt->stream));
+    Y2_CHECK(y2_event_record(ps->ev_done, rt->stream));
+    ps->busy = 1;
+    rt->pipe_inflight++;
+    return s;
+}
+
+int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt || !rt->pipe_ready || rt->pipe_inflight <= 0) error("network_detect_wait: nothing in flight");
+    const int s = rt->pipe_head;
+    struct y2_pipe_slot *ps = &rt->pipe[s];
+    Y2_CHECK(y2_event_sync(ps->ev_done));
+    const int B = net.batch;
+    for (int b = 0; b < B; ++b) {
+        int c = ps->cnt_pinned[b];
+        counts[b] = c;
+        if (c > max_det) c = max_det;
+        if (c > ps->det_cap) c = ps->det_cap;
+        memcpy(dets + (size_t)b * max_det, ps->det_pinned + (size_t)b * ps->det_cap, (size_t)c * sizeof(y2_det));
+    }
+    ps->busy = 0;
+    rt->pipe_head ^= 1;
+    rt->pipe_inflight--;
+    return s;
+}

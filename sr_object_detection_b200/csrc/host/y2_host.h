@@ -78,6 +78,20 @@ typedef struct y2_net_rt {
     int det_cap, det_batch;
     float *export_dev;   /* fp32 scratch for layer export */
     size_t export_bytes;
+    /* two-deep submit/wait pipeline (network_detect_submit): slot 0 shares in_dev / in_pinned / graph
+     * with the synchronous path, slot 1 has its own input buffers and graph */
+    struct y2_pipe_slot {
+        float *in_dev, *in_pinned;
+        y2_graph_t graph;
+        int graph_valid;
+        y2_det *det_dev, *det_pinned;
+        int *cnt_dev, *cnt_pinned;
+        int det_cap;
+        y2_event_t ev_h2d, ev_done;
+        int busy;
+    } pipe[2];
+    y2_stream_t copy_stream;
+    int pipe_ready, pipe_head, pipe_inflight;
 } y2_net_rt;
 
 static inline y2_net_rt *y2_rt(network net) { return (y2_net_rt *)net.b200; }
@@ -88,6 +102,8 @@ void y2_plan_network(network *net);
 void y2_unplan_network(network *net);
 void y2_push_convolutional_layer(layer *l);
 int y2_output_layer_index(network net);
+void y2_run_forward_from(network net, float *in_dev, y2_graph_t *graph, int *graph_valid);
+void y2_pipe_release(y2_net_rt *rt);
 
 /* layer constructors (y2_layers.c) */
 layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, int stride, int padding,

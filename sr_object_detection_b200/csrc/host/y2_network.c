@@ -459,6 +459,8 @@ static void free_layer_rt(layer *l)
     l->weights_gpu = 0;
 }
 
+static void pipe_free(y2_net_rt *rt);
+
 void y2_unplan_network(network *net)
 {
     y2_net_rt *rt = (y2_net_rt *)net->b200;
@@ -475,6 +477,7 @@ void y2_unplan_network(network *net)
     y2_free(rt->cnt_dev);
     y2_host_free(rt->cnt_pinned);
     y2_free(rt->export_dev);
+    pipe_free(rt);
     y2_stream_destroy(rt->stream);
     free(rt);
     net->b200 = 0;
@@ -653,6 +656,7 @@ static void build_plans(network *net, int batch)
         rt->graph = 0;
     }
     rt->graph_valid = 0;
+    y2_pipe_release(rt);
 }
 
 void y2_plan_network(network *net)
@@ -1072,26 +1076,61 @@ static void ensure_ready(network net)
     if (net.batch != rt->plan_batch) error("network batch changed without set_batch_network");
 }
 
-static void run_forward(network net)
+/* forward pass reading the fp32 NCHW batch at in_dev; the layer list is captured once per input
+ * buffer into *graph and replayed afterwards */
+void y2_run_forward_from(network net, float *in_dev, y2_graph_t *graph, int *graph_valid)
 {
     y2_net_rt *rt = y2_rt(net);
     network_state state;
     memset(&state, 0, sizeof(state));
     state.net = net;
-    state.input = rt->in_dev;
+    state.input = in_dev;
     if (rt->eager || rt->profile) {
         rt->launches = 0;
         forward_network_gpu(net, state);
         return;
     }
-    if (!rt->graph_valid) {
+    if (!*graph_valid) {
         rt->launches = 0;
         Y2_CHECK(y2_graph_begin(rt->stream));
         forward_network_gpu(net, state);
-        Y2_CHECK(y2_graph_end(rt->stream, &rt->graph));
-        rt->graph_valid = 1;
+        Y2_CHECK(y2_graph_end(rt->stream, graph));
+        *graph_valid = 1;
     }
-    Y2_CHECK(y2_graph_launch(rt->graph, rt->stream));
+    Y2_CHECK(y2_graph_launch(*graph, rt->stream));
+}
+
+static void run_forward(network net)
+{
+    y2_net_rt *rt = y2_rt(net);
+    y2_run_forward_from(net, rt->in_dev, &rt->graph, &rt->graph_valid);
+}
+
+/* pipeline state that does not survive a re-plan / batch change */
+void y2_pipe_release(y2_net_rt *rt)
+{
+    if (rt->pipe[1].graph) y2_graph_destroy(rt->pipe[1].graph);
+    rt->pipe[1].graph = 0;
+    rt->pipe[1].graph_valid = 0;
+}
+
+static void pipe_free(y2_net_rt *rt)
+{
+    y2_pipe_release(rt);
+    y2_free(rt->pipe[1].in_dev);
+    y2_host_free(rt->pipe[1].in_pinned);
+    for (int s = 0; s < 2; ++s) {
+        y2_free(rt->pipe[s].det_dev);
+        y2_host_free(rt->pipe[s].det_pinned);
+        y2_free(rt->pipe[s].cnt_dev);
+        y2_host_free(rt->pipe[s].cnt_pinned);
+        if (rt->pipe[s].ev_h2d) y2_event_destroy(rt->pipe[s].ev_h2d);
+        if (rt->pipe[s].ev_done) y2_event_destroy(rt->pipe[s].ev_done);
+    }
+    if (rt->copy_stream) y2_stream_destroy(rt->copy_stream);
+    memset(rt->pipe, 0, sizeof(rt->pipe));
+    rt->copy_stream = 0;
+    rt->pipe_ready = 0;
 }
 
 void network_set_eager(network net, int eager)
@@ -1419,6 +1458,7 @@ void free_network(network net)
         y2_free(rt->cnt_dev);
         y2_host_free(rt->cnt_pinned);
         y2_free(rt->export_dev);
+        pipe_free(rt);
         y2_stream_destroy(rt->stream);
         free(rt);
         (void)tmp;

@@ -136,6 +136,10 @@ def lib() -> C.CDLL:
         "network_forward_device": (None, [Network]),
         "network_detect_device": (None, [Network, f, f, C.POINTER(Detection), _ip, i]),
         "network_detect_batch": (None, [Network, fp, f, f, C.POINTER(Detection), _ip, i]),
+        "network_pipeline_staging": (fp, [Network, i]),
+        "network_pipeline_next_slot": (i, [Network]),
+        "network_detect_submit": (i, [Network, fp, f, f, i]),
+        "network_detect_wait": (i, [Network, C.POINTER(Detection), _ip, i]),
         "network_sync": (None, [Network]),
         "network_stream": (C.c_void_p, [Network]),
         "network_conv_flops": (C.c_double, [Network]),

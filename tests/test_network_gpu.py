@@ -120,3 +120,53 @@ def test_decode_and_nms_bit_exact_on_identical_region_inputs(tmp_path, name, cla
         f"keep set differs in {((got_post != 0) != (ref_post != 0)).sum()} entries"
     assert np.array_equal(got_post, ref_post)
     assert (ref_pre != 0).sum() > (ref_post != 0).sum() > 0  # the case actually suppresses something
+
+
+def test_pipelined_submit_wait_equals_synchronous_detect(tmp_path):
+    """network_detect_submit / network_detect_wait (two batches in flight, H2D of batch i+1 overlapping
+    the forward of batch i) must hand out exactly the detections of the synchronous
+    network_detect_batch, batch by batch and in submission order."""
+    import ctypes as C
+    batch, max_det = 4, 256
+    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", batch)
+    dn.set_gpu_index(0)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    lib = dn.lib()
+    batches = [synth.images(batch, 3, 416, 416, seed=100 + i) for i in range(5)]
+    thresh, nms = 0.02, 0.4  # random-init weights: class scores sit near objectness / classes
+
+    def as_list(dets, counts):
+        out = []
+        for b in range(batch):
+            n = min(counts[b], max_det)
+            out.append([(d.box_index, d.obj_id, d.prob, d.x, d.y, d.w, d.h)
+                        for d in dets[b * max_det:b * max_det + n]])
+        return out
+
+    want = []
+    for x in batches:
+        per_img, _ = dn.network_detect_batch(net, x, thresh, nms, max_det)
+        want.append([[(int(d["box_index"]), int(d["obj_id"]), float(d["prob"]), float(d["x"]), float(d["y"]),
+                       float(d["w"]), float(d["h"])) for d in img] for img in per_img])
+    assert any(len(img) for res in want for img in res), "test needs at least one detection"
+
+    dets = (dn.Detection * (batch * max_det))()
+    counts = (C.c_int * batch)()
+    got = []
+    stage = [lib.network_pipeline_staging(net, s) for s in (0, 1)]
+
+    def submit(i):
+        slot = lib.network_pipeline_next_slot(net)
+        C.memmove(stage[slot], batches[i].ctypes.data, batches[i].nbytes)
+        assert lib.network_detect_submit(net, stage[slot], thresh, nms, max_det) == slot
+
+    submit(0)
+    for i in range(1, len(batches)):
+        submit(i)
+        lib.network_detect_wait(net, dets, counts, max_det)
+        got.append(as_list(dets, counts))
+    lib.network_detect_wait(net, dets, counts, max_det)
+    got.append(as_list(dets, counts))
+    assert got == want
+    dn.free_network(net)
