@@ -194,6 +194,38 @@ __global__ void maxpool_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
     }
 }
 
+// 2x2 / stride 2 / no padding, the pool of every north-star cfg: 32-bit index math, one thread per
+// output position x 8 channels, the four window loads issued before the first max.  The layer is a
+// pure stream: (4 + 1) * 16 bytes per thread.
+__global__ void maxpool2x2_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, __nv_bfloat16 *__restrict__ out,
+                                  int out_cs, int batch, int c8, int h, int w, int oh, int ow)
+{
+    const int ohp = oh + 1, owp = ow + 1, hp = h + 1, wp = w + 1;
+    const unsigned total = (unsigned)batch * ohp * owp * c8;
+    const size_t row = (size_t)wp * in_cs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned g = i % c8;
+        const unsigned p = i / c8;
+        const unsigned ox = p % owp;
+        const unsigned q = p / owp;
+        const unsigned oy = q % ohp;
+        const unsigned b = q / ohp;
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        if (ox < (unsigned)ow && oy < (unsigned)oh) {
+            const __nv_bfloat16 *src = in + (((size_t)b * hp + 2 * oy) * wp + 2 * ox) * in_cs + g * 8;
+            const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(src));
+            const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(src + in_cs));
+            const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(src + row));
+            const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(src + row + in_cs));
+            acc = v00;
+            bf16x8_max(acc, v01);
+            bf16x8_max(acc, v10);
+            bf16x8_max(acc, v11);
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // reorg, exactly the index map of reorg_cpu(..., forward=0) (blas.c:8-29) as invoked by
 // reorg_layer.c:78-85 with the INPUT dims: out[in_index] = x[out_index], both flat NCHW
@@ -463,6 +495,15 @@ extern "C" int y2_maxpool(const void *in, int in_cs, void *out, int out_cs, int 
         return Y2_EINVAL;
     }
     const long long total = (long long)batch * (out_h + 1) * (out_w + 1) * (c / 8);
+    if (size == 2 && stride == 2 && pad == 0 && out_h == h / 2 && out_w == w / 2 && total < 0x7fffffffLL) {
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        maxpool2x2_kernel<<<(int)blocks, 256, 0, to_stream(s)>>>((const __nv_bfloat16 *)in, in_cs, (__nv_bfloat16 *)out,
+                                                                 out_cs, batch, c / 8, h, w, out_h, out_w);
+        Y2_LAUNCH_CHECK();
+        return Y2_OK;
+    }
     maxpool_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
         (const __nv_bfloat16 *)in, in_cs, (__nv_bfloat16 *)out, out_cs, batch, c / 8, h, w, out_h, out_w, size,
         stride, pad);

@@ -7,32 +7,46 @@
 //   (maxpool_layer_kernels.cu:10-48)
 // by one persistent launch that reads the caller's fp32 planar image once and writes only the
 // pooled bf16 padded-NHWC tensor.  The layer is HBM-bound (K = 27): per image it must move
-// 3*H*W*4 bytes in and (H/2)*(W/2)*32*2 bytes out; the full-resolution activation (H*W*32) never
-// exists in memory.
+// 3*H*W*4 bytes in and (H/2)*(W/2)*32*2 bytes out; the full-resolution activation never exists.
 //
-// Work decomposition.  A tile is 16 x 8 pool windows (32 x 16 pixels).  Four producer warps stage
-// the 34 x 18 x 3 fp32 halo patch with cp.async (double buffered), then each producer thread owns
-// one window and writes the four im2col rows of its 2x2 pixels (K = c*9 + r*3 + s, the order of
-// im2col.c:16-39, padded 27 -> 32) as bf16 into four 128 x 32 K-major SWIZZLE_64B operand tiles
-// A_q, q = 2*dy + dx.  One thread issues 4 x 2 tcgen05.mma (M = 128, N = 32, K = 16) into four TMEM
-// accumulators D_q.  Four epilogue warps read the four accumulators of their window from their own
-// TMEM lane, take the max, apply y = leaky(alpha * m + beta) and store 64 bytes.
+// How the im2col disappears.  A patch of (R+2) input rows x P positions is converted once to bf16
+// and stored in shared memory with ONE 16-byte row per position q of a patch row:
+//       row q = [ pixel q: c0 c1 c2 0 | pixel q+1: c0 c1 c2 0 ]          (8 bf16)
+// In the no-swizzle K-major UMMA layout the two 16-byte K-chunks of an operand row may sit at any
+// byte distance (the descriptor's leading-dimension offset); with that distance set to 32 bytes the
+// second chunk of row q IS row q+2, so a K = 16 operand row reads pixels q..q+3: the three
+// horizontal taps of a 3x3 filter row (+ one pixel against zero weights) in a single tcgen05.mma.
+// The vertical taps are three descriptors whose start address differs by one patch row.  One
+// image row of 128 positions therefore costs 3 MMAs (M = 128, N = 32, K = 16) and no data is ever
+// replicated per tap.  Two accumulators hold image rows y and y+1 in the same TMEM lanes, so the
+// 2x2 pool is a vertical max inside a thread and one shuffle with the neighbouring lane.
+//
+// Warp roles (576 threads): 0-7 converters (fp32 -> bf16 patch rows), 8 MMA issuer (+ TMEM alloc),
+// 9 TMA loader (the raw fp32 box of the next patch, zero-filled outside the image by the TMA unit),
+// 10-17 epilogue (two groups of four warps alternate over slots of two row pairs; TMEM lane quarter
+// = warp & 3).  Images whose row pitch is not a multiple of 16 bytes cannot be described by a tensor
+// map; for those the converters read global memory directly.
 //
 // max before the affine map is exact: the host makes every alpha_f >= 0 (a filter with negative
 // alpha has its weights and alpha negated, which leaves alpha*acc bit-identical), and
 // x -> leaky(fma(alpha, x, beta)) is then non-decreasing in fp32, so it commutes with max.
-#include "y2_common.cuh"
+#include "conv_plan.cuh"
+
+#include <stdlib.h>
+#include <string.h>
 
 namespace y2 {
 
-constexpr int kStemThreads = 288;  // warps 0-3 producers, 4 MMA, 5-8 epilogue
-constexpr int kStemN = 32;         // filters (padded)
-constexpr int kStemK = 32;         // 27 taps*channels padded
-constexpr int kWinX = 16, kWinY = 8;
-constexpr int kPatchW = 2 * kWinX + 2, kPatchH = 2 * kWinY + 2;  // 34 x 18
-constexpr int kPitch = 36;                                        // floats per staged row
-constexpr int kStageFloats = 3 * kPatchH * kPitch;
-constexpr int kATile = 128 * kStemK * 2;  // 8 KB per sub-position
+constexpr int kStemProducerWarps = 8;
+constexpr int kStemThreads = (kStemProducerWarps + 2 + 8) * 32;  // 576
+constexpr int kStemN = 32;          // filters (padded)
+constexpr int kStemK = 32;          // K stride of the weight matrix handed in by the host (27 used)
+constexpr int kStemRows = 16;       // image rows per patch (8 pooled rows)
+constexpr int kStemMaxP = 128;      // positions per patch row (tile width + 2)
+constexpr int kStemStages = 2;
+constexpr int kStemSlots = 4;       // TMEM slots of four 32-column accumulators (two row pairs) each
+constexpr int kStemBoxW = 132;      // floats per raw row: tile width + 8, at most
+constexpr int kPatchBytes = ((kStemRows + 2) * kStemMaxP + 136) * 16;  // + tail read by the junk lanes
 constexpr uint32_t kStemIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kStemN >> 3) << 17) |
                                 ((uint32_t)(128 >> 4) << 24);
 
@@ -40,219 +54,291 @@ struct StemParams {
     const float *in;   // fp32 [B][c][h][w]
     int batch, c, h, w;
     int oh, ow;        // pooled extent
+    int wt;            // image columns per tile (even), P = wt + 2
     int tiles_x, tiles_y, total_tiles;
-    const __nv_bfloat16 *wt;  // [32][32], K-major
+    const __nv_bfloat16 *wgt;  // [32][32], K index c*9 + r*3 + s
     const float *alpha, *beta;
     int act;
     __nv_bfloat16 *out;  // padded NHWC [B][oh+1][ow+1][out_cs]
     int out_cs;
+    int use_tma;       // raw fp32 boxes arrive through tm_in (else the converters load global memory)
+    int boxw;          // floats per raw row of the box
 };
 
 struct StemSmem {
-    alignas(1024) uint8_t a[2][4][kATile];  // 64 KB, swizzle atoms need 512 B alignment
-    alignas(1024) uint8_t w[kStemN * kStemK * 2];
-    alignas(16) float stage[2][kStageFloats];
+    alignas(128) uint8_t patch[kStemStages][kPatchBytes];
+    struct alignas(128) Raw { float v[3 * (kStemRows + 2) * kStemBoxW]; } raw[kStemStages];  // TMA destinations
+    alignas(128) uint8_t w[3][1024];  // per filter row dr: [k-chunk 2][n 32][8 bf16]
     float alpha[kStemN], beta[kStemN];
-    alignas(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+    alignas(8) uint64_t p_full[kStemStages], p_empty[kStemStages], r_full[kStemStages], r_empty[kStemStages];
+    uint64_t t_full[kStemSlots], t_empty[kStemSlots];
     uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void cp_async_f32(float *dst, const float *src, bool valid)
+// no-swizzle K-major descriptor: rows 16 B apart, 8-row groups `sbo` bytes apart, the second
+// 16-byte K chunk `lbo` bytes after the first
+__device__ __forceinline__ uint64_t stem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
 {
-    const uint32_t n = valid ? 4u : 0u;  // src-size 0 -> zero fill
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
 }
 
-// byte offset of 16-byte chunk `chunk` of row `row` in a K-major SWIZZLE_64B tile (64-byte rows):
-// the hardware XORs address bits [4,6) with bits [7,9)
-__device__ __forceinline__ uint32_t swz64(int row, int chunk)
+__device__ __forceinline__ uint2 stem_load_pixel(const StemParams &p, const float *img, int gy, int gx)
 {
-    return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-}
-
-__device__ __forceinline__ void stem_issue_loads(const StemParams &p, float *stage, int tile, int ptid)
-{
-    const int per_img = p.tiles_x * p.tiles_y;
-    const int b = tile / per_img;
-    const int t = tile - b * per_img;
-    const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-    const int y0 = ty * (2 * kWinY) - 1, x0 = tx * (2 * kWinX) - 1;
-    const float *img = p.in + (size_t)b * p.c * p.h * p.w;
-    for (int e = ptid; e < 3 * kPatchH * kPatchW; e += 128) {
-        const int ci = e / (kPatchH * kPatchW);
-        const int rem = e - ci * (kPatchH * kPatchW);
-        const int ry = rem / kPatchW, rx = rem - ry * kPatchW;
-        const int gy = y0 + ry, gx = x0 + rx;
-        const bool valid = ci < p.c && gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-        const float *src = valid ? img + ((size_t)ci * p.h + gy) * p.w + gx : p.in;
-        cp_async_f32(stage + (ci * kPatchH + ry) * kPitch + rx, src, valid);
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+        const float *s = img + (size_t)gy * p.w + gx;
+        const size_t plane = (size_t)p.h * p.w;
+        v0 = __ldg(s);
+        if (p.c > 1) v1 = __ldg(s + plane);
+        if (p.c > 2) v2 = __ldg(s + 2 * plane);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    return make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.f));
 }
 
-__global__ void __launch_bounds__(kStemThreads, 2) stem_conv_pool_kernel(const StemParams p)
+__device__ __forceinline__ void tma_load_3d(const void *desc, uint64_t *bar, void *smem_dst, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1)
+stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParams p)
 {
     extern __shared__ uint8_t stem_raw[];
-    StemSmem &sm = *reinterpret_cast<StemSmem *>(stem_raw + ((1024u - (smem_u32(stem_raw) & 1023u)) & 1023u));
+    StemSmem &sm = *reinterpret_cast<StemSmem *>(stem_raw + ((128u - (smem_u32(stem_raw) & 127u)) & 127u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = p.wt + 2;
+    const int pairs = kStemRows / 2;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.a_full[i], 128);
-            mbar_init(&sm.a_empty[i], 1);
+        for (int i = 0; i < kStemStages; ++i) {
+            mbar_init(&sm.p_full[i], kStemProducerWarps * 32);
+            mbar_init(&sm.p_empty[i], 1);
+            mbar_init(&sm.r_full[i], 1);
+            mbar_init(&sm.r_empty[i], kStemProducerWarps * 32);
+        }
+        for (int i = 0; i < kStemSlots; ++i) {
             mbar_init(&sm.t_full[i], 1);
             mbar_init(&sm.t_empty[i], 128);
         }
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == kStemProducerWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_slot)),
-                     "r"(256u)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // weights -> swizzled smem (generic proxy writes, fenced for the tensor core's async proxy)
-    if (threadIdx.x < 128) {
-        const int row = threadIdx.x >> 2, chunk = threadIdx.x & 3;
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.wt + row * kStemK + chunk * 8));
-        *reinterpret_cast<uint4 *>(sm.w + swz64(row, chunk)) = v;
-    } else if (threadIdx.x < 128 + kStemN) {
-        const int f = threadIdx.x - 128;
-        sm.alpha[f] = p.alpha[f];
-        sm.beta[f] = p.beta[f];
+    // weights: B_dr[n][k = 4*j + c] = w[n][c*9 + dr*3 + j]  (j < 3 horizontal tap, c < C_in), else 0
+    for (int e = threadIdx.x; e < 3 * kStemN * 16; e += kStemThreads) {
+        const int dr = e / (kStemN * 16);
+        const int n = (e / 16) % kStemN;
+        const int k = e % 16;
+        const int j = k >> 2, c = k & 3;
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (j < 3 && c < p.c) v = p.wgt[n * kStemK + c * 9 + dr * 3 + j];
+        const int off = (k >> 3) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(sm.w[dr] + off) = v;
+    }
+    // the tail behind the last patch row is only ever read by discarded lanes, but must stay finite
+    for (int e = threadIdx.x; e < kStemStages * kPatchBytes / 16; e += kStemThreads)
+        reinterpret_cast<uint4 *>(sm.patch[0])[e] = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < kStemN) {
+        sm.alpha[threadIdx.x] = p.alpha[threadIdx.x];
+        sm.beta[threadIdx.x] = p.beta[threadIdx.x];
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_slot;
+    const int per_img = p.tiles_x * p.tiles_y;
 
-    if (warp < 4) {
-        // ===================== producers: stage the patch, build the im2col rows =====================
-        const int ptid = threadIdx.x;  // 0..127 == window index inside the tile
-        const int wy = ptid >> 4, wx = ptid & 15;
+    if (warp < kStemProducerWarps) {
+        // ===================== converters: fp32 -> bf16 patch rows =====================
+        const int n_pos = (kStemRows + 2) * P;
+        const uint32_t inv_p = (uint32_t)(((1u << 20) + P - 1) / P);  // e / P == (e * inv_p) >> 20 for e < 2304
         int it = 0;
-        if ((int)blockIdx.x < p.total_tiles) stem_issue_loads(p, sm.stage[0], blockIdx.x, ptid);
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1;
-            const int next = tile + gridDim.x;
-            if (next < p.total_tiles) stem_issue_loads(p, sm.stage[s ^ 1], next, ptid);
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // 4 x 4 pixel neighbourhood of this window, 3 channels
-            float v[3][4][4];
-            const float *st = sm.stage[s];
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 *src =
-                        reinterpret_cast<const float2 *>(st + (ci * kPatchH + 2 * wy + j) * kPitch + 2 * wx);
-                    const float2 lo = src[0], hi = src[1];
-                    v[ci][j][0] = lo.x; v[ci][j][1] = lo.y; v[ci][j][2] = hi.x; v[ci][j][3] = hi.y;
+            const int s = it % kStemStages;
+            const uint32_t ph = (uint32_t)(it / kStemStages) & 1u;
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.patch[s]);
+            if (p.use_tma) {
+                mbar_wait_relaxed(&sm.r_full[s], ph, 9);
+                mbar_wait_relaxed(&sm.p_empty[s], ph ^ 1, 10);
+                const float *raw = sm.raw[s].v;
+                const int plane = (kStemRows + 2) * p.boxw;
+#pragma unroll 4
+                for (int e = threadIdx.x; e < n_pos; e += kStemProducerWarps * 32) {
+                    const int r = (int)(((uint32_t)e * inv_p) >> 20), q = e - r * P;
+                    const float *px = raw + r * p.boxw + q + 3;  // the box starts at image column x0 - 4
+                    float a0 = px[0], b0 = px[1], a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f;
+                    if (p.c > 1) { a1 = px[plane]; b1 = px[plane + 1]; }
+                    if (p.c > 2) { a2 = px[2 * plane]; b2 = px[2 * plane + 1]; }
+                    dst[e] = make_uint4(pack_bf16x2(a0, a1), pack_bf16x2(a2, 0.f), pack_bf16x2(b0, b1),
+                                        pack_bf16x2(b2, 0.f));
                 }
-            mbar_wait(&sm.a_empty[s], ((it >> 1) & 1) ^ 1, 10);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int dy = q >> 1, dx = q & 1;
-                uint32_t w32[16];
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    float e[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int k = 2 * k2 + h;  // K index = ci*9 + r*3 + s
-                        e[h] = (k < 27) ? v[k / 9][dy + (k % 9) / 3][dx + k % 3] : 0.f;
-                    }
-                    w32[k2] = pack_bf16x2(e[0], e[1]);
-                }
-                uint8_t *dst = sm.a[s][q];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4 *>(dst + swz64(ptid, c)) =
-                        make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
+                fence_proxy_async();
+                mbar_arrive(&sm.p_full[s]);
+                mbar_arrive(&sm.r_empty[s]);
+                continue;
             }
-            fence_proxy_async();
-            mbar_arrive(&sm.a_full[s]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer s is free for tile it+2
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == 4) {
-        // ===================== MMA issuer (whole warp waits, one elected lane issues) ===========
-        const uint64_t bdesc = make_kmajor_desc(smem_u32(sm.w), 512, 4);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(&sm.t_empty[s], ph ^ 1, 11);
-            mbar_wait(&sm.a_full[s], ph, 12);
-            tc_fence_after();
-            if (elect_one_sync()) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint64_t adesc = make_kmajor_desc(smem_u32(sm.a[s][q]), 512, 4);
-                    const uint32_t d = tmem_base + (uint32_t)(s * 4 * kStemN + q * kStemN);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kStemIdesc, (uint32_t)k);
-                }
-                umma_commit(&sm.a_empty[s]);
-                umma_commit(&sm.t_full[s]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===================== epilogue: max over the window, affine, leaky, store =====================
-        const int quarter = warp & 3;
-        const int win = quarter * 32 + lane;
-        const int wy = win >> 4, wx = win & 15;
-        const int per_img = p.tiles_x * p.tiles_y;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(&sm.t_full[s], ph, 13);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 4 * kStemN);
-            uint32_t m[32], u[32];
-            tmem_ld32(taddr, m);
-            tmem_ld32(taddr + kStemN, u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m[j] = __float_as_uint(fmaxf(__uint_as_float(m[j]), __uint_as_float(u[j])));
-            tmem_ld32(taddr + 2 * kStemN, u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m[j] = __float_as_uint(fmaxf(__uint_as_float(m[j]), __uint_as_float(u[j])));
-            tmem_ld32(taddr + 3 * kStemN, u);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&sm.t_empty[s]);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m[j] = __float_as_uint(fmaxf(__uint_as_float(m[j]), __uint_as_float(u[j])));
-
             const int b = tile / per_img;
             const int t = tile - b * per_img;
             const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-            const int oy = ty * kWinY + wy, ox = tx * kWinX + wx;
-            if (oy < p.oh && ox < p.ow) {
-                float f[32];
+            const int y0 = ty * kStemRows - 1, x0 = tx * p.wt - 1;
+            const float *img = p.in + (size_t)b * p.c * p.h * p.w;
+            mbar_wait_relaxed(&sm.p_empty[s], ph ^ 1, 10);
+            // a warp covers 31 positions per step; lane 31 only supplies the right neighbour of lane 30 (the
+            // next step recomputes it as lane 0).  Eight steps are loaded before any is consumed so that
+            // 24 independent global loads per thread are in flight (one memory round trip per patch).
+            constexpr int kBatch = 8;
+            for (int e0 = warp * 31; e0 < n_pos; e0 += kBatch * kStemProducerWarps * 31) {
+                uint2 a[kBatch];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float y = fmaf(__uint_as_float(m[j]), sm.alpha[j], sm.beta[j]);
-                    if (p.act == Y2_ACT_LEAKY) y = (y > 0.f) ? y : 0.1f * y;
-                    f[j] = y;
+                for (int u = 0; u < kBatch; ++u) {
+                    const int e = e0 + u * kStemProducerWarps * 31 + lane;
+                    const int r = e / P, q = e - r * P;
+                    a[u] = stem_load_pixel(p, img, y0 + r, x0 + q);
                 }
-                __nv_bfloat16 *o = p.out + (((size_t)b * (p.oh + 1) + oy) * (p.ow + 1) + ox) * p.out_cs;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 w;
-                    w.x = pack_bf16x2(f[8 * c + 0], f[8 * c + 1]);
-                    w.y = pack_bf16x2(f[8 * c + 2], f[8 * c + 3]);
-                    w.z = pack_bf16x2(f[8 * c + 4], f[8 * c + 5]);
-                    w.w = pack_bf16x2(f[8 * c + 6], f[8 * c + 7]);
-                    *reinterpret_cast<uint4 *>(o + 8 * c) = w;
+                for (int u = 0; u < kBatch; ++u) {
+                    const int e = e0 + u * kStemProducerWarps * 31 + lane;
+                    // a row wrap only feeds lanes that are discarded
+                    const uint32_t nx = __shfl_down_sync(0xffffffffu, a[u].x, 1);
+                    const uint32_t ny = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+                    if (lane < 31 && e < n_pos) dst[e] = make_uint4(a[u].x, a[u].y, nx, ny);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.p_full[s]);
+        }
+    } else if (warp == kStemProducerWarps + 1) {
+        // ===================== TMA loader: raw fp32 box of every patch =====================
+        if (p.use_tma) {
+            int it = 0;
+            const uint32_t box_bytes = (uint32_t)(p.c * (kStemRows + 2) * p.boxw * 4);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int s = it % kStemStages;
+                const uint32_t ph = (uint32_t)(it / kStemStages) & 1u;
+                const int b = tile / per_img;
+                const int t = tile - b * per_img;
+                const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+                mbar_wait_relaxed(&sm.r_empty[s], ph ^ 1, 8);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&sm.r_full[s], box_bytes);
+                    // the innermost box coordinate must be 16-byte aligned: start four columns left of the tile
+                    tma_load_3d(&tm_in, &sm.r_full[s], sm.raw[s].v, tx * p.wt - 4, ty * kStemRows - 1, b * p.c);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kStemProducerWarps) {
+        // ===================== MMA issuer =====================
+        const uint32_t w_lo = (smem_u32(sm.w[0]) & 0x3FFFFu) >> 4;
+        // descriptor words: hi = SBO 128 B | version 1; lo = address >> 4 | LBO >> 4 at bit 16
+        constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
+        constexpr uint32_t kLboA = (32u >> 4) << 16, kLboB = (512u >> 4) << 16;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int s = it % kStemStages;
+            const uint32_t ph = (uint32_t)(it / kStemStages) & 1u;
+            mbar_wait(&sm.p_full[s], ph, 11);
+            tc_fence_after();
+            const uint32_t patch_lo = (smem_u32(sm.patch[s]) & 0x3FFFFu) >> 4;
+#pragma unroll 1
+            for (int h = 0; h < kStemSlots; ++h) {  // slot h: image rows 4h .. 4h+3 (two row pairs)
+                mbar_wait(&sm.t_empty[h], (uint32_t)(it & 1) ^ 1, 12);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t row_lo = patch_lo + (uint32_t)(4 * h * P);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {  // image row 4h + i -> accumulator i of the slot
+                        const uint32_t d = tmem_base + (uint32_t)(h * 128 + i * 32);
+#pragma unroll
+                        for (int dr = 0; dr < 3; ++dr) {
+                            // patch row 4h + i + dr; the filter's three horizontal taps ride in K
+                            const uint64_t adesc = ((uint64_t)kHi << 32) | (uint64_t)((row_lo + (uint32_t)((i + dr) * P)) | kLboA);
+                            const uint64_t bdesc = ((uint64_t)kHi << 32) | (uint64_t)((w_lo + (uint32_t)(dr * 64)) | kLboB);
+                            umma_bf16(d, adesc, bdesc, kStemIdesc, (uint32_t)(dr != 0));
+                        }
+                    }
+                    umma_commit(&sm.t_full[h]);
+                    if (h == kStemSlots - 1) umma_commit(&sm.p_empty[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue: 2x2 max, affine, leaky, store =====================
+        const int ew = warp - (kStemProducerWarps + 2);  // 0..7
+        const int group = ew >> 2;                       // slots alternate between the two groups
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;               // TMEM lane == position inside the tile row
+        const int hsel = lane & 1;                       // even lane: channels 0-15, odd lane: 16-31
+        float al[16], be[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            al[q] = sm.alpha[hsel * 16 + q];
+            be[q] = sm.beta[hsel * 16 + q];
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int b = tile / per_img;
+            const int t = tile - b * per_img;
+            const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            for (int jp = 2 * group; jp < pairs; jp += 4)
+            for (int j = jp; j < jp + 2; ++j) {
+                const int slot = j >> 1;
+                if ((j & 1) == 0) {
+                    mbar_wait_relaxed(&sm.t_full[slot], (uint32_t)(it & 1), 13);
+                    tc_fence_after();
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 128 + (j & 1) * 64);
+                uint32_t v[32], u[32];
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + 32u, u);
+                tmem_ld_wait();
+                if (j & 1) {  // both row pairs of the slot are in registers
+                    tc_fence_before();
+                    mbar_arrive(&sm.t_empty[slot]);
+                }
+                // vertical max, then the horizontal partner's half of the channels
+                float mx[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float lo = fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q]));
+                    const float hi = fmaxf(__uint_as_float(v[q + 16]), __uint_as_float(u[q + 16]));
+                    const float send = hsel ? lo : hi;  // what the partner keeps
+                    const float keep = hsel ? hi : lo;
+                    const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+                    mx[q] = fmaxf(keep, got);
+                }
+                const int oy = ty * (kStemRows / 2) + j;
+                const int ox = (tx * p.wt + m) >> 1;
+                if (m < p.wt && oy < p.oh && ox < p.ow) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float y0 = fmaf(mx[2 * q], al[2 * q], be[2 * q]);
+                        float y1 = fmaf(mx[2 * q + 1], al[2 * q + 1], be[2 * q + 1]);
+                        if (p.act == Y2_ACT_LEAKY) {
+                            y0 = fmaxf(y0, 0.1f * y0);
+                            y1 = fmaxf(y1, 0.1f * y1);
+                        }
+                        pk[q] = pack_bf16x2(y0, y1);
+                    }
+                    __nv_bfloat16 *o = p.out + (((size_t)b * (p.oh + 1) + oy) * (p.ow + 1) + ox) * p.out_cs + hsel * 16;
+                    *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
         }
@@ -260,8 +346,8 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_conv_pool_kernel(const S
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    if (warp == kStemProducerWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -277,7 +363,7 @@ extern "C" int y2_stem_prepare(void)
     Y2_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         Y2_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(StemSmem) + 1024)));
+                                           (int)(sizeof(StemSmem) + 128)));
         attr_done[dev] = true;
     }
     return Y2_OK;
@@ -302,25 +388,47 @@ extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w
     p.w = w;
     p.oh = h / 2;
     p.ow = w / 2;
-    p.tiles_x = (p.ow + kWinX - 1) / kWinX;
-    p.tiles_y = (p.oh + kWinY - 1) / kWinY;
+    // equal column tiles of at most 124 image columns, a multiple of 4 wide (16-byte aligned TMA boxes)
+    const int wmax = kStemMaxP - 4;
+    const int nx = (2 * p.ow + wmax - 1) / wmax;
+    int wt_cols = (2 * p.ow + nx - 1) / nx;
+    wt_cols = (wt_cols + 3) / 4 * 4;
+    p.wt = wt_cols;
+    p.tiles_x = (2 * p.ow + wt_cols - 1) / wt_cols;
+    p.tiles_y = (p.oh + kStemRows / 2 - 1) / (kStemRows / 2);
     const long long total = (long long)batch * p.tiles_x * p.tiles_y;
     if (total > 0x7fffffffLL) return Y2_EINVAL;
     p.total_tiles = (int)total;
-    p.wt = (const __nv_bfloat16 *)wt;
+    p.wgt = (const __nv_bfloat16 *)wt;
     p.alpha = alpha;
     p.beta = beta;
     p.act = act;
     p.out = (__nv_bfloat16 *)out;
     p.out_cs = out_cs;
-    const size_t smem = sizeof(StemSmem) + 1024;
+    const size_t smem = sizeof(StemSmem) + 128;
     int rc = y2_stem_prepare();
     if (rc != Y2_OK) return rc;
+    // raw fp32 boxes through TMA when the image rows are 16-byte aligned; the tensor map is encoded per
+    // call (the input pointer is the caller's) and travels by value in the launch / graph node
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    p.boxw = p.wt + 8;  // image columns x0 - 4 .. x0 + wt + 3
+    p.use_tma = 0;
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc && w % 4 == 0 && ((uintptr_t)in & 15) == 0 && p.boxw <= kStemBoxW && p.boxw <= w && kStemRows + 2 <= h &&
+        !getenv("Y2_STEM_NO_TMA")) {  // a box never exceeds the tensor it slides over
+        cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch * c};
+        cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+        cuuint32_t box[3] = {(cuuint32_t)p.boxw, (cuuint32_t)(kStemRows + 2), (cuuint32_t)c};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(in), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        p.use_tma = (r == CUDA_SUCCESS);
+    }
     const int sms = sm_count();
-    // two co-resident CTAs per SM (83 KB smem, 256 TMEM columns, <= 112 registers each): the producer warps
-    // of one CTA are latency-bound, a second CTA fills the bubbles
-    const int grid = p.total_tiles < 2 * sms ? p.total_tiles : 2 * sms;
-    stem_conv_pool_kernel<<<grid, kStemThreads, smem, to_stream(s)>>>(p);
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    stem_conv_pool_kernel<<<grid, kStemThreads, smem, to_stream(s)>>>(tm, p);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

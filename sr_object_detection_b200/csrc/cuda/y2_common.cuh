@@ -96,6 +96,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
     }
 }
 
+// Same, for waiters that are not on the critical path (producers waiting for a free stage, epilogue
+// warps waiting for an accumulator): sleep between probes so the spin does not take issue slots
+// from the warps that are working on the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, int tag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("y2: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+                   (int)blockIdx.x, (int)threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
 // One lane of the (converged) warp gets 1.  Unlike `lane == 0`, ptxas knows a single thread is active
 // under this predicate, so the uniform-datapath instructions behind it (UTCHMMA, UTMALDG, UTCBAR)
 // are emitted straight-line instead of inside a per-active-thread ELECT/BRA.U.ANY loop.
