@@ -1,0 +1,336 @@
+// Implicit-GEMM 3x3 convolution on CTA pairs: tcgen05.mma.cta_group::2 over a 2-CTA cluster.
+//
+// Replaces forward_convolutional_layer_gpu (reference convolutional_kernels.cu:77-131) for the wide
+// 3x3 layers (>= 256 filters, C_in a multiple of 64) - two thirds of YOLOv2's FLOPs.
+//
+// Why pairs.  With one CTA per tile (conv_slab.cu) a 128 x 256 x 64 MMA step moves 34 KB into shared
+// memory and reads 48 KB of operands back out of it in 512 tensor-pipe clocks: the ~128 B/clk/SM of
+// shared-memory bandwidth, not the tensor pipe, bounds the layer at ~60% of peak.  A CTA pair
+// computes a 256 x 256 tile with ONE instruction stream: each CTA holds its own 128 positions of the
+// halo slab (A) and HALF of the 256-filter weight tile (B); the tensor cores of both SMs read the
+// two halves across the pair.  Per SM and step that is 18 KB of fill and 32 KB of operand reads.
+//
+// Protocol (leader = even CTA of the pair):
+//   * both CTAs TMA-load their slab / weight half into their own shared memory; the bytes are
+//     credited to the LEADER's full barriers (.cta_group::2 TMA, peer bit cleared in the mbarrier
+//     address), whose single arrival is the leader's expect_tx for both halves;
+//   * only the leader issues MMAs; tcgen05.commit multicasts the "stage free" / "accumulator
+//     full" arrivals to the barriers at the same offset in both CTAs;
+//   * each CTA drains its own 128 TMEM lanes; "accumulator drained" arrivals of both CTAs land on
+//     the leader's barrier (remote mbarrier.arrive through mapa).
+// Everything else (halo slab, row-shifted descriptors, double-buffered accumulators, 8 epilogue
+// warps) is conv_slab.cu's design.
+#include "conv_epilogue.cuh"
+
+#include <stdlib.h>
+
+namespace y2 {
+
+constexpr int kPairThreads = 352;
+constexpr int kPairEpiThreads = 256;
+constexpr int kPairMaxStagesA = 4;
+constexpr int kPairMaxStagesB = 10;
+constexpr int kPairBK = 64;
+constexpr int kPairN = 256;                          // filters per pair tile
+constexpr int kPairRowBytes = kPairBK * 2;           // 128
+constexpr int kPairBHalfBytes = 128 * kPairBK * 2;   // this CTA's half of a weight tile
+constexpr uint32_t kPairDescHi = ((8u * kPairRowBytes) >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, v1, SWIZZLE_128B
+// c = F32, a = b = BF16, K-major, N = 256, M = 256 (both CTAs)
+constexpr uint32_t kPairIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPairN >> 3) << 17) |
+                                ((uint32_t)(256 >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const SlabParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // identical carve-up in both CTAs: descriptors and barrier offsets name the peer's memory too
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int stages_a = prm.stages_a, stages_b = prm.stages_b;
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + (size_t)stages_a * prm.slab_bytes;
+    uint8_t *aux = smem_b + (size_t)stages_b * kPairBHalfBytes;
+    float2 *s_ab = reinterpret_cast<float2 *>(aux);  // [2 buf][256] (alpha, beta)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aux + 2 * kPairN * 8);
+    uint64_t *a_full = bars;
+    uint64_t *a_empty = bars + kPairMaxStagesA;
+    uint64_t *b_full = bars + 2 * kPairMaxStagesA;
+    uint64_t *b_empty = b_full + kPairMaxStagesB;
+    uint64_t *tfull_bar = b_empty + kPairMaxStagesB;
+    uint64_t *tempty_bar = tfull_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+    const int total_tiles = prm.tiles_m * prm.tiles_n;
+    const int cblocks = prm.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+        for (int i = 0; i < stages_a; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < stages_b; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 2 * kPairEpiThreads);  // the epilogue threads of both CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote arrival
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== slab producer (both CTAs, own 128 positions) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * kPairRowBytes;
+        const uint32_t load_bytes = (uint32_t)prm.box_rows * kPairRowBytes;
+        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            const int m_tile = tile / prm.tiles_n;
+            const int row0 = m_tile * 256 + (int)rank * 128 - prm.halo;
+            for (int cb = 0; cb < cblocks; ++cb) {
+                mbar_wait(&a_empty[stage], phase ^ 1, 1);
+                if (elect_one_sync()) {
+                    uint8_t *sa = smem_a + (size_t)stage * prm.slab_bytes;
+                    if (leader) mbar_expect_tx(&a_full[stage], 2 * slab_tx);
+                    for (int i = 0; i < prm.slab_loads; ++i)
+                        tma_load_2d_pair(&tm_a, &a_full[stage], sa + i * load_bytes, cb * kPairBK,
+                                         row0 + i * prm.box_rows);
+                }
+                __syncwarp();
+                if (++stage == stages_a) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== weight producer (both CTAs, own 128 filters) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+            const int m_tile = tile / prm.tiles_n;
+            const int n0 = (tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
+            for (int cb = 0; cb < cblocks; ++cb) {
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&b_empty[stage], phase ^ 1, 2);
+                    if (elect_one_sync()) {
+                        if (leader) mbar_expect_tx(&b_full[stage], 2u * kPairBHalfBytes);
+                        tma_load_2d_pair(&tm_b, &b_full[stage], smem_b + (size_t)stage * kPairBHalfBytes,
+                                         (tap * cblocks + cb) * kPairBK, n0);
+                    }
+                    __syncwarp();
+                    if (++stage == stages_b) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            int sa_i = 0, sb_i = 0;
+            uint32_t pa = 0, pb = 0;
+            int it = 0;
+            const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t slab16 = (uint32_t)prm.slab_bytes >> 4;
+            constexpr uint32_t kRow16 = kPairRowBytes >> 4;
+            const uint32_t wp16 = (uint32_t)prm.wp * kRow16;
+            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+                const int buf = it & 1;
+                const uint32_t buf_phase = (it >> 1) & 1;
+                mbar_wait(&tempty_bar[buf], buf_phase ^ 1, 3);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * kPairN);
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    mbar_wait(&a_full[sa_i], pa, 4);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
+                    const uint32_t acc_first = cb != 0;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&b_full[sb_i], pb, 5);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            const uint32_t b_lo = b_lo0 + (uint32_t)sb_i * (kPairBHalfBytes >> 4);
+                            const uint32_t a_tap = a_lo + (uint32_t)(tap / 3) * wp16 + (uint32_t)(tap % 3) * kRow16;
+#pragma unroll
+                            for (int k = 0; k < kPairBK / 16; ++k)
+                                umma_bf16_pair(d0, ((uint64_t)kPairDescHi << 32) | (uint64_t)(a_tap + (uint32_t)(k * 2)),
+                                               ((uint64_t)kPairDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(k * 2)),
+                                               kPairIdesc, (tap == 0 && k == 0) ? acc_first : 1u);
+                            umma_commit_pair(&b_empty[sb_i]);
+                            if (tap == 8) {
+                                umma_commit_pair(&a_empty[sa_i]);
+                                if (cb == cblocks - 1) umma_commit_pair(&tfull_bar[buf]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb_i == stages_b) { sb_i = 0; pb ^= 1; }
+                    }
+                    if (++sa_i == stages_a) { sa_i = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 3..10 of both CTAs, own 128 TMEM lanes) ==========
+        const int quarter = warp & 3;
+        const int half = (warp - 3) >> 2;
+        const int et = threadIdx.x - 96;  // 0..255
+        const int col0 = half * 128;
+        const int img_pos = prm.hp * prm.wp;
+        int it = 0;
+        if (pair < total_tiles) {
+            const int n0 = (pair % prm.tiles_n) * kPairN;
+            s_ab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
+        }
+        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+            const int buf = it & 1;
+            const uint32_t buf_phase = (it >> 1) & 1;
+            const int m_tile = tile / prm.tiles_n;
+            const int n0 = (tile - m_tile * prm.tiles_n) * kPairN;
+            const float2 *sab = s_ab + (prm.tiles_n > 1 ? buf * kPairN : 0);
+            const bool reload = prm.tiles_n > 1 || it == 0;
+            if (reload) asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int next = tile + n_pairs;
+            float2 ab_next = make_float2(1.f, 0.f);
+            if (prm.tiles_n > 1 && next < total_tiles) {
+                const int nn = (next % prm.tiles_n) * kPairN;
+                ab_next = make_float2(__ldg(prm.alpha + nn + et), __ldg(prm.beta + nn + et));
+            }
+            const int p = m_tile * 256 + (int)rank * 128 + quarter * 32 + lane;
+            const bool in_range = p < prm.total_pos;
+            const int b = p / img_pos;
+            const int rem = p - b * img_pos;
+            const int y = rem / prm.wp;
+            const int x = rem - y * prm.wp;
+            const bool valid = in_range && (y < prm.h) && (x < prm.w);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kPairN + col0);
+
+            mbar_wait(&tfull_bar[buf], buf_phase, 6);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr + (uint32_t)c, v0);
+                tmem_ld32(taddr + (uint32_t)(c + 32), v1);
+                tmem_ld_wait();
+                if (c == 64) {  // accumulator drained into registers: hand it back to the leader's MMA warp
+                    tc_fence_before();
+                    mbar_arrive_cluster(&tempty_bar[buf], 0);
+                }
+                if (prm.act == Y2_ACT_LEAKY) {
+                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                } else if (prm.act == Y2_ACT_LINEAR) {
+                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                } else {
+                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                }
+            }
+            if (prm.tiles_n > 1 && next < total_tiles) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // no CTA leaves while its peer may still address its shared memory / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------
+int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
+{
+    if (d->ksize != 3 || d->block_k != kPairBK || d->block_n != 256 || d->npad % kPairN) return Y2_EINVAL;
+    const int hp = d->h + 1, wp = d->w + 1;
+    const long long total = (long long)d->batch * hp * wp;
+    const int halo = wp + 1;
+    const int slab_rows = 128 + 2 * halo;
+    const int loads = (slab_rows + 255) / 256;
+    int box_rows = (slab_rows + loads - 1) / loads;
+    box_rows = (box_rows + 15) / 16 * 16;
+    if (box_rows > 256) return Y2_EINVAL;
+    const int slab_bytes = loads * box_rows * kPairRowBytes;
+    const int aux = 2 * kPairN * 8 + 512;
+    const int budget = 227 * 1024 - 1024 - aux;
+    const int stages_a = 2;
+    int stages_b = (budget - stages_a * slab_bytes) / kPairBHalfBytes;
+    if (stages_b > kPairMaxStagesB) stages_b = kPairMaxStagesB;
+    if (stages_b < 4) return Y2_EINVAL;
+    const int sms = sm_count();
+    if (sms < 2) return Y2_EINVAL;
+    const int ktot = 9 * d->cin;
+    int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
+                            (uint32_t)kPairBK, (uint32_t)box_rows, kPairBK);
+    if (rc == Y2_OK)
+        rc = encode_2d_bf16(&pl->tm_b, d->wt, (uint64_t)ktot, (uint64_t)d->npad, (uint64_t)ktot * 2, (uint32_t)kPairBK,
+                            128u, kPairBK);
+    if (rc != Y2_OK) return rc;
+    SlabParams &p = pl->slab;
+    p.cblocks = d->cin / kPairBK;
+    p.wp = wp;
+    p.hp = hp;
+    p.h = d->h;
+    p.w = d->w;
+    p.total_pos = (int)total;
+    p.tiles_m = (int)((total + 255) / 256);
+    p.tiles_n = d->npad / kPairN;
+    p.halo = halo;
+    p.slab_loads = loads;
+    p.box_rows = box_rows;
+    p.slab_bytes = slab_bytes;
+    p.stages_a = stages_a;
+    p.stages_b = stages_b;
+    p.cout = d->cout;
+    p.act = d->act;
+    p.out_mode = d->out_mode;
+    p.out_cs = d->out_cs;
+    p.couple = 0;
+    p.alpha = d->alpha;
+    p.beta = d->beta;
+    p.out = d->out;
+    pl->variant = kVariantPair;
+    pl->block_n = kPairN;
+    pl->block_k = kPairBK;
+    pl->smem_bytes = (size_t)stages_a * slab_bytes + (size_t)stages_b * kPairBHalfBytes + aux + 1024;
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+    pl->grid = 2 * pairs;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    Y2_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[dev] = true;
+    }
+    return Y2_OK;
+}
+
+int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
+{
+    conv_pair_kernel<<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->slab);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+} // namespace y2

@@ -45,7 +45,7 @@ struct SlabParams {
     void *out;
 };
 
-enum { kVariantPerTap = 0, kVariantSlab = 1 };
+enum { kVariantPerTap = 0, kVariantSlab = 1, kVariantPair = 2 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -74,4 +74,7 @@ namespace y2 {
 // (without touching the error string) when it does not and the per-tap kernel must be used
 int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d);
 int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
+// conv_pair.cu: the CTA-pair (cta_group::2) kernel for wide 3x3 layers, same contract
+int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d);
+int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
 } // namespace y2

@@ -27,7 +27,7 @@
 // 3..10 epilogue (TMEM lane quarter = warp & 3; warps 3-6 take the first half of the tile's
 // accumulator columns, warps 7-10 the second half).  Producer / MMA warps run converged and
 // elect one lane per issue (see elect_one_sync in y2_common.cuh).
-#include "conv_plan.cuh"
+#include "conv_epilogue.cuh"
 
 #include <stdlib.h>
 
@@ -60,60 +60,6 @@ struct SlabCfg {
 __device__ __forceinline__ uint64_t slab_desc(uint32_t hi, uint32_t lo)
 {
     return ((uint64_t)hi << 32) | (uint64_t)lo;
-}
-
-// one 32-column chunk of one accumulator row: affine + activation + store
-template <int ACT>
-__device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const uint32_t (&v)[32], const float2 *sab,
-                                                    int c0, int n0, int p, int b, int y, int x, bool in_range,
-                                                    bool valid)
-{
-    float f[32];
-    const float4 *ab4 = reinterpret_cast<const float4 *>(sab + c0);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float4 q = ab4[j];  // (alpha, beta) of two filters
-        float t0 = fmaf(__uint_as_float(v[2 * j]), q.x, q.y);
-        float t1 = fmaf(__uint_as_float(v[2 * j + 1]), q.z, q.w);
-        if (ACT == Y2_ACT_LEAKY) {  // max(t, 0.1 t) == (t > 0 ? t : 0.1 t) for every finite t
-            t0 = fmaxf(t0, 0.1f * t0);
-            t1 = fmaxf(t1, 0.1f * t1);
-        } else if (ACT == Y2_ACT_LOGISTIC) {
-            t0 = 1.f / (1.f + __expf(-t0));
-            t1 = 1.f / (1.f + __expf(-t1));
-        }
-        f[2 * j] = t0;
-        f[2 * j + 1] = t1;
-    }
-    const int ch0 = n0 + c0;
-    if (prm.out_mode == Y2_OUT_BF16_PADDED) {
-        if (in_range) {
-            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(prm.out) + (size_t)p * prm.out_cs + ch0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (ch0 + q * 8 < prm.cout) {
-                    uint4 w;
-                    if (valid) {
-                        w.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-                        w.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-                        w.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-                        w.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-                    } else {
-                        w = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    *reinterpret_cast<uint4 *>(o + q * 8) = w;
-                }
-            }
-        }
-    } else {  // Y2_OUT_F32_FLAT: [B][h*w][out_cs]
-        if (valid) {
-            float *o = reinterpret_cast<float *>(prm.out) +
-                       ((size_t)b * prm.h * prm.w + (size_t)y * prm.w + x) * prm.out_cs + ch0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (ch0 + j < prm.cout) o[j] = f[j];
-        }
-    }
 }
 
 template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS>

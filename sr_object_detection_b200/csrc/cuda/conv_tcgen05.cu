@@ -369,13 +369,19 @@ extern "C" int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **out_pla
     }
     const int taps = d->ksize * d->ksize;
     const int ktot = taps * d->cin;
-    // the halo-slab kernel serves every layer it fits; Y2_CONV_VARIANT=pertap forces this file's kernel
+    // kernel choice: CTA-pair kernel for wide 3x3 layers, halo-slab kernel for the other 3x3 layers, this
+    // file's per-tap kernel for 1x1 layers and whatever does not fit.  Y2_CONV_VARIANT=pertap|slab|pair
+    // restricts the choice (tests, A/B timing).
     const char *forced = getenv("Y2_CONV_VARIANT");
-    if (!(forced && !strcmp(forced, "pertap")) && d->block_n <= 256) {
-        if (slab_plan_init(pl, d) == Y2_OK) {
-            *out_plan = pl;
-            return Y2_OK;
-        }
+    const bool allow_pair = !forced || !strcmp(forced, "pair");
+    const bool allow_slab = !forced || !strcmp(forced, "slab") || !strcmp(forced, "pair");
+    if (allow_pair && pair_plan_init(pl, d) == Y2_OK) {
+        *out_plan = pl;
+        return Y2_OK;
+    }
+    if (allow_slab && slab_plan_init(pl, d) == Y2_OK) {
+        *out_plan = pl;
+        return Y2_OK;
     }
     pl->variant = kVariantPerTap;
     int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
@@ -435,6 +441,7 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
     using namespace y2;
     if (!pl) return Y2_EINVAL;
     cudaStream_t st = to_stream(s);
+    if (pl->variant == kVariantPair) return pair_plan_launch(pl, st);
     if (pl->variant == kVariantSlab) return slab_plan_launch(pl, st);
 #define Y2_CASE(BN, BK) \
     if (pl->block_n == BN && pl->block_k == BK) return launch_cfg<BN, BK>(pl, st);
@@ -449,5 +456,5 @@ extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl) { delete pl; }
 extern "C" int y2_conv_plan_tiles(const y2_conv_plan *pl)
 {
     if (!pl) return 0;
-    return pl->variant == y2::kVariantSlab ? pl->slab.tiles_m * pl->slab.tiles_n : pl->prm.tiles_m * pl->prm.tiles_n;
+    return pl->variant != y2::kVariantPerTap ? pl->slab.tiles_m * pl->slab.tiles_n : pl->prm.tiles_m * pl->prm.tiles_n;
 }

@@ -58,14 +58,15 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=["slab", "pertap"])
+@pytest.fixture(params=["auto", "slab", "pertap"])
 def conv_variant(request, monkeypatch):
-    """Both implicit-GEMM kernels stay under test: the halo-slab kernel (default) and the per-tap
-    fallback (Y2_CONV_VARIANT=pertap is read at plan creation)."""
-    if request.param == "pertap":
-        monkeypatch.setenv("Y2_CONV_VARIANT", "pertap")
-    else:
+    """All three implicit-GEMM kernels stay under test: the default choice (CTA-pair kernel for wide 3x3
+    layers), the halo-slab kernel alone and the per-tap fallback (Y2_CONV_VARIANT is read at plan
+    creation)."""
+    if request.param == "auto":  # CTA-pair kernel where it fits, then slab, then per-tap
         monkeypatch.delenv("Y2_CONV_VARIANT", raising=False)
+    else:
+        monkeypatch.setenv("Y2_CONV_VARIANT", request.param)
     return request.param
 
 
