@@ -300,13 +300,22 @@ def main() -> int:
     conv_launches = 0
     table = []
     flops_img = lib.network_conv_flops(net)
+    KERNELS = {0: "conv_tcgen05_kernel (per-tap)", 1: "conv_slab_kernel", 2: "conv_pair_kernel (cta_group::2)",
+               3: "stem_conv_pool_kernel"}
+    per_kernel = {}  # variant -> [ms, flops, launches]
     for i in range(n_layers):
         l = net.layers[i]
         fl = 2.0 * l.n * l.size * l.size * l.c * l.out_h * l.out_w * B if l.type == dn.CONVOLUTIONAL else 0.0
+        kern = lib.network_conv_kernel(net, i)
         if l.type == dn.CONVOLUTIONAL:
             conv_ms += float(layer_ms[i])
             conv_launches += 1
+            acc = per_kernel.setdefault(kern, [0.0, 0.0, 0])
+            acc[0] += float(layer_ms[i])
+            acc[1] += fl
+            acc[2] += 1
         table.append({"layer": i, "type": int(l.type), "ms": round(float(layer_ms[i]), 4),
+                      "kernel": KERNELS.get(kern),
                       "tflops": round(float(fl / (float(layer_ms[i]) * 1e9)), 1) if fl and layer_ms[i] > 0 else None})
 
     total_images = B * world * args.steps
@@ -316,6 +325,26 @@ def main() -> int:
     step_flops = flops_img * B
     achieved_tf = step_flops / (conv_ms * 1e9) if conv_ms > 0 else 0.0
     detect_launches = 6  # region_boxes, nms memset+count+mark+clear, collect
+    # dominant kernel = the convolution kernel with the largest share of the step (the CTA-pair kernel on
+    # yolo-voc): algorithmic FLOPs of the layers it runs / the CUDA-event time of those launches
+    dom = max(per_kernel, key=lambda k: per_kernel[k][0]) if per_kernel else None
+    dom_ms, dom_fl, dom_n = per_kernel.get(dom, [0.0, 0.0, 0])
+    dom_tf = dom_fl / (dom_ms * 1e9) if dom_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": f"{KERNELS.get(dom)} ({dom_n} launches per step)",
+        "achieved": round(dom_tf, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": round(dom_tf / peaks["tflops"], 4), "peak_burst": peaks["tflops_burst"],
+        "peak_source": peaks["source"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (yolo-voc L23, ncu --set full,
+        # profiles/r1j_ncu_conv_pair_L23.txt); algorithmic operand bytes of that launch: 70 MB
+        "traffic": 47.0e6 if dom == 2 else None,
+        "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / max(float(layer_ms.sum()), 1e-9), 3),
+        "all_convolutions": {"launches": conv_launches, "ms_per_step": round(conv_ms, 4),
+                             "achieved": round(achieved_tf, 1), "frac": round(achieved_tf / peaks["tflops"], 4)},
+        "per_kernel": {KERNELS.get(k): {"launches": v[2], "ms": round(v[0], 4),
+                                        "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] > 0 else None}
+                       for k, v in sorted(per_kernel.items())},
+        "step_ms_eager": round(float(layer_ms.sum()), 4)}
     line = {
         "metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
@@ -328,11 +357,7 @@ def main() -> int:
                    "algorithmic_gflop_per_image": round(flops_img / 1e9, 3)},
         "model_tflops": round(value / world * flops_img / 1e12, 1),
         "model_frac_of_peak": round(value / world * flops_img / 1e12 / peaks["tflops"], 4),
-        "roofline": {"bound": "tensor", "kernel": "conv_tcgen05_kernel (23 launches per step)",
-                     "achieved": round(achieved_tf, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / peaks["tflops"], 4), "peak_burst": peaks["tflops_burst"],
-                     "peak_source": peaks["source"], "traffic": None,
-                     "conv_ms_per_step": round(conv_ms, 4), "step_ms_eager": round(float(layer_ms.sum()), 4)},
+        "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "h2d_bytes_per_step": int(images.nbytes),
                 "d2h_bytes_per_step": int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4),

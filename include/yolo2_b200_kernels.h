@@ -111,6 +111,9 @@ void y2_conv_plan_destroy(y2_conv_plan *plan);
 /* algorithmic flops of one launch: 2*cout*ksize^2*cin_real*B*H*W is the caller's
  * business; this returns the number of MMA tiles for diagnostics. */
 int y2_conv_plan_tiles(const y2_conv_plan *plan);
+/* which kernel the plan launches: 0 per-tap (conv_tcgen05_kernel), 1 halo slab (conv_slab_kernel),
+ * 2 CTA pair (conv_pair_kernel, tcgen05.mma.cta_group::2) */
+int y2_conv_plan_variant(const y2_conv_plan *plan);
 
 /* ---- first layer (replaces, for a 3x3/1 'same' convolution over <= 3 input channels followed by a
  *      2x2/2 maxpool: cuda_make_array of the input (network_kernels.cu:399) +

@@ -453,6 +453,11 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
 
 extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl) { delete pl; }
 
+extern "C" int y2_conv_plan_variant(const y2_conv_plan *pl)
+{
+    return pl ? pl->variant : -1;
+}
+
 extern "C" int y2_conv_plan_tiles(const y2_conv_plan *pl)
 {
     if (!pl) return 0;

@@ -245,24 +245,41 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int c = 0;
-        y2_det *d = det + (size_t)b * max_det;
-        const float4 *bx = reinterpret_cast<const float4 *>(boxes) + (size_t)b * total;
-        for (int i = 0; i < total; ++i) {
-            if (s_flag[i] >= 0) {
-                if (c < max_det) {
-                    const float4 q = bx[i];
-                    d[c].x = q.x; d[c].y = q.y; d[c].w = q.z; d[c].h = q.w;
-                    d[c].prob = s_prob[i];
-                    d[c].obj_id = s_flag[i];
-                    d[c].box_index = i;
-                }
-                ++c;
-            }
+    // ordered compaction (box-index order, like the reference's loop): ballot + warp-total scan per
+    // chunk of blockDim boxes, running offset carried from chunk to chunk
+    __shared__ int s_warp_total[32];
+    __shared__ int s_running;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    y2_det *d = det + (size_t)b * max_det;
+    const float4 *bx = reinterpret_cast<const float4 *>(boxes) + (size_t)b * total;
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int obj = (i < total) ? s_flag[i] : -1;
+        const unsigned ballot = __ballot_sync(0xffffffffu, obj >= 0);
+        if (lane == 0) s_warp_total[warp] = __popc(ballot);
+        __syncthreads();
+        int before = s_running;
+        for (int wv = 0; wv < warp; ++wv) before += s_warp_total[wv];
+        const int pos = before + __popc(ballot & ((1u << lane) - 1u));
+        if (obj >= 0 && pos < max_det) {
+            const float4 q = bx[i];
+            y2_det o;
+            o.x = q.x; o.y = q.y; o.w = q.z; o.h = q.w;
+            o.prob = s_prob[i];
+            o.obj_id = obj;
+            o.box_index = i;
+            d[pos] = o;
         }
-        count[b] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = s_running;
+            for (int wv = 0; wv < nw; ++wv) t += s_warp_total[wv];
+            s_running = t;
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) count[b] = s_running;
 }
 
 // classifier tail ------------------------------------------------------------------

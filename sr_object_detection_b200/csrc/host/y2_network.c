@@ -1145,6 +1145,16 @@ int network_launch_count(network net)
     return rt ? rt->launches : 0;
 }
 
+/* kernel behind layer i: 0 per-tap, 1 halo slab, 2 CTA pair, 3 fused first layer, -1 not a convolution */
+int network_conv_kernel(network net, int i)
+{
+    if (i < 0 || i >= net.n || net.layers[i].type != CONVOLUTIONAL) return -1;
+    y2_layer_rt *r = y2_lrt(net.layers[i]);
+    if (!r) return -1;
+    if (r->stem_fused) return 3;
+    return r->plan ? y2_conv_plan_variant(r->plan) : -1;
+}
+
 void *network_stream(network net)
 {
     return net_stream(net);

@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
         "network_stream": (C.c_void_p, [Network]),
         "network_conv_flops": (C.c_double, [Network]),
         "network_launch_count": (i, [Network]),
+        "network_conv_kernel": (i, [Network, i]),
         "network_profile_layers": (i, [Network, fp, i]),
         "network_set_eager": (None, [Network, i]),
         "network_input_staging": (fp, [Network]),
