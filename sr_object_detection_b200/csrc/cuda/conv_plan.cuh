@@ -64,7 +64,7 @@ struct y2_conv_plan {
     int variant;
     y2::ConvParams prm;
     y2::SlabParams slab;
-    int block_n, block_k;
+    int block_n, block_k, taps;
     int grid;
     size_t smem_bytes;
 };

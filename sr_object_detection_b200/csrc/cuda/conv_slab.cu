@@ -38,7 +38,7 @@ constexpr int kSlabEpiThreads = 256;
 constexpr int kSlabMaxStagesA = 4;
 constexpr int kSlabMaxStagesB = 8;
 
-template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS>
+template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS, int TAPS>
 struct SlabCfg {
     static constexpr int kTileM = ACCS * kBlockM;
     static constexpr int kRowBytes = BLOCK_K * 2;
@@ -46,7 +46,8 @@ struct SlabCfg {
     static constexpr int kBStageBytes = TPS * kBBytes;
     static constexpr int kTmemCols = (2 * ACCS * BLOCK_N <= 128) ? 128 : (2 * ACCS * BLOCK_N <= 256) ? 256 : 512;
     static_assert(2 * ACCS * BLOCK_N <= 512, "accumulators exceed TMEM");
-    static_assert(TPS == 1 || TPS == 3 || TPS == 9, "taps per stage");
+    static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
+    static_assert(TAPS % TPS == 0 && (TPS == 1 || TPS == 3 || TPS == 9), "taps per stage");
     static_assert(ACCS * BLOCK_N >= 64, "each epilogue half owns whole 32-column chunks");
     static constexpr uint32_t kSBO = 8 * BLOCK_K * 2;
     static constexpr uint32_t kLayout = (BLOCK_K == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
@@ -62,12 +63,12 @@ __device__ __forceinline__ uint64_t slab_desc(uint32_t hi, uint32_t lo)
     return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
 
-template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS>
+template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS, int TAPS>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const SlabParams prm)
 {
-    using Cfg = SlabCfg<BLOCK_N, BLOCK_K, ACCS, TPS>;
+    using Cfg = SlabCfg<BLOCK_N, BLOCK_K, ACCS, TPS, TAPS>;
     constexpr int kTileM = Cfg::kTileM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -151,7 +152,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
             for (int cb = 0; cb < cblocks; ++cb) {
 #pragma unroll 1
-                for (int g = 0; g < 9 / TPS; ++g) {
+                for (int g = 0; g < TAPS / TPS; ++g) {
                     mbar_wait(&b_empty[stage], phase ^ 1, 2);
                     if (elect_one_sync()) {
                         uint8_t *sb = smem_b + (size_t)stage * Cfg::kBStageBytes;
@@ -189,7 +190,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
                 const uint32_t acc_first = cb != 0;  // tap 0, k 0 of block 0 overwrites the accumulator
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < TAPS; ++tap) {
                     if (tap % TPS == 0) {
                         mbar_wait(&b_full[sb_i], pb, 5);
                         tc_fence_after();
@@ -208,7 +209,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                           (tap == 0 && k == 0) ? acc_first : 1u);
                         }
                         if (tap % TPS == TPS - 1) umma_commit(&b_empty[sb_i]);
-                        if (tap == 8) {
+                        if (tap == TAPS - 1) {
                             umma_commit(&a_empty[sa_i]);
                             if (cb == cblocks - 1) umma_commit(&tfull_bar[buf]);
                         }
@@ -317,28 +318,29 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // -------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------
-// (BLOCK_N, BLOCK_K, ACCS, TPS): weight stages of 16-36 KB
-#define Y2_FOR_EACH_SLAB_CFG(X) \
-    X(256, 64, 1, 1) X(128, 64, 2, 1) X(64, 64, 2, 3) X(32, 64, 2, 9) X(256, 32, 1, 1) X(128, 32, 2, 3) \
-    X(64, 32, 2, 9) X(32, 32, 2, 9)
+// (BLOCK_N, BLOCK_K, ACCS, TPS, TAPS): 3x3 layers with weight stages of 16-36 KB, then the 1x1 layers
+#define Y2_FOR_EACH_SLAB_CFG(X)                                                                          \
+    X(256, 64, 1, 1, 9) X(128, 64, 2, 1, 9) X(64, 64, 2, 3, 9) X(32, 64, 2, 9, 9) X(256, 32, 1, 1, 9)      \
+    X(128, 32, 2, 3, 9) X(64, 32, 2, 9, 9) X(32, 32, 2, 9, 9) X(256, 64, 1, 1, 1) X(128, 64, 2, 1, 1)    \
+    X(64, 64, 2, 1, 1) X(32, 64, 2, 1, 1) X(128, 32, 2, 1, 1) X(64, 32, 2, 1, 1) X(32, 32, 2, 1, 1)
 
-static int slab_tps(int bn, int bk)
+static int slab_tps(int bn, int bk, int taps)
 {
-#define Y2_CASE(BN, BK, ACCS, TPS) \
-    if (bn == BN && bk == BK) return TPS;
+#define Y2_CASE(BN, BK, ACCS, TPS, TAPS) \
+    if (bn == BN && bk == BK && taps == TAPS) return TPS;
     Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
 #undef Y2_CASE
     return 0;
 }
 
-template <int BN, int BK, int ACCS, int TPS>
+template <int BN, int BK, int ACCS, int TPS, int TAPS>
 static int slab_prepare_cfg()
 {
     static bool attr_done[64] = {false};
     int dev = 0;
     Y2_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<BN, BK, ACCS, TPS>,
+        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<BN, BK, ACCS, TPS, TAPS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done[dev] = true;
     }
@@ -347,17 +349,17 @@ static int slab_prepare_cfg()
 
 int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 {
-    if (d->ksize != 3) return Y2_EINVAL;
+    const int taps = d->ksize * d->ksize;
     const int bn = d->block_n;
     const int accs = bn == 256 ? 1 : 2;
     const int tile_m = accs * kBlockM;
     const int bk = d->block_k;
-    const int tps = slab_tps(bn, bk);
+    const int tps = slab_tps(bn, bk, taps);
     if (!tps || d->npad % bn) return Y2_EINVAL;
     const int hp = d->h + 1, wp = d->w + 1;
     const long long total = (long long)d->batch * hp * wp;
     const int row_bytes = bk * 2;
-    const int halo = wp + 1;
+    const int halo = taps == 9 ? wp + 1 : 0;
     const int slab_rows = tile_m + 2 * halo;
     const int loads = (slab_rows + 255) / 256;
     int box_rows = (slab_rows + loads - 1) / loads;
@@ -367,11 +369,17 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int b_stage = tps * bn * bk * 2;
     const int aux = 2 * bn * 8 + 512;
     const int budget = 227 * 1024 - 1024 - aux;
-    const int stages_a = 2;
+    // 1x1: every channel block needs a fresh slab, keep as many slabs as weight tiles in flight
+    int stages_a = 2;
+    if (taps == 1) {
+        stages_a = budget / (slab_bytes + b_stage);
+        if (stages_a > kSlabMaxStagesA) stages_a = kSlabMaxStagesA;
+        if (stages_a < 2) return Y2_EINVAL;
+    }
     int stages_b = (budget - stages_a * slab_bytes) / b_stage;
     if (stages_b > kSlabMaxStagesB) stages_b = kSlabMaxStagesB;
     if (stages_b < 2 || (tps == 1 && stages_b < 3)) return Y2_EINVAL;
-    const int ktot = 9 * d->cin;
+    const int ktot = taps * d->cin;
     int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
                             (uint32_t)bk, (uint32_t)box_rows, bk);
     if (rc == Y2_OK)
@@ -409,9 +417,15 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     pl->smem_bytes = (size_t)stages_a * slab_bytes + (size_t)stages_b * b_stage + aux + 1024;
     const int tiles = p.tiles_m * p.tiles_n;
     const int sms = sm_count();
+    // 1x1 layers: the 256-position tiles pay off only while every SM still gets two or more of them and
+    // the output is the bf16 tensor (measured on B200: L5/L9/L13 +5..15%, the 13x13 layers and the fp32
+    // head are faster on the per-tap kernel's 128-position tiles)
+    if (taps == 1 && (tiles < 2 * sms || d->out_mode != Y2_OUT_BF16_PADDED) && !getenv("Y2_CONV_VARIANT"))
+        return Y2_EINVAL;
     pl->grid = tiles < sms ? tiles : sms;
-#define Y2_CASE(BN, BK, ACCS, TPS) \
-    if (bn == BN && bk == BK) return slab_prepare_cfg<BN, BK, ACCS, TPS>();
+    pl->taps = taps;
+#define Y2_CASE(BN, BK, ACCS, TPS, TAPS) \
+    if (bn == BN && bk == BK && taps == TAPS) return slab_prepare_cfg<BN, BK, ACCS, TPS, TAPS>();
     Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
 #undef Y2_CASE
     return Y2_EINVAL;
@@ -419,12 +433,12 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 
 int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
-#define Y2_CASE(BN, BK, ACCS, TPS)                                                                        \
-    if (pl->block_n == BN && pl->block_k == BK) {                                                         \
-        conv_slab_kernel<BN, BK, ACCS, TPS><<<pl->grid, kSlabThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, \
-                                                                                            pl->slab);    \
-        Y2_LAUNCH_CHECK();                                                                                \
-        return Y2_OK;                                                                                     \
+#define Y2_CASE(BN, BK, ACCS, TPS, TAPS)                                                                       \
+    if (pl->block_n == BN && pl->block_k == BK && pl->taps == TAPS) {                                            \
+        conv_slab_kernel<BN, BK, ACCS, TPS, TAPS><<<pl->grid, kSlabThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, \
+                                                                                                  pl->slab);     \
+        Y2_LAUNCH_CHECK();                                                                                       \
+        return Y2_OK;                                                                                            \
     }
     Y2_FOR_EACH_SLAB_CFG(Y2_CASE)
 #undef Y2_CASE
