@@ -301,7 +301,7 @@ def main() -> int:
     table = []
     flops_img = lib.network_conv_flops(net)
     KERNELS = {0: "conv_tcgen05_kernel (per-tap)", 1: "conv_slab_kernel", 2: "conv_pair_kernel (cta_group::2)",
-               3: "stem_conv_pool_kernel"}
+               3: "conv_pool_kernel (conv + maxpool)", 4: "stem_conv_pool_kernel"}
     per_kernel = {}  # variant -> [ms, flops, launches]
     for i in range(n_layers):
         l = net.layers[i]

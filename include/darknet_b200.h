@@ -282,7 +282,8 @@ void *network_stream(network net);
 /* Algorithmic conv FLOPs per image: sum 2*n*k*k*c*out_h*out_w (darknet.c:115-131 `operations`). */
 double network_conv_flops(network net);
 /* Kernel that runs convolutional layer i: 0 per-tap implicit GEMM, 1 halo-slab, 2 CTA-pair
- * (cta_group::2), 3 fused first layer (conv + maxpool); -1 if layer i is not a convolution. */
+ * (cta_group::2), 3 conv + maxpool, 4 fused first layer (conv + maxpool from the fp32 image);
+ * -1 if layer i is not a convolution. */
 int network_conv_kernel(network net, int i);
 /* Number of kernel launches one forward issues (diagnostics / bench `gpu_launches`). */
 int network_launch_count(network net);

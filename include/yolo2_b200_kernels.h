@@ -83,6 +83,10 @@ int y2_event_destroy(y2_event_t e);
 
 #define Y2_OUT_BF16_PADDED 0 /* bf16 [B][H+1][W+1][out_cs], pads written as 0 */
 #define Y2_OUT_F32_FLAT 1    /* fp32 [B][H*W][out_cs] (the reference's "flatten"ed NHWC) */
+#define Y2_OUT_BF16_POOLED 2 /* the convolution AND the 2x2/2 maxpool behind it (maxpool_layer_kernels.cu:10-48):
+                              * bf16 [B][H/2+1][W/2+1][out_cs], pads left untouched (zero at plan time).  3x3 layers
+                              * with cin == block_k and cout == npad in {64, 128}, leaky / linear, alpha >= 0 (a
+                              * filter with negative alpha has weights and alpha negated by the caller) */
 
 typedef struct y2_conv_desc {
     const void *in;   /* bf16 padded NHWC, already offset to the first input channel */
@@ -112,7 +116,7 @@ void y2_conv_plan_destroy(y2_conv_plan *plan);
  * business; this returns the number of MMA tiles for diagnostics. */
 int y2_conv_plan_tiles(const y2_conv_plan *plan);
 /* which kernel the plan launches: 0 per-tap (conv_tcgen05_kernel), 1 halo slab (conv_slab_kernel),
- * 2 CTA pair (conv_pair_kernel, tcgen05.mma.cta_group::2) */
+ * 2 CTA pair (conv_pair_kernel, tcgen05.mma.cta_group::2), 3 conv + maxpool (conv_pool_kernel) */
 int y2_conv_plan_variant(const y2_conv_plan *plan);
 
 /* ---- first layer (replaces, for a 3x3/1 'same' convolution over <= 3 input channels followed by a

@@ -45,7 +45,23 @@ struct SlabParams {
     void *out;
 };
 
-enum { kVariantPerTap = 0, kVariantSlab = 1, kVariantPair = 2 };
+// ---- conv + 2x2 maxpool kernel (conv_pool.cu) ------------------------------------------
+struct PoolParams {
+    int batch, h, w;       // conv extent (stride-1 'same': input == output extent)
+    int oh, ow;            // pooled extent
+    int wt;                // image columns per tile (even); patch row = wt + 2 positions
+    int rows;              // image rows per patch (even)
+    int tiles_x, tiles_y, total_tiles;
+    int patch_bytes;       // bytes per patch stage (multiple of 1024)
+    int stages_b;
+    int act;
+    const float *alpha;
+    const float *beta;
+    __nv_bfloat16 *out;    // pooled padded NHWC [B][oh+1][ow+1][out_cs]
+    int out_cs;
+};
+
+enum { kVariantPerTap = 0, kVariantSlab = 1, kVariantPair = 2, kVariantPool = 3 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -64,6 +80,7 @@ struct y2_conv_plan {
     int variant;
     y2::ConvParams prm;
     y2::SlabParams slab;
+    y2::PoolParams pool;
     int block_n, block_k, taps;
     int grid;
     size_t smem_bytes;
@@ -77,4 +94,7 @@ int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
 // conv_pair.cu: the CTA-pair (cta_group::2) kernel for wide 3x3 layers, same contract
 int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d);
 int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
+// conv_pool.cu: 3x3 convolution fused with the following 2x2/2 maxpool (out_mode Y2_OUT_BF16_POOLED)
+int pool_plan_init(y2_conv_plan *pl, const y2_conv_desc *d);
+int pool_plan_launch(const y2_conv_plan *pl, cudaStream_t st);
 } // namespace y2

@@ -349,7 +349,7 @@ extern "C" int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **out_pla
                   "in_cs=%d cout=%d)", d->block_n, d->block_k, d->ksize, d->cin, d->npad, d->in_cs, d->cout);
         return Y2_EINVAL;
     }
-    if (d->out_mode == Y2_OUT_BF16_PADDED && (d->out_cs % 8 || d->cout % 8 ||
+    if (d->out_mode != Y2_OUT_F32_FLAT && (d->out_cs % 8 || d->cout % 8 ||
                                               ((uintptr_t)d->out & 15))) {
         set_error("y2_conv_plan_create: bf16 output needs 16-byte aligned channel slices");
         return Y2_EINVAL;
@@ -372,6 +372,15 @@ extern "C" int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **out_pla
     // kernel choice: CTA-pair kernel for wide 3x3 layers, halo-slab kernel for the other 3x3 layers, this
     // file's per-tap kernel for 1x1 layers and whatever does not fit.  Y2_CONV_VARIANT=pertap|slab|pair
     // restricts the choice (tests, A/B timing).
+    if (d->out_mode == Y2_OUT_BF16_POOLED) {
+        const int rc = pool_plan_init(pl, d);
+        if (rc != Y2_OK) {
+            delete pl;
+            return rc;
+        }
+        *out_plan = pl;
+        return Y2_OK;
+    }
     const char *forced = getenv("Y2_CONV_VARIANT");
     const bool allow_pair = !forced || !strcmp(forced, "pair");
     const bool allow_slab = !forced || !strcmp(forced, "slab") || !strcmp(forced, "pair");
@@ -441,6 +450,7 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
     using namespace y2;
     if (!pl) return Y2_EINVAL;
     cudaStream_t st = to_stream(s);
+    if (pl->variant == kVariantPool) return pool_plan_launch(pl, st);
     if (pl->variant == kVariantPair) return pair_plan_launch(pl, st);
     if (pl->variant == kVariantSlab) return slab_plan_launch(pl, st);
 #define Y2_CASE(BN, BK) \
@@ -461,5 +471,6 @@ extern "C" int y2_conv_plan_variant(const y2_conv_plan *pl)
 extern "C" int y2_conv_plan_tiles(const y2_conv_plan *pl)
 {
     if (!pl) return 0;
+    if (pl->variant == y2::kVariantPool) return pl->pool.total_tiles;
     return pl->variant != y2::kVariantPerTap ? pl->slab.tiles_m * pl->slab.tiles_n : pl->prm.tiles_m * pl->prm.tiles_n;
 }

@@ -40,7 +40,9 @@ typedef struct y2_layer_rt {
     int use_patches, kpad;
     int stem_fused;     /* layer 0: conv + the following 2x2/2 maxpool run as one kernel that writes
                            the maxpool layer's buffer; this layer has no device output of its own */
-    int fused_into_prev; /* layer 1 of such a pair: its forward is a no-op */
+    int pool_fused;     /* a later 3x3 conv whose 2x2/2 maxpool runs in its epilogue (Y2_OUT_BF16_POOLED): same
+                           convention, the conv writes the maxpool layer's buffer */
+    int fused_into_prev; /* the maxpool of such a pair: its forward is a no-op */
     void *patches;      /* bf16 [B][H+1][W+1][kpad] */
     int wt_dirty;
     /* input packing for a non-patch first layer */

@@ -524,8 +524,8 @@ void y2_push_convolutional_layer(layer *l)
             beta[f] = l->biases[f];
         }
     }
-    if (r->stem_fused) {
-        /* the fused conv+maxpool kernel takes the max before the affine map, which needs alpha >= 0:
+    if (r->stem_fused || r->pool_fused) {
+        /* the fused conv+maxpool kernels take the max before the affine map, which needs alpha >= 0:
          * negate the filter and its alpha together (alpha*acc is unchanged bit for bit) */
         for (int f = 0; f < l->n; ++f)
             if (alpha[f] < 0) {
@@ -551,24 +551,44 @@ static int pick_block_n(int cout)
     return 256;
 }
 
-/* layer 0 = 3x3/1 'same' conv over <= 3 channels with <= 32 filters, leaky/linear, feeding ONLY a
- * 2x2/2 maxpool without padding: run both as the fused first-layer kernel */
-static int stem_fusable(network *net, int i)
+/* conv i is a 3x3/1 'same' leaky/linear layer whose output feeds ONLY the 2x2/2 unpadded maxpool
+ * right behind it (no route / shortcut reads the full-resolution tensor) */
+static int feeds_only_pool2x2(network *net, int i)
 {
-    if (i != 0 || net->n < 2 || getenv("Y2_NO_STEM_FUSION")) return 0;
-    layer *l = &net->layers[0], *m = &net->layers[1];
-    if (l->size != 3 || l->stride != 1 || l->pad != 1 || l->c > 3 || l->n > 32) return 0;
+    if (i + 1 >= net->n) return 0;
+    layer *l = &net->layers[i], *m = &net->layers[i + 1];
+    if (l->size != 3 || l->stride != 1 || l->pad != 1) return 0;
     if (l->activation != LEAKY && l->activation != LINEAR) return 0;
     if (m->type != MAXPOOL || m->size != 2 || m->stride != 2 || m->pad != 0) return 0;
-    if (l->h < 2 || l->w < 2) return 0;
-    for (int j = 2; j < net->n; ++j) {
+    if (l->out_h < 2 || l->out_w < 2) return 0;
+    for (int j = i + 2; j < net->n; ++j) {
         layer *lj = &net->layers[j];
         if (lj->type == ROUTE)
             for (int k = 0; k < lj->n; ++k)
-                if (lj->input_layers[k] == 0) return 0;
-        if (lj->type == SHORTCUT && lj->index == 0) return 0;
+                if (lj->input_layers[k] == i) return 0;
+        if (lj->type == SHORTCUT && lj->index == i) return 0;
     }
     return 1;
+}
+
+/* layer 0 over <= 3 channels with <= 32 filters: conv + pool run as the fused first-layer kernel */
+static int stem_fusable(network *net, int i)
+{
+    if (i != 0 || getenv("Y2_NO_STEM_FUSION")) return 0;
+    layer *l = &net->layers[0];
+    if (l->c > 3 || l->n > 32) return 0;
+    return feeds_only_pool2x2(net, 0);
+}
+
+/* a later conv with one channel block (<= 64 stored input channels) and exactly 64 or 128 filters: the
+ * maxpool runs in the convolution's epilogue (conv_pool.cu) */
+static int pool_fusable(network *net, int i, int cin_pad)
+{
+    if (i == 0 || getenv("Y2_NO_POOL_FUSION")) return 0;
+    layer *l = &net->layers[i];
+    if (cin_pad != 32 && cin_pad != 64) return 0;
+    if (l->n != 64 && l->n != 128) return 0;
+    return feeds_only_pool2x2(net, i);
 }
 
 /* view of the tensor a layer reads through state.input */
@@ -634,7 +654,13 @@ static void build_conv_plan(network *net, int i, int batch)
     d.act = (l->activation == LEAKY) ? Y2_ACT_LEAKY : (l->activation == LOGISTIC) ? Y2_ACT_LOGISTIC : Y2_ACT_LINEAR;
     d.out = r->out;
     d.out_cs = r->out_cs;
-    if (r->out_kind == Y2_KIND_F32_FLAT) {
+    if (r->pool_fused) {
+        y2_layer_rt *mr = (y2_layer_rt *)net->layers[i + 1].b200;
+        d.out = mr->out;
+        d.out_cs = mr->out_cs;
+        d.out_mode = Y2_OUT_BF16_POOLED;
+        d.cout = r->cpad;
+    } else if (r->out_kind == Y2_KIND_F32_FLAT) {
         d.out_mode = Y2_OUT_F32_FLAT;
         d.cout = l->n;
     } else {
@@ -715,6 +741,7 @@ void y2_plan_network(network *net)
                 r->cin_pad = cin_pad;
                 r->block_k = (cin_pad % 64 == 0) ? 64 : 32;
                 r->ktot = kk * cin_pad;
+                r->pool_fused = r->out_kind == Y2_KIND_BF16_PADDED && r->cpad == l->n && pool_fusable(net, i, cin_pad);
             }
             break;
         }
@@ -724,7 +751,7 @@ void y2_plan_network(network *net)
             if (!pr || pr->out_kind != Y2_KIND_BF16_PADDED) unsupported(i, "maxpool/reorg without a tensor input");
             if (l->type == REORG && l->reverse) unsupported(i, "reverse reorg");
             r->out_kind = Y2_KIND_BF16_PADDED;
-            if (l->type == MAXPOOL && pr->stem_fused) r->fused_into_prev = 1;
+            if (l->type == MAXPOOL && (pr->stem_fused || pr->pool_fused)) r->fused_into_prev = 1;
             if (l->type == MAXPOOL) r->cpad = pr->cpad;
             else {
                 if (pr->cpad != l->c) unsupported(i, "reorg of a channel-padded tensor");
@@ -822,7 +849,7 @@ void y2_plan_network(network *net)
         layer *l = &net->layers[i];
         y2_layer_rt *r = (y2_layer_rt *)l->b200;
         if (l->type == ROUTE || r->out_kind == Y2_KIND_NONE) continue;
-        if (r->stem_fused) { /* the full-resolution activation is never materialised */
+        if (r->stem_fused || r->pool_fused) { /* the full-resolution activation is never materialised */
             r->out = 0;
             r->out_cs = r->cpad;
             continue;
@@ -952,7 +979,7 @@ void forward_maxpool_layer_gpu(layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
-    if (r->fused_into_prev) return; /* the first-layer kernel already wrote this layer's output */
+    if (r->fused_into_prev) return; /* the convolution before it already wrote this layer's output */
     Y2_CHECK(y2_maxpool(pr->out, pr->out_cs, r->out, r->out_cs, l.batch, r->cpad, l.h, l.w, l.out_h, l.out_w,
                         l.size, l.stride, l.pad, net_stream(state.net)));
     count_launch(state.net, 1);
@@ -1145,13 +1172,14 @@ int network_launch_count(network net)
     return rt ? rt->launches : 0;
 }
 
-/* kernel behind layer i: 0 per-tap, 1 halo slab, 2 CTA pair, 3 fused first layer, -1 not a convolution */
+/* kernel behind layer i: 0 per-tap, 1 halo slab, 2 CTA pair, 3 conv + maxpool, 4 fused first layer,
+ * -1 not a convolution */
 int network_conv_kernel(network net, int i)
 {
     if (i < 0 || i >= net.n || net.layers[i].type != CONVOLUTIONAL) return -1;
     y2_layer_rt *r = y2_lrt(net.layers[i]);
     if (!r) return -1;
-    if (r->stem_fused) return 3;
+    if (r->stem_fused) return 4;
     return r->plan ? y2_conv_plan_variant(r->plan) : -1;
 }
 
@@ -1259,6 +1287,27 @@ static float *export_layer(network net, int i)
         Y2_CHECK(y2_stream_sync(rt->stream));
         y2_conv_plan_destroy(plan);
         y2_free(patches);
+        y2_free(full);
+    } else if (r->pool_fused) {
+        /* inspection path: the conv+pool kernel never stores the full-resolution activation, recompute it
+         * from the (still resident) input with the plain convolution kernel into a scratch buffer */
+        void *full = dev_alloc_zero(padded_bytes(net.batch, l->out_h, l->out_w, r->cpad));
+        y2_view v = input_view(&net, i);
+        y2_conv_desc d;
+        memset(&d, 0, sizeof(d));
+        d.in = v.ptr; d.in_cs = v.cs; d.cin = r->cin_pad; d.ksize = l->size;
+        d.batch = net.batch; d.h = l->out_h; d.w = l->out_w;
+        d.wt = r->wt_dev; d.cout = r->cpad; d.npad = r->npad; d.block_n = r->block_n; d.block_k = r->block_k;
+        d.alpha = r->alpha_dev; d.beta = r->beta_dev;
+        d.act = (l->activation == LEAKY) ? Y2_ACT_LEAKY : Y2_ACT_LINEAR;
+        d.out = full; d.out_cs = r->cpad; d.out_mode = Y2_OUT_BF16_PADDED;
+        y2_conv_plan *plan = 0;
+        Y2_CHECK(y2_conv_plan_create(&d, &plan));
+        Y2_CHECK(y2_conv_plan_launch(plan, rt->stream));
+        Y2_CHECK(y2_unpack_to_nchw_f32(full, rt->export_dev, net.batch, l->out_c, l->out_h, l->out_w, r->cpad,
+                                       rt->stream));
+        Y2_CHECK(y2_stream_sync(rt->stream));
+        y2_conv_plan_destroy(plan);
         y2_free(full);
     } else if (r->out_kind == Y2_KIND_BF16_PADDED) {
         Y2_CHECK(y2_unpack_to_nchw_f32(r->out, rt->export_dev, net.batch, l->out_c, l->out_h, l->out_w, r->out_cs,

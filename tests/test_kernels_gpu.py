@@ -311,3 +311,29 @@ def test_stem_conv_pool_matches_fp32_reference(batch, c, h, w, n):
     assert out[:, oh, :, :].abs().max().item() == 0 and out[:, :, ow, :].abs().max().item() == 0
     if n < 32:
         assert out[..., n:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("batch,cin,h,w,cout", [(2, 32, 208, 208, 64), (2, 64, 104, 104, 128), (1, 32, 50, 38, 64),
+                                                (3, 64, 26, 30, 64), (2, 32, 13, 13, 128)])
+def test_conv_pool_fused_matches_fp32_reference(batch, cin, h, w, cout):
+    """3x3 conv + affine + leaky + 2x2/2 maxpool in one launch (Y2_OUT_BF16_POOLED) against PyTorch
+    fp32 on the same bf16-rounded operands.  Tolerance 1e-2 of the tensor max (bf16 output rounding)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5 + cin + cout + h)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev) * 2 - 1
+    wt = (torch.rand(cout, cin, 3, 3, generator=g).to(dev) * 2 - 1) * (2.0 / (9 * cin)) ** 0.5
+    alpha = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    beta = (torch.rand(cout, generator=g) * 0.2 - 0.1).to(dev)
+    x_p = G.to_padded_nhwc(x)
+    wt_p = G.pack_weights(wt, cin, cout)
+    oh, ow = h // 2, w // 2
+    out_cs = cout + 64
+    out = torch.zeros(batch, oh + 1, ow + 1, out_cs, dtype=torch.bfloat16, device=dev)
+    G.run_conv(x_p, cin, cin, batch, h, w, 3, wt_p, cout, cout, cout, cin, alpha, beta, ACT_LEAKY, out, out_cs, 2)
+    ref = torch.nn.functional.max_pool2d(_ref_conv(x, wt, alpha, beta, ACT_LEAKY, 3), 2, 2)
+    got = G.from_padded_nhwc(out, cout, oh, ow)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-2, f"max err / max|ref| = {err:.3e}"
+    # pads and the neighbouring channels of the wider buffer stay untouched
+    assert out[:, oh].abs().max().item() == 0 and out[:, :, ow].abs().max().item() == 0
+    assert out[..., cout:].abs().max().item() == 0
