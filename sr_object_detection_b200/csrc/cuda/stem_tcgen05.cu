@@ -21,10 +21,11 @@
 // replicated per tap.  Two accumulators hold image rows y and y+1 in the same TMEM lanes, so the
 // 2x2 pool is a vertical max inside a thread and one shuffle with the neighbouring lane.
 //
-// Warp roles (576 threads): 0-7 converters (fp32 -> bf16 patch rows), 8 MMA issuer (+ TMEM alloc),
-// 9 TMA loader (the raw fp32 box of the next patch, zero-filled outside the image by the TMA unit),
-// 10-17 epilogue (two groups of four warps alternate over slots of two row pairs; TMEM lane quarter
-// = warp & 3).  Images whose row pitch is not a multiple of 16 bytes cannot be described by a tensor
+// Warp roles (768 threads): 0-5 converters (fp32 -> bf16 patch rows), 6 MMA issuer (+ TMEM alloc),
+// 7 TMA loader (the raw fp32 box of the next patch, zero-filled outside the image by the TMA unit),
+// 8-23 epilogue: four groups of four warps = (slot parity) x (channel half); the epilogue is a long
+// dependent chain per thread, so it is spread over many warps, each draining 16 of the 32 channels
+// of its slots (TMEM lane quarter = warp & 3).  Images whose row pitch is not a multiple of 16 bytes cannot be described by a tensor
 // map; for those the converters read global memory directly.
 //
 // max before the affine map is exact: the host makes every alpha_f >= 0 (a filter with negative
@@ -37,8 +38,9 @@
 
 namespace y2 {
 
-constexpr int kStemProducerWarps = 8;
-constexpr int kStemThreads = (kStemProducerWarps + 2 + 8) * 32;  // 576
+constexpr int kStemProducerWarps = 6;
+constexpr int kStemEpilogueWarps = 16;
+constexpr int kStemThreads = (kStemProducerWarps + 2 + kStemEpilogueWarps) * 32;  // 768
 constexpr int kStemN = 32;          // filters (padded)
 constexpr int kStemK = 32;          // K stride of the weight matrix handed in by the host (27 used)
 constexpr int kStemRows = 16;       // image rows per patch (8 pooled rows)
@@ -127,7 +129,7 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
         }
         for (int i = 0; i < kStemSlots; ++i) {
             mbar_init(&sm.t_full[i], 1);
-            mbar_init(&sm.t_empty[i], 128);
+            mbar_init(&sm.t_empty[i], 256);  // both channel-half groups
         }
         fence_barrier_init();
     }
@@ -279,44 +281,47 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
         }
     } else {
         // ===================== epilogue: 2x2 max, affine, leaky, store =====================
-        const int ew = warp - (kStemProducerWarps + 2);  // 0..7
-        const int group = ew >> 2;                       // slots alternate between the two groups
+        const int ew = warp - (kStemProducerWarps + 2);  // 0..15
+        const int sgroup = ew >> 3;                      // slots alternate between the two slot groups
+        const int chalf = (ew >> 2) & 1;                 // channels [16 chalf, 16 chalf + 16)
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;               // TMEM lane == position inside the tile row
-        const int hsel = lane & 1;                       // even lane: channels 0-15, odd lane: 16-31
-        float al[16], be[16];
+        const int hsel = lane & 1;                       // even lane finishes 8 channels, odd lane the other 8
+        const int cbase = chalf * 16 + hsel * 8;         // first channel this thread stores
+        float al[8], be[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            al[q] = sm.alpha[hsel * 16 + q];
-            be[q] = sm.beta[hsel * 16 + q];
+        for (int q = 0; q < 8; ++q) {
+            al[q] = sm.alpha[cbase + q];
+            be[q] = sm.beta[cbase + q];
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int b = tile / per_img;
             const int t = tile - b * per_img;
             const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-            for (int jp = 2 * group; jp < pairs; jp += 4)
+            for (int jp = 2 * sgroup; jp < pairs; jp += 4)
             for (int j = jp; j < jp + 2; ++j) {
                 const int slot = j >> 1;
                 if ((j & 1) == 0) {
                     mbar_wait_relaxed(&sm.t_full[slot], (uint32_t)(it & 1), 13);
                     tc_fence_after();
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 128 + (j & 1) * 64);
-                uint32_t v[32], u[32];
-                tmem_ld32(taddr, v);
-                tmem_ld32(taddr + 32u, u);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                       (uint32_t)(slot * 128 + (j & 1) * 64 + chalf * 16);
+                uint32_t v[16], u[16];
+                tmem_ld16(taddr, v);
+                tmem_ld16(taddr + 32u, u);
                 tmem_ld_wait();
                 if (j & 1) {  // both row pairs of the slot are in registers
                     tc_fence_before();
                     mbar_arrive(&sm.t_empty[slot]);
                 }
-                // vertical max, then the horizontal partner's half of the channels
-                float mx[16];
+                // vertical max in-thread, then trade halves with the horizontal neighbour
+                float mx[8];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     const float lo = fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q]));
-                    const float hi = fmaxf(__uint_as_float(v[q + 16]), __uint_as_float(u[q + 16]));
+                    const float hi = fmaxf(__uint_as_float(v[q + 8]), __uint_as_float(u[q + 8]));
                     const float send = hsel ? lo : hi;  // what the partner keeps
                     const float keep = hsel ? hi : lo;
                     const float got = __shfl_xor_sync(0xffffffffu, send, 1);
@@ -325,9 +330,9 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
                 const int oy = ty * (kStemRows / 2) + j;
                 const int ox = (tx * p.wt + m) >> 1;
                 if (m < p.wt && oy < p.oh && ox < p.ow) {
-                    uint32_t pk[8];
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         float y0 = fmaf(mx[2 * q], al[2 * q], be[2 * q]);
                         float y1 = fmaf(mx[2 * q + 1], al[2 * q + 1], be[2 * q + 1]);
                         if (p.act == Y2_ACT_LEAKY) {
@@ -336,9 +341,8 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
                         }
                         pk[q] = pack_bf16x2(y0, y1);
                     }
-                    __nv_bfloat16 *o = p.out + (((size_t)b * (p.oh + 1) + oy) * (p.ow + 1) + ox) * p.out_cs + hsel * 16;
+                    __nv_bfloat16 *o = p.out + (((size_t)b * (p.oh + 1) + oy) * (p.ow + 1) + ox) * p.out_cs + cbase;
                     *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4 *>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
         }
