@@ -19,15 +19,16 @@
 // Restricted to one channel block (C_in <= 64) and 64 / 128 filters; weights are streamed per row
 // pair exactly like conv_slab.cu streams them per tile.
 //
-// Warp roles (352 threads): 0 patch producer, 1 MMA issuer (+ TMEM alloc), 2 weight producer,
-// 3..10 epilogue (two groups of four warps alternate over the row pairs).
+// Warp roles (608 threads): 0 patch producer, 1 MMA issuer (+ TMEM alloc), 2 weight producer,
+// 3..18 epilogue: four groups of four warps = (row-pair parity) x (half of every 32-channel chunk);
+// the epilogue is a long dependent chain per thread, so it is spread over many warps.
 #include "conv_plan.cuh"
 
 #include <stdlib.h>
 
 namespace y2 {
 
-constexpr int kPoolThreads = 352;
+constexpr int kPoolThreads = 608;  // 3 producer / MMA warps + 16 epilogue warps
 constexpr int kPoolMaxStagesB = 8;
 constexpr int kPoolStagesA = 2;
 
@@ -98,7 +99,7 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         for (int i = 0; i < Cfg::kSlots; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 128);
+            mbar_init(&tempty_bar[i], 256);  // both channel-half groups
         }
         fence_barrier_init();
     }
@@ -209,17 +210,19 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else {
         // ===================== epilogue: 2x2 max, affine, leaky, store =====================
-        const int ew = warp - 3;           // 0..7
-        const int group = ew >> 2;         // row pairs alternate between the two groups
+        const int ew = warp - 3;             // 0..15
+        const int pgroup = ew >> 3;          // row pairs alternate between the two pair groups
+        const int chalf = (ew >> 2) & 1;     // columns [16 chalf, 16 chalf + 16) of every 32-column chunk
         const int quarter = warp & 3;
-        const int m = quarter * 32 + lane; // TMEM lane == position inside the tile row
-        const int hsel = lane & 1;         // even lane finishes channels [0,16) of a 32-chunk, odd lane [16,32)
+        const int m = quarter * 32 + lane;   // TMEM lane == position inside the tile row
+        const int hsel = lane & 1;           // even lane finishes 8 of those channels, odd lane the other 8
+        const int cbase = chalf * 16 + hsel * 8;
         int it = 0;
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
             const int b = tile / per_img;
             const int t = tile - b * per_img;
             const int ty = t / prm.tiles_x, tx = t - ty * prm.tiles_x;
-            for (int j = group; j < pairs; j += 2) {
+            for (int j = pgroup; j < pairs; j += 2) {
                 const int slot_it = it * pairs + j;
                 const int slot = slot_it % Cfg::kSlots;
                 mbar_wait_relaxed(&tfull_bar[slot], (uint32_t)(slot_it / Cfg::kSlots) & 1u, 6);
@@ -227,33 +230,34 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int oy = (ty * prm.rows >> 1) + j;
                 const int ox = (tx * prm.wt + m) >> 1;
                 const bool ok = m < prm.wt && oy < prm.oh && ox < prm.ow;
-                __nv_bfloat16 *o = prm.out + (((size_t)b * (prm.oh + 1) + oy) * (prm.ow + 1) + ox) * prm.out_cs + hsel * 16;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * Cfg::kSlotCols);
+                __nv_bfloat16 *o = prm.out + (((size_t)b * (prm.oh + 1) + oy) * (prm.ow + 1) + ox) * prm.out_cs + cbase;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                       (uint32_t)(slot * Cfg::kSlotCols + chalf * 16);
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(taddr + (uint32_t)c0, v);
-                    tmem_ld32(taddr + (uint32_t)(BLOCK_N + c0), u);
+                    uint32_t v[16], u[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    tmem_ld16(taddr + (uint32_t)(BLOCK_N + c0), u);
                     tmem_ld_wait();
-                    if (c0 + 32 >= BLOCK_N) {  // slot drained into registers
+                    if (c0 + 32 >= BLOCK_N) {  // this thread's share of the slot is in registers
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[slot]);
                     }
-                    float mx[16];
+                    float mx[8];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
+                    for (int q = 0; q < 8; ++q) {
                         const float lo = fmaxf(__uint_as_float(v[q]), __uint_as_float(u[q]));
-                        const float hi = fmaxf(__uint_as_float(v[q + 16]), __uint_as_float(u[q + 16]));
+                        const float hi = fmaxf(__uint_as_float(v[q + 8]), __uint_as_float(u[q + 8]));
                         const float send = hsel ? lo : hi;  // what the partner keeps
                         const float keep = hsel ? hi : lo;
                         const float got = __shfl_xor_sync(0xffffffffu, send, 1);
                         mx[q] = fmaxf(keep, got);
                     }
                     if (ok) {
-                        const float4 *ab4 = reinterpret_cast<const float4 *>(s_ab + c0 + hsel * 16);
-                        uint32_t pk[8];
+                        const float4 *ab4 = reinterpret_cast<const float4 *>(s_ab + c0 + cbase);
+                        uint32_t pk[4];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
+                        for (int q = 0; q < 4; ++q) {
                             const float4 ab = ab4[q];  // (alpha, beta) of two filters
                             float y0 = fmaf(mx[2 * q], ab.x, ab.y);
                             float y1 = fmaf(mx[2 * q + 1], ab.z, ab.w);
@@ -264,7 +268,6 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             pk[q] = pack_bf16x2(y0, y1);
                         }
                         *reinterpret_cast<uint4 *>(o + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(o + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
             }
