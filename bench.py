@@ -211,7 +211,10 @@ def main() -> int:
     lib.cuda_set_device(local_rank)
     net = dn.parse_network_cfg(cfg)
     dn.load_weights(net, weights)
-    images = synth.images(B, 3, SIDE, SIDE, seed=SEED_X + rank * B)
+    from sr_object_detection_b200 import dp
+    lo, hi = dp.shard_range(rank, world, B * world)  # this rank's slice of the global batch (weak scaling)
+    assert hi - lo == B
+    images = synth.images(B, 3, SIDE, SIDE, seed=SEED_X + lo)
     stream = C.c_void_p(lib.network_stream(net))
 
     # stage the batch once in the pinned buffer; `value` keeps it resident in HBM
