@@ -193,6 +193,8 @@ def main() -> int:
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own banner / logs go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available():
