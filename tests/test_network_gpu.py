@@ -30,11 +30,14 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
     return cfg, weights, x, inp
 
 
-@pytest.mark.parametrize("name,batch", [("tiny-yolo-voc", 2), ("yolo-voc", 2)])
-def test_layer_activations_match_reference(tmp_path, name, batch):
+@pytest.mark.parametrize("name,batch,side", [("tiny-yolo-voc", 2, 416), ("yolo-voc", 2, 416), ("yolo", 1, 608),
+                                             ("darknet19_448", 1, 448), ("yolo-voc", 3, 320)])
+def test_layer_activations_match_reference(tmp_path, name, batch, side):
+    """BASELINE.json configs 1-3 and 5 (at a batch the CPU reference finishes in seconds): every layer of
+    the B200 forward pass against the reference's CPU forward on the same weights and images."""
     if not R.have_ref():
         pytest.skip("oracle/_ref/darknet_ref not built")
-    cfg, weights, x, inp = _setup(tmp_path, name, batch)
+    cfg, weights, x, inp = _setup(tmp_path, name, batch, w=side, h=side)
     ref_dir = tmp_path / "ref"
     R.forward(R.REF_BIN, cfg, weights, inp, ref_dir, thresh=0.24, nms=0.4)
 
