@@ -285,11 +285,29 @@ def main() -> int:
     ms_dev = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same pipeline fed with raw uint8 RGB images (what an image decoder hands over): a quarter of the upload
+    u8_images = np.random.default_rng(SEED_X + lo).integers(0, 256, size=(B, SIDE, SIDE, 3), dtype=np.uint8)
+    pipe_stage_u8 = [lib.network_pipeline_staging_u8(net, s) for s in (0, 1)]
+    for ps in pipe_stage_u8:
+        C.memmove(ps, u8_images.ctypes.data, u8_images.nbytes)
+
+    def submit_u8():
+        lib.network_detect_submit_u8(net, pipe_stage_u8[lib.network_pipeline_next_slot(net)], THRESH, NMS, MAX_DET)
+
+    def run_e2e_u8(steps):
+        submit_u8()
+        for _ in range(1, steps):
+            submit_u8()
+            lib.network_detect_wait(net, dets, counts, MAX_DET)
+        lib.network_detect_wait(net, dets, counts, MAX_DET)
+
     for _ in range(3):
         step_e2e_sync()
     ms_e2e_sync = timed(step_e2e_sync, args.steps)
     run_e2e_pipelined(3)
     ms_e2e = timed(lambda: run_e2e_pipelined(args.steps), 1)
+    run_e2e_u8(3)
+    ms_e2e_u8 = timed(lambda: run_e2e_u8(args.steps), 1)
 
     # per-layer device times (eager pass with CUDA events on the network stream), for the
     # roofline of the dominant kernel: the tcgen05 convolution
@@ -370,6 +388,11 @@ def main() -> int:
                        "dets, counts, max_det), two batches in flight",
                 "sync_value": round(total_images / (ms_e2e_sync / 1000.0), 1),
                 "sync_api": "network_detect_batch(net, host_images, thresh, nms, dets, counts, max_det)"},
+        "e2e_u8": {"value": round(total_images / (ms_e2e_u8 / 1000.0), 1), "unit": "images/s",
+                   "ms_per_step": round(ms_e2e_u8 / args.steps, 4), "h2d_bytes_per_step": int(u8_images.nbytes),
+                   "d2h_bytes_per_step": int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4),
+                   "api": "network_detect_submit_u8(net, pinned_uint8_rgb_images, ...) / network_detect_wait: raw decoded "
+                          "images, byte/255 on the device (bit-identical detections to the float call)"},
         "gpu_launches": int((launches_fwd + detect_launches) * args.steps),
         "clocks": clocks,
     }

@@ -275,6 +275,16 @@ float *network_pipeline_staging(network net, int slot);
 int network_pipeline_next_slot(network net); /* slot the next network_detect_submit will use */
 int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det);
 int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det);
+/* The same calls fed with raw decoded images: uint8 interleaved RGB [batch][h][w][3] at the network's
+ * resolution.  Each byte becomes (float)(byte / 255.) on the device exactly as the reference's loaders
+ * do on the host (yolo_v2_class.cpp:129-149 load_image_stb; yolo_v2_class.hpp mat_to_image), so the
+ * detections are identical to the float calls on the converted image, at a quarter of the upload.
+ * Needs a network whose first layer is the fused first-layer kernel (all north-star detector cfgs) and
+ * a width that is a multiple of 16. */
+unsigned char *network_pipeline_staging_u8(network net, int slot);
+int network_detect_submit_u8(network net, const unsigned char *input_hwc, float thresh, float nms, int max_det);
+void network_detect_batch_u8(network net, const unsigned char *input_hwc, float thresh, float nms,
+                             y2_detection *dets, int *counts, int max_det);
 /* Block until the network's stream is idle. */
 void network_sync(network net);
 /* Device stream the network runs on (cudaStream_t) — for timing with CUDA events. */

@@ -130,6 +130,13 @@ int y2_stem_prepare(void);
 int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w, const void *wt, int npad,
                       const float *alpha, const float *beta, int act, void *out, int out_cs,
                       y2_stream_t s);
+/* Same layer fed with the raw decoded image: uint8 interleaved RGB [B][h][w][3]; every byte becomes
+ * (float)(byte / 255.) exactly as the reference's loaders do on the host (yolo_v2_class.cpp:129-149
+ * load_image_stb, yolo_v2_class.hpp:95-115 mat_to_image), so the result is bit-identical to
+ * y2_stem_conv_pool on the converted planar image at a quarter of the upload.  w % 16 == 0. */
+int y2_stem_conv_pool_u8(const unsigned char *in_hwc, int batch, int h, int w, const void *wt, int npad,
+                         const float *alpha, const float *beta, int act, void *out, int out_cs,
+                         y2_stream_t s);
 
 /* ---- layout / packing kernels ------------------------------------------------------ */
 

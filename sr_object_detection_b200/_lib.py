@@ -95,6 +95,7 @@ def _declare(lib: C.CDLL) -> None:
         "y2_conv_plan_variant": (i, [vp]),
         "y2_stem_prepare": (i, []),
         "y2_stem_conv_pool": (i, [vp, i, i, i, i, vp, i, vp, vp, i, vp, i, vp]),
+        "y2_stem_conv_pool_u8": (i, [vp, i, i, i, vp, i, vp, vp, i, vp, i, vp]),
         "y2_pack_nchw_f32": (i, [vp, vp, i, i, i, i, i, i, vp]),
         "y2_pack_patches_f32": (i, [vp, vp, i, i, i, i, i, i, vp]),
         "y2_unpack_to_nchw_f32": (i, [vp, vp, i, i, i, i, i, vp]),

@@ -63,8 +63,9 @@ struct StemParams {
     int act;
     __nv_bfloat16 *out;  // padded NHWC [B][oh+1][ow+1][out_cs]
     int out_cs;
-    int use_tma;       // raw fp32 boxes arrive through tm_in (else the converters load global memory)
-    int boxw;          // floats per raw row of the box
+    int use_tma;       // 1: raw fp32 planar boxes arrive through tm_in, 2: raw uint8 HWC boxes (the image is
+                       // [B][H][W][3] bytes, value = byte / 255), 0: the converters load global fp32 directly
+    int boxw;          // floats (mode 1) or bytes (mode 2) per raw row of the box
 };
 
 struct StemSmem {
@@ -72,6 +73,7 @@ struct StemSmem {
     struct alignas(128) Raw { float v[3 * (kStemRows + 2) * kStemBoxW]; } raw[kStemStages];  // TMA destinations
     alignas(128) uint8_t w[3][1024];  // per filter row dr: [k-chunk 2][n 32][8 bf16]
     float alpha[kStemN], beta[kStemN];
+    float lut[256];    // byte -> (float)(byte / 255.), the conversion of yolo_v2_class.cpp:141 / image.c
     alignas(8) uint64_t p_full[kStemStages], p_empty[kStemStages], r_full[kStemStages], r_empty[kStemStages];
     uint64_t t_full[kStemSlots], t_empty[kStemSlots];
     uint32_t tmem_slot;
@@ -157,6 +159,7 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
         sm.alpha[threadIdx.x] = p.alpha[threadIdx.x];
         sm.beta[threadIdx.x] = p.beta[threadIdx.x];
     }
+    if (threadIdx.x < 256) sm.lut[threadIdx.x] = (float)((double)threadIdx.x / 255.);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -173,6 +176,25 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
             const int s = it % kStemStages;
             const uint32_t ph = (uint32_t)(it / kStemStages) & 1u;
             uint4 *dst = reinterpret_cast<uint4 *>(sm.patch[s]);
+            if (p.use_tma == 2) {
+                mbar_wait_relaxed(&sm.r_full[s], ph, 9);
+                mbar_wait_relaxed(&sm.p_empty[s], ph ^ 1, 10);
+                const int t = tile % per_img;
+                const int tx = t % p.tiles_x;
+                const int x3 = (tx * p.wt - 1) * 3;
+                const uint8_t *raw = reinterpret_cast<const uint8_t *>(sm.raw[s].v) + (x3 - (x3 & ~15));
+#pragma unroll 4
+                for (int e = threadIdx.x; e < n_pos; e += kStemProducerWarps * 32) {
+                    const int r = (int)(((uint32_t)e * inv_p) >> 20), q = e - r * P;
+                    const uint8_t *px = raw + r * p.boxw + 3 * q;  // pixel q and its right neighbour, RGB bytes
+                    dst[e] = make_uint4(pack_bf16x2(sm.lut[px[0]], sm.lut[px[1]]), pack_bf16x2(sm.lut[px[2]], 0.f),
+                                        pack_bf16x2(sm.lut[px[3]], sm.lut[px[4]]), pack_bf16x2(sm.lut[px[5]], 0.f));
+                }
+                fence_proxy_async();
+                mbar_arrive(&sm.p_full[s]);
+                mbar_arrive(&sm.r_empty[s]);
+                continue;
+            }
             if (p.use_tma) {
                 mbar_wait_relaxed(&sm.r_full[s], ph, 9);
                 mbar_wait_relaxed(&sm.p_empty[s], ph ^ 1, 10);
@@ -227,7 +249,8 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
         // ===================== TMA loader: raw fp32 box of every patch =====================
         if (p.use_tma) {
             int it = 0;
-            const uint32_t box_bytes = (uint32_t)(p.c * (kStemRows + 2) * p.boxw * 4);
+            const uint32_t box_bytes = p.use_tma == 2 ? (uint32_t)((kStemRows + 2) * p.boxw)
+                                                      : (uint32_t)(p.c * (kStemRows + 2) * p.boxw * 4);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
                 const int s = it % kStemStages;
                 const uint32_t ph = (uint32_t)(it / kStemStages) & 1u;
@@ -238,7 +261,11 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
                 if (elect_one_sync()) {
                     mbar_expect_tx(&sm.r_full[s], box_bytes);
                     // the innermost box coordinate must be 16-byte aligned: start four columns left of the tile
-                    tma_load_3d(&tm_in, &sm.r_full[s], sm.raw[s].v, tx * p.wt - 4, ty * kStemRows - 1, b * p.c);
+                    if (p.use_tma == 2)  // byte column of pixel x0 - 1, rounded down to 16 bytes
+                        tma_load_3d(&tm_in, &sm.r_full[s], sm.raw[s].v, (((tx * p.wt - 1) * 3) & ~15) >> 2,
+                                    ty * kStemRows - 1, b);  // the tensor map counts 32-bit words
+                    else
+                        tma_load_3d(&tm_in, &sm.r_full[s], sm.raw[s].v, tx * p.wt - 4, ty * kStemRows - 1, b * p.c);
                 }
                 __syncwarp();
             }
@@ -373,9 +400,9 @@ extern "C" int y2_stem_prepare(void)
     return Y2_OK;
 }
 
-extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w, const void *wt, int npad,
-                                 const float *alpha, const float *beta, int act, void *out, int out_cs,
-                                 y2_stream_t s)
+// in: fp32 planar [B][c][h][w] when !u8, uint8 interleaved [B][h][w][3] when u8
+static int stem_launch(const void *in, bool u8, int batch, int c, int h, int w, const void *wt, int npad,
+                       const float *alpha, const float *beta, int act, void *out, int out_cs, y2_stream_t s)
 {
     if (!in || !wt || !alpha || !beta || !out || batch <= 0 || c <= 0 || c > 3 || h < 2 || w < 2 || npad != kStemN ||
         out_cs % 8 || out_cs < kStemN || ((uintptr_t)out & 15) || ((uintptr_t)wt & 15) ||
@@ -385,7 +412,7 @@ extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w
         return Y2_EINVAL;
     }
     StemParams p;
-    p.in = in;
+    p.in = u8 ? nullptr : (const float *)in;
     p.batch = batch;
     p.c = c;
     p.h = h;
@@ -412,27 +439,65 @@ extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w
     const size_t smem = sizeof(StemSmem) + 128;
     int rc = y2_stem_prepare();
     if (rc != Y2_OK) return rc;
-    // raw fp32 boxes through TMA when the image rows are 16-byte aligned; the tensor map is encoded per
-    // call (the input pointer is the caller's) and travels by value in the launch / graph node
+    // raw boxes through TMA when the image rows are 16-byte aligned; the tensor map is encoded per call
+    // (the input pointer is the caller's) and travels by value in the launch / graph node
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
-    p.boxw = p.wt + 8;  // image columns x0 - 4 .. x0 + wt + 3
     p.use_tma = 0;
     EncodeTiledFn enc = get_encode_fn();
-    if (enc && w % 4 == 0 && ((uintptr_t)in & 15) == 0 && p.boxw <= kStemBoxW && p.boxw <= w && kStemRows + 2 <= h &&
-        !getenv("Y2_STEM_NO_TMA")) {  // a box never exceeds the tensor it slides over
-        cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch * c};
-        cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
-        cuuint32_t box[3] = {(cuuint32_t)p.boxw, (cuuint32_t)(kStemRows + 2), (cuuint32_t)c};
+    if (u8) {
+        // bytes (x0 - 1)*3 .. (x0 + wt + 2)*3 of a row, from the 16-byte boundary below the first one
+        p.boxw = ((wt_cols + 3) * 3 + 15 + 15) / 16 * 16;
+        if (!enc || c != 3 || (3 * w) % 16 || ((uintptr_t)in & 15) || p.boxw > 3 * w || kStemRows + 2 > h ||
+            (size_t)(kStemRows + 2) * p.boxw > sizeof(StemSmem::Raw)) {
+            set_error("y2_stem_conv_pool_u8: needs 3 channels, a width that is a multiple of 16 and at least %d rows "
+                      "(h=%d w=%d c=%d)", kStemRows + 2, h, w, c);
+            return Y2_EINVAL;
+        }
+        // described as 32-bit words: a box dimension is limited to 256 elements, a row of bytes would not fit
+        cuuint64_t gdim[3] = {(cuuint64_t)w * 3 / 4, (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t gstr[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * h * 3};
+        cuuint32_t box[3] = {(cuuint32_t)p.boxw / 4, (cuuint32_t)(kStemRows + 2), 1u};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(in), gdim, gstr, box, estr,
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(in), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        p.use_tma = (r == CUDA_SUCCESS);
+        if (r != CUDA_SUCCESS) {
+            set_error("y2_stem_conv_pool_u8: cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+            return Y2_ECUDA;
+        }
+        p.use_tma = 2;
+    } else {
+        p.boxw = p.wt + 8;  // image columns x0 - 4 .. x0 + wt + 3
+        if (enc && w % 4 == 0 && ((uintptr_t)in & 15) == 0 && p.boxw <= kStemBoxW && p.boxw <= w && kStemRows + 2 <= h &&
+            !getenv("Y2_STEM_NO_TMA")) {  // a box never exceeds the tensor it slides over
+            cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch * c};
+            cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+            cuuint32_t box[3] = {(cuuint32_t)p.boxw, (cuuint32_t)(kStemRows + 2), (cuuint32_t)c};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(in), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            p.use_tma = (r == CUDA_SUCCESS);
+        }
     }
     const int sms = sm_count();
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     stem_conv_pool_kernel<<<grid, kStemThreads, smem, to_stream(s)>>>(tm, p);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
+}
+
+extern "C" int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w, const void *wt, int npad,
+                                 const float *alpha, const float *beta, int act, void *out, int out_cs,
+                                 y2_stream_t s)
+{
+    return stem_launch(in, false, batch, c, h, w, wt, npad, alpha, beta, act, out, out_cs, s);
+}
+
+extern "C" int y2_stem_conv_pool_u8(const unsigned char *in_hwc, int batch, int h, int w, const void *wt, int npad,
+                                    const float *alpha, const float *beta, int act, void *out, int out_cs,
+                                    y2_stream_t s)
+{
+    return stem_launch(in_hwc, true, batch, 3, h, w, wt, npad, alpha, beta, act, out, out_cs, s);
 }

@@ -247,12 +247,39 @@ int network_pipeline_next_slot(network net)
     return (rt->pipe_head + rt->pipe_inflight) & 1;
 }
 
-int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det)
+static void pipe_init_u8(network net)
+{
+    y2_net_rt *rt = y2_rt(net);
+    pipe_init(net);
+    if (rt->pipe[0].in_u8_dev) return;
+    layer *l0 = &net.layers[0];
+    y2_layer_rt *r0 = (y2_layer_rt *)l0->b200;
+    if (!r0 || !r0->stem_fused || l0->c != 3)
+        error("uint8 input needs a network whose first layer runs the fused first-layer kernel (3x3 conv over 3 "
+              "channels followed by a 2x2/2 maxpool)");
+    const size_t bytes = (size_t)rt->cap_batch * net.h * net.w * 3;
+    for (int s = 0; s < 2; ++s) {
+        Y2_CHECK(y2_malloc((void **)&rt->pipe[s].in_u8_dev, bytes));
+        Y2_CHECK(y2_host_alloc((void **)&rt->pipe[s].in_u8_pinned, bytes));
+    }
+}
+
+unsigned char *network_pipeline_staging_u8(network net, int slot)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt || slot < 0 || slot > 1) error("network_pipeline_staging_u8: bad slot or unplanned network");
+    pipe_init_u8(net);
+    return rt->pipe[slot].in_u8_pinned;
+}
+
+/* input: fp32 planar [B][c][h][w] (u8 == 0) or uint8 interleaved RGB [B][h][w][3] (u8 == 1) */
+static int submit_common(network net, const void *input, int u8, float thresh, float nms, int max_det)
 {
     y2_net_rt *rt = y2_rt(net);
     if (!rt) error("network_detect_submit: network has no device plan");
     if (net.batch != rt->plan_batch) error("network batch changed without set_batch_network");
-    pipe_init(net);
+    if (u8) pipe_init_u8(net);
+    else pipe_init(net);
     if (rt->pipe_inflight >= 2) error("network_detect_submit: two batches already in flight, call network_detect_wait");
     Y2_CHECK(y2_set_device(rt->device));
     const int s = (rt->pipe_head + rt->pipe_inflight) & 1;
@@ -261,16 +288,29 @@ int network_detect_submit(network net, const float *input, float thresh, float n
     y2_layer_rt *r = (y2_layer_rt *)l->b200;
     const int B = net.batch;
     const int total = l->w * l->h * l->n;
-    const size_t bytes = (size_t)B * net.inputs * sizeof(float);
     pipe_reserve_dets(rt, s, B, max_det);
-    /* pageable caller memory is staged through the slot's pinned buffer (a host copy; fill
-     * network_pipeline_staging(net, slot) directly to avoid it) */
-    if (input && input != ps->in_pinned) memcpy(ps->in_pinned, input, bytes);
-    Y2_CHECK(y2_memcpy_h2d(ps->in_dev, ps->in_pinned, bytes, rt->copy_stream));
+    /* pageable caller memory is staged through the slot's pinned buffer (a host copy; fill the slot's
+     * staging buffer directly to avoid it) */
+    if (u8) {
+        const size_t bytes = (size_t)B * net.h * net.w * 3;
+        if (input && input != ps->in_u8_pinned) memcpy(ps->in_u8_pinned, input, bytes);
+        Y2_CHECK(y2_memcpy_h2d(ps->in_u8_dev, ps->in_u8_pinned, bytes, rt->copy_stream));
+    } else {
+        const size_t bytes = (size_t)B * net.inputs * sizeof(float);
+        if (input && input != ps->in_pinned) memcpy(ps->in_pinned, input, bytes);
+        Y2_CHECK(y2_memcpy_h2d(ps->in_dev, ps->in_pinned, bytes, rt->copy_stream));
+    }
     Y2_CHECK(y2_event_record(ps->ev_h2d, rt->copy_stream));
     Y2_CHECK(y2_stream_wait_event(rt->stream, ps->ev_h2d));
-    if (s == 0) y2_run_forward_from(net, ps->in_dev, &rt->graph, &rt->graph_valid);
-    else y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
+    if (u8) {
+        rt->input_u8 = 1; /* read while the layer list is captured */
+        y2_run_forward_from(net, (float *)ps->in_u8_dev, &ps->graph_u8, &ps->graph_u8_valid);
+        rt->input_u8 = 0;
+    } else if (s == 0) {
+        y2_run_forward_from(net, ps->in_dev, &rt->graph, &rt->graph_valid);
+    } else {
+        y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
+    }
     Y2_CHECK(y2_region_boxes((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
                              l->classes, 1.f, 1.f, thresh, 0, l->classfix,
                              l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0, rt->stream));
@@ -283,6 +323,16 @@ int network_detect_submit(network net, const float *input, float thresh, float n
     ps->busy = 1;
     rt->pipe_inflight++;
     return s;
+}
+
+int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det)
+{
+    return submit_common(net, input, 0, thresh, nms, max_det);
+}
+
+int network_detect_submit_u8(network net, const unsigned char *input_hwc, float thresh, float nms, int max_det)
+{
+    return submit_common(net, input_hwc, 1, thresh, nms, max_det);
 }
 
 int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det)
@@ -304,4 +354,13 @@ int network_detect_wait(network net, y2_detection *dets, int *counts, int max_de
     rt->pipe_head ^= 1;
     rt->pipe_inflight--;
     return s;
+}
+
+void network_detect_batch_u8(network net, const unsigned char *input_hwc, float thresh, float nms, y2_detection *dets,
+                             int *counts, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (rt && rt->pipe_inflight) error("network_detect_batch_u8: batches of the submit/wait pipeline are in flight");
+    submit_common(net, input_hwc, 1, thresh, nms, max_det);
+    network_detect_wait(net, dets, counts, max_det);
 }

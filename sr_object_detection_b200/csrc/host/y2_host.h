@@ -91,9 +91,14 @@ typedef struct y2_net_rt {
         int det_cap;
         y2_event_t ev_h2d, ev_done;
         int busy;
+        /* raw uint8 HWC input of the same slot (network_detect_submit_u8) */
+        unsigned char *in_u8_dev, *in_u8_pinned;
+        y2_graph_t graph_u8;
+        int graph_u8_valid;
     } pipe[2];
     y2_stream_t copy_stream;
     int pipe_ready, pipe_head, pipe_inflight;
+    int input_u8;        /* the forward pass being issued reads uint8 HWC images (first-layer kernel only) */
 } y2_net_rt;
 
 static inline y2_net_rt *y2_rt(network net) { return (y2_net_rt *)net.b200; }

@@ -959,8 +959,12 @@ void forward_convolutional_layer_gpu(layer l, network_state state)
     if (r->stem_fused) {
         y2_layer_rt *mr = y2_lrt(state.net.layers[state.index + 1]);
         const int act = (l.activation == LEAKY) ? Y2_ACT_LEAKY : Y2_ACT_LINEAR;
-        Y2_CHECK(y2_stem_conv_pool(state.input, l.batch, l.c, l.h, l.w, r->wt_dev, r->npad, r->alpha_dev,
-                                   r->beta_dev, act, mr->out, mr->out_cs, s));
+        if (y2_rt(state.net)->input_u8)
+            Y2_CHECK(y2_stem_conv_pool_u8((const unsigned char *)state.input, l.batch, l.h, l.w, r->wt_dev, r->npad,
+                                          r->alpha_dev, r->beta_dev, act, mr->out, mr->out_cs, s));
+        else
+            Y2_CHECK(y2_stem_conv_pool(state.input, l.batch, l.c, l.h, l.w, r->wt_dev, r->npad, r->alpha_dev,
+                                       r->beta_dev, act, mr->out, mr->out_cs, s));
         count_launch(state.net, 1);
         return;
     }
@@ -1139,6 +1143,11 @@ void y2_pipe_release(y2_net_rt *rt)
     if (rt->pipe[1].graph) y2_graph_destroy(rt->pipe[1].graph);
     rt->pipe[1].graph = 0;
     rt->pipe[1].graph_valid = 0;
+    for (int s = 0; s < 2; ++s) {
+        if (rt->pipe[s].graph_u8) y2_graph_destroy(rt->pipe[s].graph_u8);
+        rt->pipe[s].graph_u8 = 0;
+        rt->pipe[s].graph_u8_valid = 0;
+    }
 }
 
 static void pipe_free(y2_net_rt *rt)
@@ -1147,6 +1156,8 @@ static void pipe_free(y2_net_rt *rt)
     y2_free(rt->pipe[1].in_dev);
     y2_host_free(rt->pipe[1].in_pinned);
     for (int s = 0; s < 2; ++s) {
+        y2_free(rt->pipe[s].in_u8_dev);
+        y2_host_free(rt->pipe[s].in_u8_pinned);
         y2_free(rt->pipe[s].det_dev);
         y2_host_free(rt->pipe[s].det_pinned);
         y2_free(rt->pipe[s].cnt_dev);

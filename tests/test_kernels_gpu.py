@@ -337,3 +337,30 @@ def test_conv_pool_fused_matches_fp32_reference(batch, cin, h, w, cout):
     # pads and the neighbouring channels of the wider buffer stay untouched
     assert out[:, oh].abs().max().item() == 0 and out[:, :, ow].abs().max().item() == 0
     assert out[..., cout:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("batch,h,w", [(2, 64, 128), (3, 416, 416), (1, 50, 160)])
+def test_stem_u8_input_is_bit_identical_to_the_float_path(batch, h, w):
+    """uint8 interleaved RGB input (the decoded image) against the fp32 planar input the reference's
+    loaders would have produced from it ((float)byte / 255., yolo_v2_class.cpp:129-149): identical bytes out."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(1000 + h)
+    u8 = torch.randint(0, 256, (batch, h, w, 3), generator=g, dtype=torch.uint8)
+    planar = (u8.permute(0, 3, 1, 2).to(torch.float32).to(torch.float64) / 255.0).to(torch.float32).contiguous()
+    wt = ((torch.rand(32, 3, 3, 3, generator=g) * 2 - 1) * (2.0 / 27) ** 0.5)
+    wt_p = torch.zeros(32, 32, dtype=torch.bfloat16)
+    wt_p[:, :27] = wt.reshape(32, 27).to(torch.bfloat16)
+    alpha = torch.rand(32, generator=g) + 0.5
+    beta = torch.rand(32, generator=g) * 0.4 - 0.2
+    u8, planar, wt_p, alpha, beta = (t.to(dev) for t in (u8.contiguous(), planar, wt_p, alpha, beta))
+    oh, ow = h // 2, w // 2
+    out_f = torch.zeros(batch, oh + 1, ow + 1, 32, dtype=torch.bfloat16, device=dev)
+    out_u = torch.zeros_like(out_f)
+    lib = _lib.load()
+    _lib.check(lib.y2_stem_conv_pool(planar.data_ptr(), batch, 3, h, w, wt_p.data_ptr(), 32, alpha.data_ptr(),
+                                     beta.data_ptr(), ACT_LEAKY, out_f.data_ptr(), 32, _stream()), "stem f32")
+    _lib.check(lib.y2_stem_conv_pool_u8(u8.data_ptr(), batch, h, w, wt_p.data_ptr(), 32, alpha.data_ptr(),
+                                        beta.data_ptr(), ACT_LEAKY, out_u.data_ptr(), 32, _stream()), "stem u8")
+    torch.cuda.synchronize()
+    assert out_f.abs().max().item() > 0
+    assert torch.equal(out_u.view(torch.int16), out_f.view(torch.int16))

@@ -173,3 +173,39 @@ def test_pipelined_submit_wait_equals_synchronous_detect(tmp_path):
     got.append(as_list(dets, counts))
     assert got == want
     dn.free_network(net)
+
+
+def test_u8_input_detections_equal_float_input(tmp_path):
+    """network_detect_batch_u8 / network_detect_submit_u8 on raw uint8 RGB images must give exactly the
+    detections of the float calls on the image the reference's loaders derive from it (byte / 255.)."""
+    import ctypes as C
+    batch, max_det = 3, 256
+    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", batch)
+    dn.set_gpu_index(0)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    lib = dn.lib()
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, size=(batch, 416, 416, 3), dtype=np.uint8)
+    planar = (u8.transpose(0, 3, 1, 2).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
+    thresh, nms = 0.02, 0.4
+    want, _ = dn.network_detect_batch(net, np.ascontiguousarray(planar), thresh, nms, max_det)
+    assert any(len(w) for w in want), "test needs at least one detection"
+    dets = (dn.Detection * (batch * max_det))()
+    counts = (C.c_int * batch)()
+    lib.network_detect_batch_u8(net, u8.ctypes.data_as(C.POINTER(C.c_ubyte)), thresh, nms, dets, counts, max_det)
+    arr = np.ctypeslib.as_array(dets)
+    for b in range(batch):
+        got = arr[b * max_det:b * max_det + min(counts[b], max_det)]
+        assert got.tobytes() == want[b].tobytes(), f"image {b}: uint8 and float paths disagree"
+    # and through the pipeline, twice per slot
+    stage = [lib.network_pipeline_staging_u8(net, s) for s in (0, 1)]
+    for _ in range(4):
+        slot = lib.network_pipeline_next_slot(net)
+        C.memmove(stage[slot], u8.ctypes.data, u8.nbytes)
+        lib.network_detect_submit_u8(net, stage[slot], thresh, nms, max_det)
+        lib.network_detect_wait(net, dets, counts, max_det)
+        arr = np.ctypeslib.as_array(dets)
+        for b in range(batch):
+            assert arr[b * max_det:b * max_det + min(counts[b], max_det)].tobytes() == want[b].tobytes()
+    dn.free_network(net)

@@ -13,6 +13,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -58,7 +59,7 @@ def main():
         cin_pad = storage_channels(cin)
         f32 = name == "L30"
         cpad = cout if f32 else storage_channels(cout)
-        bn = pick_block_n(cout)
+        bn = int(os.environ.get('Y2_BENCH_BN', 0)) or pick_block_n(cout)
         npad = (max(cout, cpad) + bn - 1) // bn * bn
         bk = 64 if cin_pad % 64 == 0 else 32
         x = (torch.rand(B, hw + 1, hw + 1, cin_pad, device=dev) - 0.5).to(torch.bfloat16)
