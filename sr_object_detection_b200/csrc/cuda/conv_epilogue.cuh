@@ -58,4 +58,49 @@ __device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const
     }
 }
 
+// affine + activation of one 32-column chunk, packed to bf16 (zeros when the row is a pad position)
+template <int ACT>
+__device__ __forceinline__ void slab_affine_pack(const uint32_t (&v)[32], const float2 *sab, int c0, bool valid,
+                                                 uint4 *w)
+{
+    const float4 *ab4 = reinterpret_cast<const float4 *>(sab + c0);
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 q = ab4[j];  // (alpha, beta) of two filters
+        float t0 = fmaf(__uint_as_float(v[2 * j]), q.x, q.y);
+        float t1 = fmaf(__uint_as_float(v[2 * j + 1]), q.z, q.w);
+        if (ACT == Y2_ACT_LEAKY) {
+            t0 = fmaxf(t0, 0.1f * t0);
+            t1 = fmaxf(t1, 0.1f * t1);
+        } else if (ACT == Y2_ACT_LOGISTIC) {
+            t0 = 1.f / (1.f + __expf(-t0));
+            t1 = 1.f / (1.f + __expf(-t1));
+        }
+        pk[j] = valid ? pack_bf16x2(t0, t1) : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+// 32 rows x 64 channels of one warp -> its 4 KB staging tile in the SWIZZLE_128B layout of the output
+// tensor map (16-byte chunk c of row r at chunk c ^ (r & 7): conflict free), then ONE TMA store: the
+// copy engine writes full 128-byte lines, the LSU sees 8 shared-memory stores per thread instead of 8
+// global stores that touch 32 different lines each.
+__device__ __forceinline__ void slab_store_tma(const void *tm_out, uint4 *stage, const uint4 (&w)[8], int lane,
+                                               int p_first, int ch0)
+{
+    // the previous box of this warp must have been read out of the staging tile
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) stage[lane * 8 + (c ^ (lane & 7))] = w[c];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(tm_out, stage, ch0, p_first);
+        tma_store_commit();
+    }
+}
+
 } // namespace y2

@@ -306,6 +306,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.out_mode = d->out_mode;
     p.out_cs = d->out_cs;
     p.couple = 0;
+    p.tma_store = 0;
     p.alpha = d->alpha;
     p.beta = d->beta;
     p.out = d->out;

@@ -39,6 +39,7 @@ struct SlabParams {
     int slab_bytes;        // bytes per slab stage
     int stages_a, stages_b;
     int cout, act, out_mode, out_cs;
+    int tma_store;         // bf16 output leaves through per-warp TMA stores (else direct 16-byte stores)
     int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
     const float *alpha;
     const float *beta;
@@ -77,6 +78,7 @@ int encode_2d_bf16(CUtensorMap *tm, const void *base, uint64_t dim0, uint64_t di
 struct y2_conv_plan {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
+    CUtensorMap tm_out;  // slab kernel: the output tensor (TMA stores)
     int variant;
     y2::ConvParams prm;
     y2::SlabParams slab;

@@ -30,6 +30,7 @@
 #include "conv_epilogue.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace y2 {
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ uint64_t slab_desc(uint32_t hi, uint32_t lo)
 template <int BLOCK_N, int BLOCK_K, int ACCS, int TPS, int TAPS>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const SlabParams prm)
+                 const __grid_constant__ CUtensorMap tm_out, const SlabParams prm)
 {
     using Cfg = SlabCfg<BLOCK_N, BLOCK_K, ACCS, TPS, TAPS>;
     constexpr int kTileM = Cfg::kTileM;
@@ -86,6 +87,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint64_t *tfull_bar = b_empty + kSlabMaxStagesB;
     uint64_t *tempty_bar = tfull_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    // [8 epilogue warps][32 rows][128 B] staging of the TMA stores, 1024-byte aligned (swizzle atom)
+    uint4 *s_stage = reinterpret_cast<uint4 *>(aux + ((2 * BLOCK_N * 8 + 512 + 1023) / 1024) * 1024);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -278,7 +281,20 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[buf]);
                     }
-                    if (prm.act == Y2_ACT_LEAKY) {
+                    if (prm.tma_store) {  // bf16 tensor, 64-channel aligned: staged, one TMA store per warp
+                        uint4 w[8];
+                        if (prm.act == Y2_ACT_LEAKY) {
+                            slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, col0 + c, valid, w);
+                            slab_affine_pack<Y2_ACT_LEAKY>(v1, sab, col0 + c + 32, valid, w + 4);
+                        } else if (prm.act == Y2_ACT_LINEAR) {
+                            slab_affine_pack<Y2_ACT_LINEAR>(v0, sab, col0 + c, valid, w);
+                            slab_affine_pack<Y2_ACT_LINEAR>(v1, sab, col0 + c + 32, valid, w + 4);
+                        } else {
+                            slab_affine_pack<Y2_ACT_LOGISTIC>(v0, sab, col0 + c, valid, w);
+                            slab_affine_pack<Y2_ACT_LOGISTIC>(v1, sab, col0 + c + 32, valid, w + 4);
+                        }
+                        slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + col0 + c);
+                    } else if (prm.act == Y2_ACT_LEAKY) {
                         slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
                         slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
                     } else if (prm.act == Y2_ACT_LINEAR) {
@@ -304,6 +320,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (prm.tiles_n > 1 && next < total_tiles && ab_lane) s_ab[(buf ^ 1) * BLOCK_N + et] = ab_next;
         }
+        if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -367,7 +384,7 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     if (box_rows > 256) return Y2_EINVAL;
     const int slab_bytes = loads * box_rows * row_bytes;  // multiple of 1024
     const int b_stage = tps * bn * bk * 2;
-    const int aux = 2 * bn * 8 + 512;
+    const int aux = ((2 * bn * 8 + 512 + 1023) / 1024) * 1024 + 8 * 4096;  // alpha/beta, barriers | store staging
     const int budget = 227 * 1024 - 1024 - aux;
     // 1x1: every channel block needs a fresh slab, keep as many slabs as weight tiles in flight
     int stages_a = 2;
@@ -387,6 +404,15 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
                             (uint32_t)bn, bk);
     if (rc != Y2_OK) return rc;
     SlabParams &p = pl->slab;
+    // output through TMA stores when it is the bf16 tensor in whole 64-channel groups (box = 64 channels x 32
+    // positions, SWIZZLE_128B): pad positions are stored as zeros like before, rows past the tensor are clipped
+    p.tma_store = 0;
+    memset(&pl->tm_out, 0, sizeof(pl->tm_out));
+    if (d->out_mode == Y2_OUT_BF16_PADDED && bn >= 64 && d->cout % 64 == 0 && !getenv("Y2_SLAB_NO_TMA_STORE")) {
+        rc = encode_2d_bf16(&pl->tm_out, d->out, (uint64_t)d->cout, (uint64_t)total, (uint64_t)d->out_cs * 2, 64u, 32u, 64);
+        if (rc != Y2_OK) return rc;
+        p.tma_store = 1;
+    }
     p.cblocks = d->cin / bk;
     p.wp = wp;
     p.hp = hp;
@@ -436,7 +462,7 @@ int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 #define Y2_CASE(BN, BK, ACCS, TPS, TAPS)                                                                       \
     if (pl->block_n == BN && pl->block_k == BK && pl->taps == TAPS) {                                            \
         conv_slab_kernel<BN, BK, ACCS, TPS, TAPS><<<pl->grid, kSlabThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, \
-                                                                                                  pl->slab);     \
+                                                                                                  pl->tm_out, pl->slab); \
         Y2_LAUNCH_CHECK();                                                                                       \
         return Y2_OK;                                                                                            \
     }

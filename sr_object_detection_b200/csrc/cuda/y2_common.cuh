@@ -160,6 +160,27 @@ __device__ __forceinline__ void tma_load_2d(const void *desc, uint64_t *bar, voi
         : "memory");
 }
 
+// TMA store of one box from shared memory (bulk async-group completion); the issuing thread commits
+// the group and later waits until the source buffer may be overwritten
+__device__ __forceinline__ void tma_store_2d(const void *desc, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, one CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate)
