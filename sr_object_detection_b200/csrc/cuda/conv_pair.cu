@@ -23,6 +23,7 @@
 #include "conv_epilogue.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace y2 {
 
@@ -41,7 +42,7 @@ constexpr uint32_t kPairIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const SlabParams prm)
+                 const __grid_constant__ CUtensorMap tm_out, const SlabParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs: descriptors and barrier offsets name the peer's memory too
@@ -60,6 +61,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint64_t *tfull_bar = b_empty + kPairMaxStagesB;
     uint64_t *tempty_bar = tfull_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    // [8 epilogue warps][32 rows][128 B] staging of the TMA stores, 1024-byte aligned (swizzle atom)
+    uint4 *s_stage = reinterpret_cast<uint4 *>(aux + ((2 * kPairN * 8 + 512 + 1023) / 1024) * 1024);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -234,7 +237,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tc_fence_before();
                     mbar_arrive_cluster(&tempty_bar[buf], 0);
                 }
-                if (prm.act == Y2_ACT_LEAKY) {
+                if (prm.tma_store) {  // bf16 tensor: staged, one TMA store per warp and 64 channels
+                    uint4 w[8];
+                    if (prm.act == Y2_ACT_LEAKY) {
+                        slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, col0 + c, valid, w);
+                        slab_affine_pack<Y2_ACT_LEAKY>(v1, sab, col0 + c + 32, valid, w + 4);
+                    } else if (prm.act == Y2_ACT_LINEAR) {
+                        slab_affine_pack<Y2_ACT_LINEAR>(v0, sab, col0 + c, valid, w);
+                        slab_affine_pack<Y2_ACT_LINEAR>(v1, sab, col0 + c + 32, valid, w + 4);
+                    } else {
+                        slab_affine_pack<Y2_ACT_LOGISTIC>(v0, sab, col0 + c, valid, w);
+                        slab_affine_pack<Y2_ACT_LOGISTIC>(v1, sab, col0 + c + 32, valid, w + 4);
+                    }
+                    slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + col0 + c);
+                } else if (prm.act == Y2_ACT_LEAKY) {
                     slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
                     slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
                 } else if (prm.act == Y2_ACT_LINEAR) {
@@ -247,6 +263,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (prm.tiles_n > 1 && next < total_tiles) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
         }
+        if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -271,7 +288,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     box_rows = (box_rows + 15) / 16 * 16;
     if (box_rows > 256) return Y2_EINVAL;
     const int slab_bytes = loads * box_rows * kPairRowBytes;
-    const int aux = 2 * kPairN * 8 + 512;
+    const int aux = ((2 * kPairN * 8 + 512 + 1023) / 1024) * 1024 + 8 * 4096;  // alpha/beta, barriers | store staging
     const int budget = 227 * 1024 - 1024 - aux;
     const int stages_a = 2;
     int stages_b = (budget - stages_a * slab_bytes) / kPairBHalfBytes;
@@ -307,6 +324,12 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.out_cs = d->out_cs;
     p.couple = 0;
     p.tma_store = 0;
+    memset(&pl->tm_out, 0, sizeof(pl->tm_out));
+    if (d->out_mode == Y2_OUT_BF16_PADDED && d->cout % 64 == 0 && !getenv("Y2_SLAB_NO_TMA_STORE")) {
+        rc = encode_2d_bf16(&pl->tm_out, d->out, (uint64_t)d->cout, (uint64_t)total, (uint64_t)d->out_cs * 2, 64u, 32u, 64);
+        if (rc != Y2_OK) return rc;
+        p.tma_store = 1;
+    }
     p.alpha = d->alpha;
     p.beta = d->beta;
     p.out = d->out;
@@ -329,7 +352,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 
 int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
-    conv_pair_kernel<<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->slab);
+    conv_pair_kernel<<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

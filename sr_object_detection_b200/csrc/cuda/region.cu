@@ -222,27 +222,30 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float *pb = probs + (size_t)b * total * classes;
-    for (int i = warp; i < total; i += nw) {
+    // one thread per box: max_index (utils.c:533-545) is a sequential scan with strict >, the first
+    // maximum wins; a box's class row is contiguous, so the scan runs on 16-byte loads where it can
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const float *p = pb + (size_t)i * classes;
-        float best = -FLT_MAX;
-        int arg = 0x7fffffff;
-        for (int j = lane; j < classes; j += 32) {
-            const float v = p[j];
+        float best = p[0];
+        int arg = 0;
+        int j = 1;
+        if ((classes & 3) == 0 && ((uintptr_t)p & 15) == 0) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(p);
+            for (int q = 0; q < classes / 4; ++q) {
+                const float4 v = __ldg(p4 + q);
+                if (q > 0 && v.x > best) { best = v.x; arg = 4 * q; }
+                if (v.y > best) { best = v.y; arg = 4 * q + 1; }
+                if (v.z > best) { best = v.z; arg = 4 * q + 2; }
+                if (v.w > best) { best = v.w; arg = 4 * q + 3; }
+            }
+            j = classes;
+        }
+        for (; j < classes; ++j) {
+            const float v = __ldg(p + j);
             if (v > best) { best = v; arg = j; }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
-            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-        }
-        if (lane == 0) {
-            // max_index starts from a[0] with strict >, so an all-equal row yields 0
-            if (arg == 0x7fffffff) arg = 0;
-            const float pv = p[arg];
-            s_flag[i] = (pv > thresh) ? arg : -1;
-            s_prob[i] = pv;
-        }
+        s_flag[i] = (best > thresh) ? arg : -1;
+        s_prob[i] = best;
     }
     __syncthreads();
     // ordered compaction (box-index order, like the reference's loop): ballot + warp-total scan per
