@@ -151,6 +151,16 @@ int y2_pack_nchw_f32(const float *src, void *dst, int batch, int c, int h, int w
 int y2_pack_patches_f32(const float *src, void *dst, int batch, int c, int h, int w,
                         int ksize, int kpad, y2_stream_t s);
 
+/* General patch gather for convolutions of any size / stride / padding (the 7x7/2 first layer and
+ * the 3x3/2 layers of cfg/resnet50.cfg): the rows of the reference's im2col_cpu (im2col.c:16-39),
+ * written as bf16 [B][oh+1][ow+1][kpad] so the convolution becomes a 1x1 GEMM over them.
+ *   _f32 : first layer, fp32 NCHW input, K index = c*k*k + r*k + s (the reference's own order);
+ *   _bf16: later layers, bf16 padded NHWC input, K index = (r*k + s)*cin_pad + c, kpad = k*k*cin_pad. */
+int y2_gather_patches_f32(const float *src, void *dst, int batch, int c, int h, int w, int ksize,
+                          int stride, int pad, int oh, int ow, int kpad, y2_stream_t s);
+int y2_gather_patches_bf16(const void *in, int in_cs, int cin_pad, int h, int w, void *dst, int batch,
+                           int ksize, int stride, int pad, int oh, int ow, y2_stream_t s);
+
 /* bf16 padded NHWC slice -> fp32 NCHW [B][C][H][W] (host-visible l.output layout). */
 int y2_unpack_to_nchw_f32(const void *src, float *dst, int batch, int c, int h, int w,
                           int cs, y2_stream_t s);
@@ -229,7 +239,10 @@ int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp,
  * NHWC of extent out_h x out_w, out_cpad stored channels (out_c real); add: the `from` layer. */
 int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_c, int add_h,
                 int add_w, void *out, int out_cs, int out_c, int out_cpad, int out_h, int out_w,
-                int batch, int act, y2_stream_t s);
+                int batch, int act, const float *add_f32, int add_f32_cs, float *out_f32, y2_stream_t s);
+/* add_f32 / out_f32 (either may be NULL): fp32 copies of the residual stream, padded NHWC with
+ * add_f32_cs / out_cpad floats per position.  A chain of shortcuts then accumulates in fp32 (as the
+ * reference does) while the convolutions keep reading the bf16 tensors. */
 
 /* library identity, for the loader tests */
 const char *y2_version(void);

@@ -98,6 +98,8 @@ def _declare(lib: C.CDLL) -> None:
         "y2_stem_conv_pool_u8": (i, [vp, i, i, i, vp, i, vp, vp, i, vp, i, vp]),
         "y2_pack_nchw_f32": (i, [vp, vp, i, i, i, i, i, i, vp]),
         "y2_pack_patches_f32": (i, [vp, vp, i, i, i, i, i, i, vp]),
+        "y2_gather_patches_f32": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
+        "y2_gather_patches_bf16": (i, [vp, i, i, i, i, vp, i, i, i, i, i, i, vp]),
         "y2_unpack_to_nchw_f32": (i, [vp, vp, i, i, i, i, i, vp]),
         "y2_flat_to_nchw_f32": (i, [vp, vp, i, i, i, i, vp]),
         "y2_nchw_to_flat_f32": (i, [vp, vp, i, i, i, vp]),
@@ -112,7 +114,7 @@ def _declare(lib: C.CDLL) -> None:
         "y2_collect": (i, [vp, vp, i, i, i, f, vp, vp, i, vp]),
         "y2_avgpool_flat": (i, [vp, vp, i, i, i, i, vp]),
         "y2_softmax_rows": (i, [vp, vp, i, i, f, vp]),
-        "y2_shortcut": (i, [vp, i, vp, i, i, i, i, vp, i, i, i, i, i, i, i, vp]),
+        "y2_shortcut": (i, [vp, i, vp, i, i, i, i, vp, i, i, i, i, i, i, i, vp, i, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name, None)

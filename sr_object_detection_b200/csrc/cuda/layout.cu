@@ -87,6 +87,76 @@ __global__ void pack_patches_kernel(const float *__restrict__ src, __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------
+// general patch gather for the convolutions the shifted-descriptor kernels do not cover
+// (any size / stride / padding: the 7x7/2 first layer and the 3x3/2 layers of resnet50.cfg).
+// The convolution then runs as a 1x1 tcgen05 GEMM over the gathered rows.  One thread per
+// (output position, 8 K values), one 16-byte store each.
+//   first layer:  fp32 NCHW in,  K index = c*k*k + r*k + s          (im2col.c:26-28)
+//   later layers: bf16 padded NHWC in, K index = (r*k + s)*cin_pad + c
+// ---------------------------------------------------------------------------------
+__global__ void gather_patches_f32_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                          int batch, int c, int h, int w, int ksize, int stride, int pad,
+                                          int oh, int ow, int kpad)
+{
+    const int ohp = oh + 1, owp = ow + 1, k8 = kpad / 8, kk = ksize * ksize, kreal = c * kk;
+    const long long total = (long long)batch * ohp * owp * k8;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % k8);
+        const long long p = t / k8;
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+        if (ox < ow && oy < oh) {
+            const float *s = src + (size_t)b * c * h * w;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = g * 8 + q;
+                if (k < kreal) {
+                    const int ci = k / kk, r = (k % kk) / ksize, sx = k % ksize;
+                    const int yy = oy * stride + r - pad, xx = ox * stride + sx - pad;
+                    if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[q] = __ldg(s + ((size_t)ci * h + yy) * w + xx);
+                }
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(dst + (size_t)p * kpad + g * 8) = o;
+    }
+}
+
+__global__ void gather_patches_bf16_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int cin_pad, int h,
+                                           int w, __nv_bfloat16 *__restrict__ dst, int batch, int ksize,
+                                           int stride, int pad, int oh, int ow)
+{
+    const int ohp = oh + 1, owp = ow + 1, c8 = cin_pad / 8, kk = ksize * ksize, kpad = kk * cin_pad;
+    const int hp = h + 1, wp = w + 1;
+    const long long total = (long long)batch * ohp * owp * kk * c8;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t % c8);
+        const int tap = (int)((t / c8) % kk);
+        const long long p = t / ((long long)c8 * kk);
+        const int ox = (int)(p % owp);
+        const int oy = (int)((p / owp) % ohp);
+        const int b = (int)(p / ((long long)owp * ohp));
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ox < ow && oy < oh) {
+            const int yy = oy * stride + tap / ksize - pad, xx = ox * stride + tap % ksize - pad;
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                v = __ldg(reinterpret_cast<const uint4 *>(in + (((size_t)b * hp + yy) * wp + xx) * in_cs + g * 8));
+        }
+        *reinterpret_cast<uint4 *>(dst + (size_t)p * kpad + (size_t)tap * cin_pad + g * 8) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // bf16 padded NHWC slice -> fp32 NCHW (export of l.output).  32x32 smem transpose so
 // both sides are coalesced: reads run along channels, writes along x.
 // ---------------------------------------------------------------------------------
@@ -353,7 +423,8 @@ __global__ void copy_channels_kernel(const __nv_bfloat16 *__restrict__ in, int i
 __global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
                                 const __nv_bfloat16 *__restrict__ add, int add_cs, int add_c, int add_h,
                                 int add_w, __nv_bfloat16 *__restrict__ out, int out_cs, int c8, int out_c,
-                                int out_h, int out_w, int batch, int act)
+                                int out_h, int out_w, int batch, int act, const float *__restrict__ add32,
+                                int add32_cs, float *__restrict__ out32)
 {
     const int ohp = out_h + 1, owp = out_w + 1, ahp = add_h + 1, awp = add_w + 1;
     int stride = add_w / out_w, sample = out_w / add_w;
@@ -378,12 +449,22 @@ __global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
             for (int q = 0; q < 8; ++q) f[q] = __bfloat162float(hi[q]);
             const int i = ox / sample, j = oy / sample;
             if (ox % sample == 0 && oy % sample == 0 && i < minw && j < minh && g * 8 < minc) {
-                const uint4 va = __ldg(reinterpret_cast<const uint4 *>(
-                    add + (((size_t)b * ahp + (size_t)j * stride) * awp + (size_t)i * stride) * add_cs + g * 8));
-                const __nv_bfloat16 *ha = reinterpret_cast<const __nv_bfloat16 *>(&va);
+                const size_t apos = ((size_t)b * ahp + (size_t)j * stride) * awp + (size_t)i * stride;
+                float a[8];
+                if (add32) { /* the residual stream's fp32 copy */
+                    const float4 *pa = reinterpret_cast<const float4 *>(add32 + apos * add32_cs + g * 8);
+                    const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+                    a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                } else {
+                    const uint4 va = __ldg(reinterpret_cast<const uint4 *>(add + apos * add_cs + g * 8));
+                    const __nv_bfloat16 *ha = reinterpret_cast<const __nv_bfloat16 *>(&va);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = __bfloat162float(ha[q]);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    if (g * 8 + q < minc) f[q] += __bfloat162float(ha[q]);
+                    if (g * 8 + q < minc) f[q] += a[q];
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -395,6 +476,11 @@ __global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
             res.y = pack_bf16x2(f[2], f[3]);
             res.z = pack_bf16x2(f[4], f[5]);
             res.w = pack_bf16x2(f[6], f[7]);
+            if (out32) {
+                float4 *po = reinterpret_cast<float4 *>(out32 + (size_t)p * (c8 * 8) + g * 8);
+                po[0] = make_float4(f[0], f[1], f[2], f[3]);
+                po[1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
         }
         *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) = res;
     }
@@ -406,10 +492,10 @@ using namespace y2;
 
 extern "C" int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_c, int add_h,
                            int add_w, void *out, int out_cs, int out_c, int out_cpad, int out_h, int out_w,
-                           int batch, int act, y2_stream_t s)
+                           int batch, int act, const float *add_f32, int add_f32_cs, float *out_f32, y2_stream_t s)
 {
     if (!in || !add || !out || out_cpad % 8 || in_cs % 8 || add_cs % 8 || out_cs % 8 || out_c > out_cpad ||
-        add_h <= 0 || add_w <= 0 || out_h <= 0 || out_w <= 0) {
+        add_h <= 0 || add_w <= 0 || out_h <= 0 || out_w <= 0 || (add_f32 && add_f32_cs % 4)) {
         set_error("y2_shortcut: invalid arguments (out_cpad=%d in_cs=%d add_cs=%d out_cs=%d)", out_cpad, in_cs,
                   add_cs, out_cs);
         return Y2_EINVAL;
@@ -417,7 +503,7 @@ extern "C" int y2_shortcut(const void *in, int in_cs, const void *add, int add_c
     const long long total = (long long)batch * (out_h + 1) * (out_w + 1) * (out_cpad / 8);
     shortcut_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
         (const __nv_bfloat16 *)in, in_cs, (const __nv_bfloat16 *)add, add_cs, add_c, add_h, add_w,
-        (__nv_bfloat16 *)out, out_cs, out_cpad / 8, out_c, out_h, out_w, batch, act);
+        (__nv_bfloat16 *)out, out_cs, out_cpad / 8, out_c, out_h, out_w, batch, act, add_f32, add_f32_cs, out_f32);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }
@@ -450,6 +536,36 @@ extern "C" int y2_pack_patches_f32(const float *src, void *dst, int batch, int c
         set_error("y2_pack_patches_f32: kpad must be 32 or 64");
         return Y2_EINVAL;
     }
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_gather_patches_f32(const float *src, void *dst, int batch, int c, int h, int w, int ksize,
+                                     int stride, int pad, int oh, int ow, int kpad, y2_stream_t s)
+{
+    if (!src || !dst || batch <= 0 || kpad % 8 || c * ksize * ksize > kpad || stride < 1 || oh <= 0 || ow <= 0) {
+        set_error("y2_gather_patches_f32: invalid arguments (c*k*k=%d kpad=%d stride=%d)", c * ksize * ksize, kpad,
+                  stride);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (oh + 1) * (ow + 1) * (kpad / 8);
+    gather_patches_f32_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize, stride, pad, oh, ow, kpad);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_gather_patches_bf16(const void *in, int in_cs, int cin_pad, int h, int w, void *dst, int batch,
+                                      int ksize, int stride, int pad, int oh, int ow, y2_stream_t s)
+{
+    if (!in || !dst || batch <= 0 || cin_pad % 8 || in_cs % 8 || cin_pad > in_cs || stride < 1 || oh <= 0 ||
+        ow <= 0 || ksize < 1) {
+        set_error("y2_gather_patches_bf16: invalid arguments (cin_pad=%d in_cs=%d stride=%d)", cin_pad, in_cs, stride);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)batch * (oh + 1) * (ow + 1) * ksize * ksize * (cin_pad / 8);
+    gather_patches_bf16_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, in_cs, cin_pad, h, w, (__nv_bfloat16 *)dst, batch, ksize, stride, pad, oh, ow);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

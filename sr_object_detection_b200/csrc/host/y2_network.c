@@ -444,6 +444,7 @@ static void free_layer_rt(layer *l)
     y2_free(r->patches);
     y2_free(r->packed_in);
     y2_free(r->reorg_table);
+    y2_free(r->stream_f32);
     y2_free(r->boxes_dev);
     y2_free(r->probs_dev);
     y2_free(r->biases_dev);
@@ -498,7 +499,7 @@ void y2_push_convolutional_layer(layer *l)
     const int kk = l->size * l->size;
     const size_t elems = (size_t)r->npad * r->ktot;
     uint16_t *w = (uint16_t *)calloc(elems, sizeof(uint16_t));
-    if (r->use_patches) {
+    if (r->use_patches == 1) {
         /* K index = c*kk + r*k + s : the reference's own [c][kh][kw] order (im2col.c:26-28) */
         for (int f = 0; f < l->n; ++f)
             for (int k = 0; k < l->c * kk; ++k)
@@ -709,8 +710,10 @@ void y2_plan_network(network *net)
         r->placed_in = -1;
         switch (l->type) {
         case CONVOLUTIONAL: {
-            if (l->stride != 1 || (l->size != 1 && l->size != 3) || l->pad != l->size / 2)
-                unsupported(i, "convolution other than 1x1/3x3 stride 1 'same'");
+            /* 1x1 and 3x3 stride-1 'same' layers run on the shifted-descriptor kernels; every other
+             * size / stride / padding goes through a patch gather + 1x1 GEMM (use_patches) */
+            const int native = l->stride == 1 && (l->size == 1 || l->size == 3) && l->pad == l->size / 2;
+            if (l->stride < 1 || l->size < 1 || l->out_h < 1 || l->out_w < 1) unsupported(i, "degenerate convolution");
             if (l->activation != LEAKY && l->activation != LINEAR && l->activation != LOGISTIC)
                 unsupported(i, "activation other than leaky/linear/logistic");
             if (l->binary || l->xnor) unsupported(i, "binary/xnor convolution");
@@ -723,7 +726,21 @@ void y2_plan_network(network *net)
             r->npad = round_up(l->n, r->block_n);
             if (r->cpad > r->npad) r->npad = round_up(r->cpad, r->block_n);
             const int kk = l->size * l->size;
-            if (i == 0 && l->c * kk <= 64 && l->size == 3) {
+            if (!native) {
+                if (i == 0) {
+                    r->use_patches = 1; /* K = c*k*k + r*k + s, zero-padded to a K block */
+                    r->kpad = (l->c * kk <= 32) ? 32 : round_up(l->c * kk, 64);
+                    r->cin_pad = r->kpad;
+                } else {
+                    y2_layer_rt *pr = (y2_layer_rt *)net->layers[i - 1].b200;
+                    if (pr->out_kind != Y2_KIND_BF16_PADDED) unsupported(i, "convolution after a flat layer");
+                    r->use_patches = 2; /* K = tap*cin_pad + c, the order the weights are packed in anyway */
+                    r->cin_pad = pr->cpad;
+                    r->kpad = kk * pr->cpad;
+                }
+                r->ktot = r->kpad;
+                r->block_k = (r->kpad % 64 == 0) ? 64 : 32;
+            } else if (i == 0 && l->c * kk <= 64 && l->size == 3) {
                 r->use_patches = 1;
                 r->kpad = (l->c * kk <= 32) ? 32 : 64;
                 r->ktot = r->kpad;
@@ -902,9 +919,15 @@ void y2_plan_network(network *net)
             l->biases_gpu = r->beta_dev;
             l->scales_gpu = r->alpha_dev;
             if (r->stem_fused) Y2_CHECK(y2_stem_prepare());
-            else if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->kpad));
+            else if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->out_h, l->out_w, r->kpad));
             else if (i == 0) r->packed_in = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->cin_pad));
             y2_push_convolutional_layer(l);
+        } else if (l->type == SHORTCUT) {
+            /* a later shortcut that adds this one's output reads it in fp32, so the residual stream is
+             * not rounded to bf16 once per block (it would random-walk away over resnet50's 16 blocks) */
+            for (int j = i + 1; j < net->n; ++j)
+                if (net->layers[j].type == SHORTCUT && net->layers[j].index == i && !r->stream_f32)
+                    r->stream_f32 = (float *)dev_alloc_zero((size_t)B * (l->out_h + 1) * (l->out_w + 1) * r->cpad * 4);
         } else if (l->type == REORG) {
             y2_layer_rt *pr = (y2_layer_rt *)net->layers[i - 1].b200;
             if (l->out_c % 8 == 0 && r->out_cs % 8 == 0) {
@@ -968,8 +991,14 @@ void forward_convolutional_layer_gpu(layer l, network_state state)
         count_launch(state.net, 1);
         return;
     }
-    if (r->use_patches) {
-        Y2_CHECK(y2_pack_patches_f32(state.input, r->patches, l.batch, l.c, l.h, l.w, l.size, r->kpad, s));
+    if (r->use_patches == 2) {
+        y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
+        Y2_CHECK(y2_gather_patches_bf16(pr->out, pr->out_cs, r->cin_pad, l.h, l.w, r->patches, l.batch, l.size,
+                                        l.stride, l.pad, l.out_h, l.out_w, s));
+        count_launch(state.net, 1);
+    } else if (r->use_patches) {
+        Y2_CHECK(y2_gather_patches_f32(state.input, r->patches, l.batch, l.c, l.h, l.w, l.size, l.stride, l.pad,
+                                       l.out_h, l.out_w, r->kpad, s));
         count_launch(state.net, 1);
     } else if (r->packed_in) {
         Y2_CHECK(y2_pack_nchw_f32(state.input, r->packed_in, l.batch, l.c, l.h, l.w, r->cin_pad, r->cin_pad, s));
@@ -1058,7 +1087,8 @@ void forward_shortcut_layer_gpu(layer l, network_state state)
     const int act = (l.activation == LEAKY) ? Y2_ACT_LEAKY : (l.activation == LOGISTIC) ? Y2_ACT_LOGISTIC : Y2_ACT_LINEAR;
     /* (l.w, l.h, l.c) describe the `from` tensor, out_* the running one (shortcut_layer.c:7-34) */
     Y2_CHECK(y2_shortcut(pr->out, pr->out_cs, fr->out, fr->out_cs, l.c, l.h, l.w, r->out, r->out_cs, l.out_c,
-                         r->cpad, l.out_h, l.out_w, l.batch, act, net_stream(state.net)));
+                         r->cpad, l.out_h, l.out_w, l.batch, act, fr->stream_f32, fr->cpad, r->stream_f32,
+                         net_stream(state.net)));
     count_launch(state.net, 1);
 }
 

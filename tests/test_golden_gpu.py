@@ -49,7 +49,7 @@ def test_decode_nms_bit_exact_vs_reference_golden(tmp_path, monkeypatch, name):
     dn.free_network(net)
 
 
-@pytest.mark.parametrize("name", ["mini_yolo", "mini_yolo_tree"])
+@pytest.mark.parametrize("name", ["mini_yolo", "mini_yolo_tree", "mini_resnet"])
 def test_toy_network_layers_match_reference_golden(tmp_path, monkeypatch, name):
     d = np.load(GOLDEN / f"{name}.npz")
     _materialise(d, tmp_path)

@@ -185,6 +185,66 @@ def test_first_layer_patches_path():
     assert err <= 1e-2
 
 
+@pytest.mark.parametrize("c,h,w,k,stride,pad", [(3, 32, 48, 7, 2, 3), (3, 31, 29, 11, 4, 2), (1, 20, 20, 5, 1, 2),
+                                                (3, 16, 16, 3, 2, 1)])
+def test_gather_patches_f32_matches_im2col(c, h, w, k, stride, pad):
+    """General first-layer gather (any size / stride / padding) against torch's unfold, which walks the
+    same [c][kh][kw] K order as the reference's im2col_cpu (im2col.c:16-39).  Bit-exact."""
+    dev = torch.device("cuda:0")
+    batch = 2
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    kreal = c * k * k
+    kpad = 32 if kreal <= 32 else (kreal + 63) // 64 * 64
+    g = torch.Generator(device="cpu").manual_seed(9)
+    x = torch.rand(batch, c, h, w, generator=g).to(dev)
+    lib = _lib.load()
+    patches = torch.full((batch, oh + 1, ow + 1, kpad), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_gather_patches_f32(x.data_ptr(), patches.data_ptr(), batch, c, h, w, k, stride, pad, oh, ow,
+                                         kpad, _stream()))
+    unf = torch.nn.functional.unfold(x, k, padding=pad, stride=stride).view(batch, kreal, oh, ow)
+    assert torch.equal(patches[:, :oh, :ow, :kreal].permute(0, 3, 1, 2), unf.to(torch.bfloat16))
+    assert patches[:, :oh, :ow, kreal:].abs().max().item() == 0
+    assert patches[:, oh].abs().max().item() == 0 and patches[:, :, ow].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("c,cs,h,w,k,stride,pad", [(64, 64, 16, 16, 3, 2, 1), (32, 96, 13, 17, 3, 2, 1),
+                                                   (64, 64, 9, 9, 1, 2, 0), (32, 32, 12, 12, 5, 1, 2)])
+def test_gather_patches_bf16_strided_conv(c, cs, h, w, k, stride, pad):
+    """Mid-network gather (bf16 padded NHWC in, K = tap*cin_pad + c): rows bit-exact against unfold, and
+    gather + 1x1 GEMM == the strided convolution within the bf16 tolerance."""
+    dev = torch.device("cuda:0")
+    batch, cout = 2, 64
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = (torch.rand(batch, c, h, w, generator=g).to(dev) - 0.5)
+    xin = torch.zeros(batch, h + 1, w + 1, cs, dtype=torch.bfloat16, device=dev)
+    xin[:, :h, :w, :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    xin[..., c:] = 3.0  # a neighbour's channels in a concat buffer must not leak in
+    xin[:, h, :, c:] = 0
+    lib = _lib.load()
+    kk = k * k
+    patches = torch.full((batch, oh + 1, ow + 1, kk * c), 7.0, dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.y2_gather_patches_bf16(xin.data_ptr(), cs, c, h, w, patches.data_ptr(), batch, k, stride, pad, oh,
+                                          ow, _stream()))
+    unf = torch.nn.functional.unfold(x.to(torch.bfloat16).float(), k, padding=pad, stride=stride)
+    unf = unf.view(batch, c, kk, oh, ow).permute(0, 3, 4, 2, 1).reshape(batch, oh, ow, kk * c)
+    assert torch.equal(patches[:, :oh, :ow], unf.to(torch.bfloat16))
+    assert patches[:, oh].abs().max().item() == 0 and patches[:, :, ow].abs().max().item() == 0
+    wt = (torch.rand(cout, c, k, k, generator=g).to(dev) * 2 - 1) * (2.0 / (kk * c)) ** 0.5
+    alpha = torch.rand(cout, generator=g).to(dev) + 0.5
+    beta = torch.rand(cout, generator=g).to(dev) * 0.2
+    wt_p = wt.permute(0, 2, 3, 1).reshape(cout, kk * c).to(torch.bfloat16).contiguous()
+    out = torch.zeros(batch, oh + 1, ow + 1, cout, dtype=torch.bfloat16, device=dev)
+    bk = 64 if (kk * c) % 64 == 0 else 32
+    G.run_conv(patches, kk * c, kk * c, batch, oh, ow, 1, wt_p, cout, cout, 64, bk, alpha, beta, ACT_LEAKY, out, cout,
+               OUT_BF16)
+    xb, wb = x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float()
+    ref = torch.nn.functional.conv2d(xb, wb, padding=pad, stride=stride) * alpha.view(1, -1, 1, 1) + beta.view(1, -1, 1, 1)
+    ref = torch.where(ref > 0, ref, 0.1 * ref)
+    got = G.from_padded_nhwc(out, cout, oh, ow)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() <= 1e-2
+
+
 def test_pack_unpack_roundtrip_bit_exact():
     dev = torch.device("cuda:0")
     lib = _lib.load()

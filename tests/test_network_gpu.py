@@ -31,7 +31,8 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
 
 
 @pytest.mark.parametrize("name,batch,side", [("tiny-yolo-voc", 2, 416), ("yolo-voc", 2, 416), ("yolo", 1, 608),
-                                             ("darknet19_448", 1, 448), ("yolo-voc", 3, 320)])
+                                             ("darknet19_448", 1, 448), ("yolo-voc", 3, 320),
+                                             ("resnet50", 2, 256), ("resnet50", 1, 224)])
 def test_layer_activations_match_reference(tmp_path, name, batch, side):
     """BASELINE.json configs 1-3 and 5 (at a batch the CPU reference finishes in seconds): every layer of
     the B200 forward pass against the reference's CPU forward on the same weights and images."""
