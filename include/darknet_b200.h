@@ -157,7 +157,12 @@ extern int gpu_index;
 #define BLOCK 512
 void cuda_set_device(int n);
 int cuda_get_device(void);
-void check_error_code(int status, const char *what); /* cuda.c:27-49 check_error: print, abort */
+void check_error_code(int status, const char *what); /* y2 status codes: print, abort */
+void check_error(int cuda_status);                   /* cuda.c:27-49; the argument is a cudaError_t */
+/* layout-identical to CUDA's dim3 (three unsigned ints, returned by value) so this header needs no
+ * CUDA include; cuda.c:51-62 */
+typedef struct { unsigned int x, y, z; } y2_dim3;
+y2_dim3 cuda_gridsize(size_t n);
 float *cuda_make_array(float *x, size_t n);
 int *cuda_make_int_array(size_t n);
 void cuda_push_array(float *x_gpu, float *x, size_t n);
@@ -188,6 +193,62 @@ int get_network_input_size(network net);
 void set_batch_network(network *net, int b);                       /* network.c:308-320 */
 int resize_network(network *net, int w, int h);                    /* network.c:322-388 */
 char *get_layer_string(LAYER_TYPE a);                              /* network.c:77-130 */
+
+/* ---- per-layer API (convolutional_layer.h:13-37, maxpool_layer.h:12-20, reorg_layer.h:9-17,
+ * route_layer.h:8-16, region_layer.h:9-18, shortcut_layer.h, avgpool_layer.h, softmax_layer.h,
+ * cost_layer.h).  make_* build the host-side layer (extents, host weight arrays, forward_gpu pointer);
+ * the device side is planned per network by parse_network_cfg / resize_network / set_batch_network.
+ * forward_*_layer_gpu are the l.forward_gpu targets.  The CPU forwards (forward_*_layer) are not
+ * exported: this library has no CPU execution path (l.forward aborts with a message). -------------- */
+typedef layer convolutional_layer;
+typedef layer maxpool_layer;
+typedef layer route_layer;
+typedef layer region_layer;
+typedef layer avgpool_layer;
+typedef layer softmax_layer;
+typedef layer cost_layer;
+layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, int stride, int padding,
+                               ACTIVATION activation, int batch_normalize, int binary, int xnor,
+                               int adam);                          /* convolutional_layer.c:166-287 */
+layer make_maxpool_layer(int batch, int h, int w, int c, int size, int stride, int padding); /* maxpool_layer.c:20-57 */
+layer make_reorg_layer(int batch, int w, int h, int c, int stride, int reverse);   /* reorg_layer.c:7-49 */
+layer make_route_layer(int batch, int n, int *input_layers, int *input_sizes);     /* route_layer.c:6-37 */
+layer make_region_layer(int batch, int w, int h, int n, int classes, int coords);  /* region_layer.c:14-53 */
+layer make_shortcut_layer(int batch, int index, int w, int h, int c, int w2, int h2, int c2); /* shortcut_layer.c:7-37 */
+layer make_avgpool_layer(int batch, int w, int h, int c);                          /* avgpool_layer.c:5-30 */
+layer make_softmax_layer(int batch, int inputs, int groups);                       /* softmax_layer.c:11-33 */
+layer make_cost_layer(int batch, int inputs, COST_TYPE type, float scale);         /* cost_layer.c:36-60 */
+void forward_convolutional_layer_gpu(layer l, network_state state);  /* convolutional_kernels.cu:77-131 */
+void forward_maxpool_layer_gpu(layer l, network_state state);        /* maxpool_layer_kernels.cu:86-100 */
+void forward_reorg_layer_gpu(layer l, network_state state);          /* reorg_layer.c:97-104 */
+void forward_route_layer_gpu(layer l, network_state state);          /* route_layer.c:104-117 */
+void forward_shortcut_layer_gpu(layer l, network_state state);       /* shortcut_layer.c:54-59 */
+void forward_avgpool_layer_gpu(layer l, network_state state);        /* avgpool_layer_kernels.cu:46-54 */
+void forward_softmax_layer_gpu(layer l, network_state state);        /* softmax_layer.c:77-96 */
+void forward_cost_layer_gpu(layer l, network_state state);           /* cost_layer.c:118-140 */
+void resize_convolutional_layer(convolutional_layer *l, int w, int h); /* convolutional_layer.c:343-399 */
+void resize_maxpool_layer(maxpool_layer *l, int w, int h);           /* maxpool_layer.c:59-77 */
+void resize_reorg_layer(layer *l, int w, int h);                     /* reorg_layer.c:51-76 */
+void resize_route_layer(route_layer *l, network *net);               /* route_layer.c:39-71 */
+void resize_region_layer(layer *l, int w, int h);                    /* region_layer.c:55-71 */
+void resize_avgpool_layer(avgpool_layer *l, int w, int h);           /* avgpool_layer.c:32-37 */
+
+/* ---- blas.h:16-19,43-53, activations.h:16-18: vector helpers on host arrays and on
+ * cuda_make_array buffers (fp32).  gemm*, im2col* and blas_handle are NOT provided: the convolution
+ * is an implicit GEMM inside the tcgen05 kernels. ----------------------------------- */
+void fill_cpu(int N, float ALPHA, float *X, int INCX);
+void copy_cpu(int N, float *X, int INCX, float *Y, int INCY);
+void axpy_cpu(int N, float ALPHA, float *X, int INCX, float *Y, int INCY);
+void scal_cpu(int N, float ALPHA, float *X, int INCX);
+void fill_ongpu(int N, float ALPHA, float *X, int INCX);
+void copy_ongpu(int N, float *X, int INCX, float *Y, int INCY);
+void copy_ongpu_offset(int N, float *X, int OFFX, int INCX, float *Y, int OFFY, int INCY);
+void axpy_ongpu(int N, float ALPHA, float *X, int INCX, float *Y, int INCY);
+void axpy_ongpu_offset(int N, float ALPHA, float *X, int OFFX, int INCX, float *Y, int OFFY, int INCY);
+void scal_ongpu(int N, float ALPHA, float *X, int INCX);
+float activate(float x, ACTIVATION a);                              /* activations.c:64-93 */
+void activate_array(float *x, const int n, const ACTIVATION a);     /* activations.c:95-101 */
+void activate_array_ongpu(float *x, int n, ACTIVATION a);           /* activation_kernels.cu:143-159 */
 
 /* ---- region_layer.h:9-18, box.h:12-20 -------------------------------------------------- */
 void forward_region_layer_gpu(const layer l, network_state state); /* region_layer.c:383-422 */

@@ -244,6 +244,20 @@ int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_
  * add_f32_cs / out_cpad floats per position.  A chain of shortcuts then accumulates in fp32 (as the
  * reference does) while the convolutions keep reading the bf16 tensors. */
 
+/* ---- fp32 vector helpers behind fill/copy/axpy/scal_ongpu and activate_array_ongpu
+ * (blas_kernels.cu:402-470,560-616; activation_kernels.cu:143-159).  inc* in elements.  Not on the
+ * detection hot path. */
+int y2_vec_fill(long long n, float alpha, float *x, long long incx, y2_stream_t s);
+int y2_vec_copy(long long n, const float *x, long long incx, float *y, long long incy, y2_stream_t s);
+int y2_vec_axpy(long long n, float alpha, const float *x, long long incx, float *y, long long incy,
+                y2_stream_t s);
+int y2_vec_scal(long long n, float alpha, float *x, long long incx, y2_stream_t s);
+/* activation = the ACTIVATION enum value of activations.h:6-8 (0 LOGISTIC ... 12 LHTAN) */
+int y2_vec_activate(float *x, long long n, int activation, y2_stream_t s);
+/* for check_error(cudaError_t) (cuda.c:27-49) */
+const char *y2_cuda_error_string(int cuda_status);
+int y2_cuda_last_status(void);
+
 /* library identity, for the loader tests */
 const char *y2_version(void);
 

@@ -178,3 +178,15 @@ extern "C" int y2_event_destroy(y2_event_t e)
     if (e) Y2_CUDA_CHECK(cudaEventDestroy((cudaEvent_t)e));
     return Y2_OK;
 }
+
+/* cudaGetErrorString for the reference's check_error(cudaError_t) (cuda.c:27-49) */
+extern "C" const char *y2_cuda_error_string(int cuda_status)
+{
+    return cudaGetErrorString((cudaError_t)cuda_status);
+}
+
+/* cudaGetLastError, cleared: what check_error is usually fed (cuda.c: check_error(cudaPeekAtLastError())) */
+extern "C" int y2_cuda_last_status(void)
+{
+    return (int)cudaGetLastError();
+}

@@ -113,26 +113,7 @@ int y2_output_layer_index(network net);
 void y2_run_forward_from(network net, float *in_dev, y2_graph_t *graph, int *graph_valid);
 void y2_pipe_release(y2_net_rt *rt);
 
-/* layer constructors (y2_layers.c) */
-layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, int stride, int padding,
-                               ACTIVATION activation, int batch_normalize, int binary, int xnor, int adam);
-layer make_maxpool_layer(int batch, int h, int w, int c, int size, int stride, int padding);
-layer make_reorg_layer(int batch, int w, int h, int c, int stride, int reverse);
-layer make_route_layer(int batch, int n, int *input_layers, int *input_sizes);
-layer make_region_layer(int batch, int w, int h, int n, int classes, int coords);
-layer make_shortcut_layer(int batch, int index, int w, int h, int c, int w2, int h2, int c2);
-layer make_avgpool_layer(int batch, int w, int h, int c);
-layer make_softmax_layer(int batch, int inputs, int groups);
-layer make_cost_layer(int batch, int inputs, COST_TYPE type, float scale);
-
-void forward_convolutional_layer_gpu(layer l, network_state state);
-void forward_maxpool_layer_gpu(layer l, network_state state);
-void forward_reorg_layer_gpu(layer l, network_state state);
-void forward_route_layer_gpu(layer l, network_state state);
-void forward_shortcut_layer_gpu(layer l, network_state state);
-void forward_avgpool_layer_gpu(layer l, network_state state);
-void forward_softmax_layer_gpu(layer l, network_state state);
-void forward_cost_layer_gpu(layer l, network_state state);
+/* layer constructors, per-layer forwards and resizes: declared in include/darknet_b200.h */
 void forward_no_cpu_path(layer l, network_state state);
 
 uint16_t y2_f32_to_bf16(float f);

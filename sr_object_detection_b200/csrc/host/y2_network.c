@@ -1435,58 +1435,12 @@ int resize_network(network *net, int w, int h)
     for (int i = 0; i < net->n; ++i) {
         layer *l = &net->layers[i];
         switch (l->type) {
-        case CONVOLUTIONAL:
-            l->w = w;
-            l->h = h;
-            l->out_w = (w + 2 * l->pad - l->size) / l->stride + 1;
-            l->out_h = (h + 2 * l->pad - l->size) / l->stride + 1;
-            l->outputs = l->out_h * l->out_w * l->out_c;
-            l->inputs = l->w * l->h * l->c;
-            break;
-        case MAXPOOL:
-            l->w = w;
-            l->h = h;
-            l->inputs = h * w * l->c;
-            l->out_w = (w + 2 * l->pad) / l->stride;
-            l->out_h = (h + 2 * l->pad) / l->stride;
-            l->outputs = l->out_w * l->out_h * l->c;
-            break;
-        case REGION:
-            l->w = w;
-            l->h = h;
-            l->outputs = h * w * l->n * (l->classes + l->coords + 1);
-            l->inputs = l->outputs;
-            break;
-        case ROUTE: {
-            layer first = net->layers[l->input_layers[0]];
-            l->out_w = first.out_w;
-            l->out_h = first.out_h;
-            l->out_c = first.out_c;
-            l->outputs = first.outputs;
-            l->input_sizes[0] = first.outputs;
-            for (int k = 1; k < l->n; ++k) {
-                layer next = net->layers[l->input_layers[k]];
-                l->outputs += next.outputs;
-                l->input_sizes[k] = next.outputs;
-                if (next.out_w == first.out_w && next.out_h == first.out_h) l->out_c += next.out_c;
-                else l->out_h = l->out_w = l->out_c = 0;
-            }
-            l->inputs = l->outputs;
-            break;
-        }
-        case REORG:
-            l->w = w;
-            l->h = h;
-            l->out_w = w / l->stride;
-            l->out_h = h / l->stride;
-            l->outputs = l->out_h * l->out_w * l->out_c;
-            l->inputs = l->outputs;
-            break;
-        case AVGPOOL:
-            l->w = w;
-            l->h = h;
-            l->inputs = h * w * l->c;
-            break;
+        case CONVOLUTIONAL: resize_convolutional_layer(l, w, h); break;
+        case MAXPOOL: resize_maxpool_layer(l, w, h); break;
+        case REGION: resize_region_layer(l, w, h); break;
+        case ROUTE: resize_route_layer(l, net); break;
+        case REORG: resize_reorg_layer(l, w, h); break;
+        case AVGPOOL: resize_avgpool_layer(l, w, h); break;
         case COST:
         case SOFTMAX:
             break;

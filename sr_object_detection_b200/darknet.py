@@ -106,6 +106,15 @@ CONVOLUTIONAL, DECONVOLUTIONAL, CONNECTED, MAXPOOL, SOFTMAX, DETECTION, DROPOUT,
     NORMALIZATION, AVGPOOL, LOCAL, SHORTCUT, ACTIVE, RNN, GRU, CRNN, BATCHNORM, NETWORK, XNOR, REGION, \
     REORG, BLANK = range(24)
 
+# ACTIVATION (activations.h:6-8)
+LOGISTIC, RELU, RELIE, LINEAR, RAMP, TANH, PLSE, LEAKY, ELU, LOGGY, STAIR, HARDTAN, LHTAN = range(13)
+
+
+class Dim3(C.Structure):
+    """dim3 as returned by cuda_gridsize (cuda.c:51-62)."""
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("z", C.c_uint)]
+
+
 _declared = False
 
 
@@ -155,6 +164,22 @@ def lib() -> C.CDLL:
         "free_image": (None, [Image]),
         "read_tree": (C.POINTER(Tree), [C.c_char_p]),
         "max_index": (i, [fp, i]),
+        "fill_cpu": (None, [i, f, fp, i]),
+        "copy_cpu": (None, [i, fp, i, fp, i]),
+        "axpy_cpu": (None, [i, f, fp, i, fp, i]),
+        "scal_cpu": (None, [i, f, fp, i]),
+        "fill_ongpu": (None, [i, f, C.c_void_p, i]),
+        "copy_ongpu": (None, [i, C.c_void_p, i, C.c_void_p, i]),
+        "axpy_ongpu": (None, [i, f, C.c_void_p, i, C.c_void_p, i]),
+        "scal_ongpu": (None, [i, f, C.c_void_p, i]),
+        "activate": (f, [f, i]),
+        "activate_array": (None, [fp, i, i]),
+        "activate_array_ongpu": (None, [C.c_void_p, i, i]),
+        "cuda_gridsize": (Dim3, [C.c_size_t]),
+        "cuda_make_array": (C.c_void_p, [fp, C.c_size_t]),
+        "cuda_push_array": (None, [C.c_void_p, fp, C.c_size_t]),
+        "cuda_pull_array": (None, [C.c_void_p, fp, C.c_size_t]),
+        "cuda_free": (None, [C.c_void_p]),
         "y2_abi_sizeof": (C.c_size_t, [i]),
     }
     for name, (res, args) in sig.items():

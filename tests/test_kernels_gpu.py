@@ -424,3 +424,55 @@ def test_stem_u8_input_is_bit_identical_to_the_float_path(batch, h, w):
     torch.cuda.synchronize()
     assert out_f.abs().max().item() > 0
     assert torch.equal(out_u.view(torch.int16), out_f.view(torch.int16))
+
+
+def test_device_vector_helpers_and_activate_array_ongpu():
+    """fill/copy/axpy/scal_ongpu and activate_array_ongpu on cuda_make_array buffers (blas.h:43-53,
+    activations.h:18): strided and unit-stride (float4) paths; axpy/scal without fma -> bit-exact."""
+    from sr_object_detection_b200 import darknet as dn
+    lib = dn.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for n, incx, incy in [(1000, 1, 1), (1003, 1, 1), (333, 3, 2), (5, 1, 1)]:
+        x = torch.randn(n * incx + 3, generator=g).to(dev)
+        y = torch.randn(n * incy + 3, generator=g).to(dev)
+        want = y.clone()
+        want[0:n * incy:incy] = want[0:n * incy:incy] + (0.37 * x[0:n * incx:incx])
+        lib.axpy_ongpu(n, 0.37, x.data_ptr(), incx, y.data_ptr(), incy)
+        torch.cuda.synchronize()
+        assert torch.equal(y, want)
+        lib.scal_ongpu(n, 1.7, y.data_ptr(), incy)
+        want[0:n * incy:incy] *= 1.7
+        torch.cuda.synchronize()
+        assert torch.equal(y, want)
+        lib.copy_ongpu(n, x.data_ptr(), incx, y.data_ptr(), incy)
+        want[0:n * incy:incy] = x[0:n * incx:incx]
+        torch.cuda.synchronize()
+        assert torch.equal(y, want)
+        lib.fill_ongpu(n, -3.5, y.data_ptr(), incy)
+        want[0:n * incy:incy] = -3.5
+        torch.cuda.synchronize()
+        assert torch.equal(y, want)
+    # unaligned base pointer: falls back to the scalar kernel
+    z = torch.zeros(64, device=dev)
+    lib.fill_ongpu(40, 2.0, z.data_ptr() + 4, 1)
+    torch.cuda.synchronize()
+    assert z[0].item() == 0 and (z[1:41] == 2).all() and (z[41:] == 0).all()
+    # activations: host activate_array (double math) is the checker for the device kernel (float math)
+    x = torch.linspace(-6, 6, 4097)
+    for a in range(13):
+        host = x.clone().numpy()
+        lib.activate_array(host.ctypes.data_as(C.POINTER(C.c_float)), host.size, a)
+        d = x.to(dev)
+        lib.activate_array_ongpu(d.data_ptr(), d.numel(), a)
+        torch.cuda.synchronize()
+        assert np.allclose(d.cpu().numpy(), host, rtol=2e-6, atol=2e-7), a
+    # cuda_make_array / push / pull round trip
+    h = np.arange(100, dtype=np.float32)
+    fp = h.ctypes.data_as(C.POINTER(C.c_float))
+    dptr = lib.cuda_make_array(fp, h.size)
+    lib.scal_ongpu(h.size, 2.0, dptr, 1)
+    back = np.zeros_like(h)
+    lib.cuda_pull_array(dptr, back.ctypes.data_as(C.POINTER(C.c_float)), h.size)
+    assert np.array_equal(back, h * 2)
+    lib.cuda_free(dptr)

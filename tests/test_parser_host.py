@@ -189,3 +189,87 @@ def test_host_helpers_match_reference_semantics():
     inter = np.float32(w * hgt)
     union = np.float32(np.float32(np.float32(0.2) * np.float32(0.2) + np.float32(0.2) * np.float32(0.2)) - inter)
     assert lib.box_iou(b1, b2) == pytest.approx(float(inter / union), rel=1e-6)
+
+
+# ---- vector / activation helpers of the reference's C surface (blas.h:16-19, activations.h:16, cuda.h:32) ----
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def test_host_vector_helpers_follow_blas_semantics():
+    lib = dn.lib()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(40).astype(np.float32)
+    y = rng.standard_normal(40).astype(np.float32)
+    y0 = y.copy()
+    lib.axpy_cpu(13, 0.5, _fp(x), 3, _fp(y), 2)          # Y[i*2] += .5 * X[i*3]
+    want = y0.copy()
+    want[0:26:2] += np.float32(0.5) * x[0:39:3]
+    assert np.array_equal(y, want)
+    lib.scal_cpu(10, 3.0, _fp(y), 4)
+    want[0:40:4] *= np.float32(3.0)
+    assert np.array_equal(y, want)
+    lib.copy_cpu(8, _fp(x), 5, _fp(y), 1)
+    want[:8] = x[0:40:5]
+    assert np.array_equal(y, want)
+    lib.fill_cpu(7, -2.0, _fp(y), 3)
+    want[0:21:3] = -2.0
+    assert np.array_equal(y, want)
+
+
+def _ref_activate(x, a):
+    """activations.h:22-60 restated with numpy: float in, double math, one rounding to float."""
+    x = x.astype(np.float32)
+    xd = x.astype(np.float64)
+    f32 = lambda v: np.asarray(v, dtype=np.float64).astype(np.float32)  # noqa: E731
+    if a == dn.LINEAR:
+        return x
+    if a == dn.LOGISTIC:
+        return f32(1. / (1. + np.exp(-xd)))
+    if a == dn.LOGGY:
+        return f32(2. / (1. + np.exp(-xd)) - 1)
+    if a == dn.RELU:
+        return x * (x > 0)
+    if a == dn.ELU:
+        return f32((xd >= 0) * xd + (xd < 0) * (np.exp(xd) - 1))
+    if a == dn.RELIE:
+        return np.where(x > 0, x, f32(.01 * xd))
+    if a == dn.RAMP:
+        return f32(xd * (xd > 0) + .1 * xd)
+    if a == dn.LEAKY:
+        return np.where(x > 0, x, f32(.1 * xd))
+    if a == dn.TANH:
+        e = np.exp((np.float32(2) * x).astype(np.float64))
+        return f32((e - 1) / (e + 1))
+    if a == dn.PLSE:
+        return f32(np.where(xd < -4, .01 * (xd + 4), np.where(xd > 4, .01 * (xd - 4) + 1, .125 * xd + .5)))
+    if a == dn.STAIR:
+        n = np.floor(xd)
+        frac = (x - n.astype(np.float32)).astype(np.float64)  # float - int is a float subtraction in C
+        return f32(np.where(n % 2 == 0, np.floor(xd / 2.), frac + np.floor(xd / 2.)))
+    if a == dn.HARDTAN:
+        return np.clip(x, -1, 1)
+    if a == dn.LHTAN:
+        return f32(np.where(xd < 0, .001 * xd, np.where(xd > 1, .001 * (xd - 1) + 1, xd)))
+    raise AssertionError(a)
+
+
+@pytest.mark.parametrize("a", range(13))
+def test_activate_array_matches_reference_definitions(a):
+    lib = dn.lib()
+    x = np.concatenate([np.linspace(-6, 6, 241), [0.0, -0.0, 1.0, -1.0, 4.0, -4.0]]).astype(np.float32)
+    got = x.copy()
+    lib.activate_array(_fp(got), got.size, a)
+    want = _ref_activate(x, a)
+    assert np.allclose(got, want, rtol=2e-7, atol=1e-9), np.abs(got - want).max()
+    if a in (dn.LINEAR, dn.RELU, dn.LEAKY, dn.RELIE, dn.HARDTAN, dn.LOGISTIC):
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,want", [(1, (1, 1, 1)), (512, (1, 1, 1)), (513, (2, 1, 1)), (512 * 65535, (65535, 1, 1)),
+                                    (512 * 65535 + 1, (256, 256, 1)), (10 ** 9, (1398, 1398, 1))])
+def test_cuda_gridsize(n, want):
+    """cuda.c:51-62: blocks of BLOCK=512 threads, folded into (x, y) above 65535 blocks."""
+    d = dn.lib().cuda_gridsize(n)
+    assert (d.x, d.y, d.z) == want
+    assert d.x * d.y * 512 >= n
