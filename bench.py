@@ -150,7 +150,7 @@ def run_reference(args) -> int:
         r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS),
                             str(args.warmup), str(args.steps)], capture_output=True, text=True)
         if r.returncode != 0:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-160:]}))
+            _emit({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-160:]})
             return 0
         d = json.loads(r.stdout.strip().splitlines()[-1])
         ips = d["images_per_s"]
@@ -165,11 +165,33 @@ def run_reference(args) -> int:
             "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        _emit(line)
     return 0
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write banners to file descriptor 1 on their
+    own (NCCL prints "NCCL version ..." from C), so keep a private duplicate of the real stdout for the
+    JSON line and point fd 1 at stderr for everything else in this process."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def _emit(line: dict) -> None:
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> int:
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -408,8 +430,7 @@ def main() -> int:
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tmp)
-        print(json.dumps(line))
-        sys.stdout.flush()
+        _emit(line)
         if args.profile_out:
             Path(args.profile_out).write_text(json.dumps({"batch": B, "layers": table, "line": line}, indent=1))
     dn.free_network(net)
