@@ -346,6 +346,15 @@ unsigned char *network_pipeline_staging_u8(network net, int slot);
 int network_detect_submit_u8(network net, const unsigned char *input_hwc, float thresh, float nms, int max_det);
 void network_detect_batch_u8(network net, const unsigned char *input_hwc, float thresh, float nms,
                              y2_detection *dets, int *counts, int max_det);
+/* Decoded frames of ANY size, uint8 interleaved RGB [batch][frame_h][frame_w][3]: the bytes are
+ * uploaded as they are and both load_image_stb's byte/255. (yolo_v2_class.cpp:129-149) and resize_image
+ * (image.c:1950-1993) run on the device, bit-identical to the host path of Detector::detect(filename)
+ * (yolo_v2_class.cpp:173-206).  Works with every supported cfg (3 input channels). */
+unsigned char *network_pipeline_staging_frames(network net, int slot, int frame_w, int frame_h);
+int network_detect_submit_frames(network net, const unsigned char *frames_hwc, int frame_w, int frame_h,
+                                 float thresh, float nms, int max_det);
+void network_detect_batch_frames(network net, const unsigned char *frames_hwc, int frame_w, int frame_h,
+                                 float thresh, float nms, y2_detection *dets, int *counts, int max_det);
 /* Block until the network's stream is idle. */
 void network_sync(network net);
 /* Device stream the network runs on (cudaStream_t) — for timing with CUDA events. */

@@ -161,6 +161,12 @@ int y2_gather_patches_f32(const float *src, void *dst, int batch, int c, int h, 
 int y2_gather_patches_bf16(const void *in, int in_cs, int cin_pad, int h, int w, void *dst, int batch,
                            int ksize, int stride, int pad, int oh, int ow, y2_stream_t s);
 
+/* Decoded frames -> network input on the device: uint8 interleaved RGB [B][src_h][src_w][3] ->
+ * fp32 planar [B][3][h][w], = load_image_stb's byte/255. (yolo_v2_class.cpp:129-149) followed by
+ * resize_image (image.c:1950-1993), bit-identical to that host path. */
+int y2_resize_u8_to_f32(const unsigned char *src, float *dst, int batch, int src_w, int src_h, int w,
+                        int h, y2_stream_t s);
+
 /* bf16 padded NHWC slice -> fp32 NCHW [B][C][H][W] (host-visible l.output layout). */
 int y2_unpack_to_nchw_f32(const void *src, float *dst, int batch, int c, int h, int w,
                           int cs, y2_stream_t s);

@@ -59,8 +59,9 @@ public:
 
     YOLODLL_API std::vector<bbox_t> tracking(std::vector<bbox_t> cur_bbox_vec, int const frames_story = 6);
 
-    /* B200 extension: raw decoded frame, uint8 interleaved RGB at the network's resolution; the
-     * byte -> float conversion of load_image / mat_to_image happens on the device (identical result) */
+    /* B200 extension: raw decoded frame, uint8 interleaved RGB of any size; the byte -> float
+     * conversion of load_image and resize_image (image.c:1950-1993) happen on the device, with the same
+     * result as detect(image_filename) gives for that frame */
     YOLODLL_API std::vector<bbox_t> detect_rgb8(const unsigned char *rgb, int w, int h, float thresh = 0.2f);
 
 #ifdef OPENCV

@@ -157,6 +157,58 @@ __global__ void gather_patches_bf16_kernel(const __nv_bfloat16 *__restrict__ in,
 }
 
 // ---------------------------------------------------------------------------------
+// decoded frame -> network input: uint8 interleaved RGB [B][sh][sw][3] -> fp32 planar [B][3][h][w],
+// the composition of the reference's loaders and its resize on the host:
+//   load_image_stb        im[k][y][x] = (float)byte / 255.           (yolo_v2_class.cpp:129-149)
+//   resize_image          two-pass bilinear, horizontal into `part`, then vertical (image.c:1950-1993)
+// Every float expression keeps the reference's operation order and roundings (explicit _rn
+// intrinsics, no fma), so the result is bit-identical to the host path; the horizontal pass is
+// recomputed for the two source rows a target pixel needs instead of materialising `part`.
+// Quirk kept: the last target row takes only the (1-dy) term (image.c:1985 `continue`).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float resize_part(const unsigned char *__restrict__ row, const float *lut, int sw, int w,
+                                             int c, int k, float w_scale)
+{
+    if (c == w - 1 || sw == 1) return lut[row[(size_t)(sw - 1) * 3 + k]];
+    const float sx = __fmul_rn((float)c, w_scale);
+    int ix = (int)sx;
+    const float dx = __fsub_rn(sx, (float)ix);
+    int ix1 = ix + 1;
+    if (ix1 > sw - 1) ix1 = sw - 1; // the reference would assert here; unreachable for exact scales
+    const float a = __fmul_rn(__fsub_rn(1.f, dx), lut[row[(size_t)ix * 3 + k]]);
+    const float b = __fmul_rn(dx, lut[row[(size_t)ix1 * 3 + k]]);
+    return __fadd_rn(a, b);
+}
+
+__global__ void resize_u8_to_f32_kernel(const unsigned char *__restrict__ src, float *__restrict__ dst, int batch,
+                                        int sw, int sh, int w, int h, float w_scale, float h_scale)
+{
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (float)((double)(float)i / 255.);
+    __syncthreads();
+    const long long total = (long long)batch * 3 * h * w;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % w);
+        const int r = (int)((t / w) % h);
+        const int k = (int)((t / ((long long)w * h)) % 3);
+        const int b = (int)(t / ((long long)w * h * 3));
+        const unsigned char *img = src + (size_t)b * sh * sw * 3;
+        const float sy = __fmul_rn((float)r, h_scale);
+        int iy = (int)sy;
+        if (iy > sh - 1) iy = sh - 1;
+        const float dy = __fsub_rn(sy, (float)iy);
+        float val = __fmul_rn(__fsub_rn(1.f, dy), resize_part(img + (size_t)iy * sw * 3, lut, sw, w, c, k, w_scale));
+        if (!(r == h - 1 || sh == 1)) {
+            int iy1 = iy + 1;
+            if (iy1 > sh - 1) iy1 = sh - 1;
+            val = __fadd_rn(val, __fmul_rn(dy, resize_part(img + (size_t)iy1 * sw * 3, lut, sw, w, c, k, w_scale)));
+        }
+        dst[t] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // bf16 padded NHWC slice -> fp32 NCHW (export of l.output).  32x32 smem transpose so
 // both sides are coalesced: reads run along channels, writes along x.
 // ---------------------------------------------------------------------------------
@@ -566,6 +618,23 @@ extern "C" int y2_gather_patches_bf16(const void *in, int in_cs, int cin_pad, in
     const long long total = (long long)batch * (oh + 1) * (ow + 1) * ksize * ksize * (cin_pad / 8);
     gather_patches_bf16_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
         (const __nv_bfloat16 *)in, in_cs, cin_pad, h, w, (__nv_bfloat16 *)dst, batch, ksize, stride, pad, oh, ow);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_resize_u8_to_f32(const unsigned char *src, float *dst, int batch, int src_w, int src_h, int w,
+                                   int h, y2_stream_t s)
+{
+    if (!src || !dst || batch <= 0 || src_w <= 0 || src_h <= 0 || w <= 0 || h <= 0) {
+        set_error("y2_resize_u8_to_f32: invalid arguments (%dx%d -> %dx%d)", src_w, src_h, w, h);
+        return Y2_EINVAL;
+    }
+    // image.c:1954-1955: float w_scale = (float)(im.w - 1) / (w - 1)  (w == 1 divides by zero there too)
+    const float w_scale = (float)(src_w - 1) / (w - 1);
+    const float h_scale = (float)(src_h - 1) / (h - 1);
+    const long long total = (long long)batch * 3 * h * w;
+    resize_u8_to_f32_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(src, dst, batch, src_w, src_h, w, h,
+                                                                            w_scale, h_scale);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

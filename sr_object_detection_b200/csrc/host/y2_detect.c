@@ -272,14 +272,28 @@ unsigned char *network_pipeline_staging_u8(network net, int slot)
     return rt->pipe[slot].in_u8_pinned;
 }
 
-/* input: fp32 planar [B][c][h][w] (u8 == 0) or uint8 interleaved RGB [B][h][w][3] (u8 == 1) */
-static int submit_common(network net, const void *input, int u8, float thresh, float nms, int max_det)
+static void pipe_reserve_frames(y2_net_rt *rt, int s, size_t bytes)
+{
+    struct y2_pipe_slot *ps = &rt->pipe[s];
+    if (ps->frames_cap >= bytes) return;
+    y2_free(ps->frames_dev);
+    y2_host_free(ps->frames_pinned);
+    Y2_CHECK(y2_malloc((void **)&ps->frames_dev, bytes));
+    Y2_CHECK(y2_host_alloc((void **)&ps->frames_pinned, bytes));
+    ps->frames_cap = bytes;
+}
+
+/* input: fp32 planar [B][c][h][w] (u8 == 0), uint8 interleaved RGB [B][h][w][3] at the network's
+ * resolution (u8 == 1), or uint8 interleaved RGB frames [B][fh][fw][3] of any size (u8 == 2) */
+static int submit_common(network net, const void *input, int u8, int fw, int fh, float thresh, float nms,
+                         int max_det)
 {
     y2_net_rt *rt = y2_rt(net);
     if (!rt) error("network_detect_submit: network has no device plan");
     if (net.batch != rt->plan_batch) error("network batch changed without set_batch_network");
-    if (u8) pipe_init_u8(net);
+    if (u8 == 1) pipe_init_u8(net);
     else pipe_init(net);
+    if (u8 == 2 && (net.c != 3 || fw <= 0 || fh <= 0)) error("network_detect_submit_frames: needs 3-channel input and a frame size");
     if (rt->pipe_inflight >= 2) error("network_detect_submit: two batches already in flight, call network_detect_wait");
     Y2_CHECK(y2_set_device(rt->device));
     const int s = (rt->pipe_head + rt->pipe_inflight) & 1;
@@ -291,7 +305,12 @@ static int submit_common(network net, const void *input, int u8, float thresh, f
     pipe_reserve_dets(rt, s, B, max_det);
     /* pageable caller memory is staged through the slot's pinned buffer (a host copy; fill the slot's
      * staging buffer directly to avoid it) */
-    if (u8) {
+    if (u8 == 2) {
+        const size_t bytes = (size_t)B * fh * fw * 3;
+        pipe_reserve_frames(rt, s, bytes);
+        if (input && input != ps->frames_pinned) memcpy(ps->frames_pinned, input, bytes);
+        Y2_CHECK(y2_memcpy_h2d(ps->frames_dev, ps->frames_pinned, bytes, rt->copy_stream));
+    } else if (u8) {
         const size_t bytes = (size_t)B * net.h * net.w * 3;
         if (input && input != ps->in_u8_pinned) memcpy(ps->in_u8_pinned, input, bytes);
         Y2_CHECK(y2_memcpy_h2d(ps->in_u8_dev, ps->in_u8_pinned, bytes, rt->copy_stream));
@@ -302,7 +321,9 @@ static int submit_common(network net, const void *input, int u8, float thresh, f
     }
     Y2_CHECK(y2_event_record(ps->ev_h2d, rt->copy_stream));
     Y2_CHECK(y2_stream_wait_event(rt->stream, ps->ev_h2d));
-    if (u8) {
+    if (u8 == 2) /* byte/255. + resize_image on the device, into the slot's fp32 input */
+        Y2_CHECK(y2_resize_u8_to_f32(ps->frames_dev, ps->in_dev, B, fw, fh, net.w, net.h, rt->stream));
+    if (u8 == 1) {
         rt->input_u8 = 1; /* read while the layer list is captured */
         y2_run_forward_from(net, (float *)ps->in_u8_dev, &ps->graph_u8, &ps->graph_u8_valid);
         rt->input_u8 = 0;
@@ -327,12 +348,12 @@ static int submit_common(network net, const void *input, int u8, float thresh, f
 
 int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det)
 {
-    return submit_common(net, input, 0, thresh, nms, max_det);
+    return submit_common(net, input, 0, 0, 0, thresh, nms, max_det);
 }
 
 int network_detect_submit_u8(network net, const unsigned char *input_hwc, float thresh, float nms, int max_det)
 {
-    return submit_common(net, input_hwc, 1, thresh, nms, max_det);
+    return submit_common(net, input_hwc, 1, 0, 0, thresh, nms, max_det);
 }
 
 int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det)
@@ -361,6 +382,44 @@ void network_detect_batch_u8(network net, const unsigned char *input_hwc, float 
 {
     y2_net_rt *rt = y2_rt(net);
     if (rt && rt->pipe_inflight) error("network_detect_batch_u8: batches of the submit/wait pipeline are in flight");
-    submit_common(net, input_hwc, 1, thresh, nms, max_det);
+    submit_common(net, input_hwc, 1, 0, 0, thresh, nms, max_det);
+    network_detect_wait(net, dets, counts, max_det);
+}
+
+/* Decoded frames of any size: upload the raw bytes, then byte/255. (load_image_stb) and resize_image
+ * (image.c:1950-1993) run on the device, bit-identical to Detector::detect(filename)'s host path
+ * (yolo_v2_class.cpp:173-206).  Frames already at the network's resolution take the uint8 first-layer
+ * path when the network has one. */
+int network_detect_submit_frames(network net, const unsigned char *frames_hwc, int frame_w, int frame_h, float thresh,
+                                 float nms, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt) error("network_detect_submit_frames: network has no device plan");
+    y2_layer_rt *r0 = (y2_layer_rt *)net.layers[0].b200;
+    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3)
+        return submit_common(net, frames_hwc, 1, 0, 0, thresh, nms, max_det);
+    return submit_common(net, frames_hwc, 2, frame_w, frame_h, thresh, nms, max_det);
+}
+
+unsigned char *network_pipeline_staging_frames(network net, int slot, int frame_w, int frame_h)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt || slot < 0 || slot > 1 || frame_w <= 0 || frame_h <= 0)
+        error("network_pipeline_staging_frames: bad slot, frame size or unplanned network");
+    y2_layer_rt *r0 = (y2_layer_rt *)net.layers[0].b200;
+    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3)
+        return network_pipeline_staging_u8(net, slot);
+    pipe_init(net);
+    Y2_CHECK(y2_set_device(rt->device));
+    pipe_reserve_frames(rt, slot, (size_t)rt->cap_batch * frame_h * frame_w * 3);
+    return rt->pipe[slot].frames_pinned;
+}
+
+void network_detect_batch_frames(network net, const unsigned char *frames_hwc, int frame_w, int frame_h, float thresh,
+                                 float nms, y2_detection *dets, int *counts, int max_det)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (rt && rt->pipe_inflight) error("network_detect_batch_frames: batches of the submit/wait pipeline are in flight");
+    network_detect_submit_frames(net, frames_hwc, frame_w, frame_h, thresh, nms, max_det);
     network_detect_wait(net, dets, counts, max_det);
 }

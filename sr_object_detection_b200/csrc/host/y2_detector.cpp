@@ -224,10 +224,11 @@ std::vector<bbox_t> Detector::detect_rgb8(const unsigned char *rgb, int w, int h
     State &st = state_of(detector_gpu_ptr);
     network &net = st.net;
     if (!rgb) throw std::runtime_error("Image is empty");
-    if (w != net.w || h != net.h) throw std::runtime_error("detect_rgb8 needs a frame of the network's resolution");
+    if (w <= 0 || h <= 0) throw std::runtime_error("Image is empty");
     DeviceScope scope(net.gpu_index);
     int count = 0;
-    network_detect_batch_u8(net, rgb, thresh, nms, st.dets.data(), &count, st.total);
+    /* any frame size: byte/255. and resize_image run on the device, as detect(filename) does on the host */
+    network_detect_batch_frames(net, rgb, w, h, thresh, nms, st.dets.data(), &count, st.total);
     if (count > st.total) count = st.total;
     std::vector<bbox_t> found;
     found.reserve(count);

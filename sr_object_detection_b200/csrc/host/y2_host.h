@@ -96,6 +96,9 @@ typedef struct y2_net_rt {
         unsigned char *in_u8_dev, *in_u8_pinned;
         y2_graph_t graph_u8;
         int graph_u8_valid;
+        /* decoded frames of any size (network_detect_submit_frames): resized on the device into in_dev */
+        unsigned char *frames_dev, *frames_pinned;
+        size_t frames_cap;
     } pipe[2];
     y2_stream_t copy_stream;
     int pipe_ready, pipe_head, pipe_inflight;

@@ -1188,6 +1188,8 @@ static void pipe_free(y2_net_rt *rt)
     for (int s = 0; s < 2; ++s) {
         y2_free(rt->pipe[s].in_u8_dev);
         y2_host_free(rt->pipe[s].in_u8_pinned);
+        y2_free(rt->pipe[s].frames_dev);
+        y2_host_free(rt->pipe[s].frames_pinned);
         y2_free(rt->pipe[s].det_dev);
         y2_host_free(rt->pipe[s].det_pinned);
         y2_free(rt->pipe[s].cnt_dev);

@@ -152,6 +152,9 @@ def lib() -> C.CDLL:
         "network_pipeline_staging_u8": (C.POINTER(C.c_ubyte), [Network, i]),
         "network_detect_submit_u8": (i, [Network, C.POINTER(C.c_ubyte), f, f, i]),
         "network_detect_batch_u8": (None, [Network, C.POINTER(C.c_ubyte), f, f, C.POINTER(Detection), _ip, i]),
+        "network_pipeline_staging_frames": (C.POINTER(C.c_ubyte), [Network, i, i, i]),
+        "network_detect_submit_frames": (i, [Network, C.POINTER(C.c_ubyte), i, i, f, f, i]),
+        "network_detect_batch_frames": (None, [Network, C.POINTER(C.c_ubyte), i, i, f, f, C.POINTER(Detection), _ip, i]),
         "network_sync": (None, [Network]),
         "network_stream": (C.c_void_p, [Network]),
         "network_conv_flops": (C.c_double, [Network]),

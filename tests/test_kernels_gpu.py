@@ -476,3 +476,40 @@ def test_device_vector_helpers_and_activate_array_ongpu():
     lib.cuda_pull_array(dptr, back.ctypes.data_as(C.POINTER(C.c_float)), h.size)
     assert np.array_equal(back, h * 2)
     lib.cuda_free(dptr)
+
+
+@pytest.mark.parametrize("sw,sh,w,h", [(640, 480, 416, 416), (300, 200, 416, 416), (416, 416, 416, 416),
+                                       (1920, 1080, 608, 608), (37, 53, 64, 32), (1, 9, 32, 32)])
+def test_device_resize_is_bit_identical_to_load_image_plus_resize_image(tmp_path, sw, sh, w, h):
+    """y2_resize_u8_to_f32 (uint8 HWC frame -> fp32 planar network input) against the CPU chain it
+    replaces: byte/255. (yolo_v2_class.cpp:129-149) then resize_image (image.c:1950-1993), computed by the
+    oracle (pinned to the reference by tests/golden/resize.npz) and by the library's own host resize_image."""
+    import subprocess
+    from sr_object_detection_b200 import darknet as dn
+    from tests import ref_util as R
+    R.build_oracle()
+    dev = torch.device("cuda:0")
+    batch = 2
+    rng = np.random.default_rng(sw * 7 + sh)
+    u8 = rng.integers(0, 256, size=(batch, sh, sw, 3), dtype=np.uint8)
+    planar = (u8.transpose(0, 3, 1, 2).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
+    lib = _lib.load()
+    src = torch.from_numpy(u8).to(dev)
+    dst = torch.full((batch, 3, h, w), -1.0, device=dev)
+    _lib.check(lib.y2_resize_u8_to_f32(src.data_ptr(), dst.data_ptr(), batch, sw, sh, w, h, _stream()))
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    dl = dn.lib()
+    for b in range(batch):
+        np.ascontiguousarray(planar[b]).tofile(tmp_path / "im.f32")
+        subprocess.run([str(R.ORACLE_BIN), "resize", "im.f32", "3", str(sh), str(sw), str(h), str(w), "out.f32"],
+                       check=True, cwd=tmp_path, capture_output=True)
+        want = np.fromfile(tmp_path / "out.f32", dtype=np.float32).reshape(3, h, w)
+        assert np.array_equal(got[b].view(np.uint32), want.view(np.uint32)), \
+            f"frame {b}: {(got[b] != want).sum()} of {want.size} values differ from the oracle"
+        src_img = np.ascontiguousarray(planar[b])
+        im = dn.Image(sh, sw, 3, src_img.ctypes.data_as(C.POINTER(C.c_float)))
+        out = dl.resize_image(im, w, h)
+        host = np.ctypeslib.as_array(out.data, shape=(3, h, w)).copy()
+        dl.free_image(out)
+        assert np.array_equal(host.view(np.uint32), want.view(np.uint32))

@@ -215,3 +215,53 @@ def test_u8_input_detections_equal_float_input(tmp_path):
         for b in range(batch):
             assert arr[b * max_det:b * max_det + min(counts[b], max_det)].tobytes() == want[b].tobytes()
     dn.free_network(net)
+
+
+def test_frames_of_any_size_equal_host_resize_then_float_detect(tmp_path):
+    """network_detect_batch_frames (raw uint8 frames of any size; byte/255. + resize_image on the device)
+    must give exactly the detections of the reference's host chain: load_image -> resize_image ->
+    network_predict -> get_region_boxes -> do_nms_sort (yolo_v2_class.cpp:173-239)."""
+    import ctypes as C
+    batch, max_det = 2, 256
+    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", batch)
+    dn.set_gpu_index(0)
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    lib = dn.lib()
+    thresh, nms = 0.02, 0.4
+    dets = (dn.Detection * (batch * max_det))()
+    counts = (C.c_int * batch)()
+    for fw, fh in [(640, 480), (416, 416), (333, 517)]:
+        rng = np.random.default_rng(fw)
+        u8 = rng.integers(0, 256, size=(batch, fh, fw, 3), dtype=np.uint8)
+        planar = (u8.transpose(0, 3, 1, 2).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
+        sized = np.empty((batch, 3, 416, 416), dtype=np.float32)
+        for b in range(batch):
+            src = np.ascontiguousarray(planar[b])
+            out = lib.resize_image(dn.Image(fh, fw, 3, src.ctypes.data_as(C.POINTER(C.c_float))), 416, 416)
+            sized[b] = np.ctypeslib.as_array(out.data, shape=(3, 416, 416))
+            lib.free_image(out)
+        want, _ = dn.network_detect_batch(net, sized, thresh, nms, max_det)
+        assert any(len(w) for w in want), "test needs at least one detection"
+        lib.network_detect_batch_frames(net, u8.ctypes.data_as(C.POINTER(C.c_ubyte)), fw, fh, thresh, nms, dets,
+                                        counts, max_det)
+        arr = np.ctypeslib.as_array(dets)
+        for b in range(batch):
+            got = arr[b * max_det:b * max_det + min(counts[b], max_det)]
+            assert got.tobytes() == want[b].tobytes(), f"{fw}x{fh} image {b}: device and host resize paths disagree"
+    # pipelined, frames written straight into the pinned staging buffer
+    fw, fh = 640, 480
+    u8 = np.random.default_rng(fw).integers(0, 256, size=(batch, fh, fw, 3), dtype=np.uint8)
+    lib.network_detect_batch_frames(net, u8.ctypes.data_as(C.POINTER(C.c_ubyte)), fw, fh, thresh, nms, dets, counts,
+                                    max_det)
+    ref = [np.ctypeslib.as_array(dets)[b * max_det:b * max_det + min(counts[b], max_det)].tobytes() for b in range(batch)]
+    for _ in range(4):
+        slot = lib.network_pipeline_next_slot(net)
+        stage = lib.network_pipeline_staging_frames(net, slot, fw, fh)
+        C.memmove(stage, u8.ctypes.data, u8.nbytes)
+        lib.network_detect_submit_frames(net, stage, fw, fh, thresh, nms, max_det)
+        lib.network_detect_wait(net, dets, counts, max_det)
+        arr = np.ctypeslib.as_array(dets)
+        for b in range(batch):
+            assert arr[b * max_det:b * max_det + min(counts[b], max_det)].tobytes() == ref[b]
+    dn.free_network(net)
