@@ -20,6 +20,16 @@
 //     the leader's barrier (remote mbarrier.arrive through mapa).
 // Everything else (halo slab, row-shifted descriptors, double-buffered accumulators, 8 epilogue
 // warps) is conv_slab.cu's design.
+//
+// Work distribution.  Whole tiles round-robin leave the last wave partly empty when the tile count is
+// a small non-multiple of the 74 pairs (13x13 layers at batch 64: 196 tiles = 2.65 waves, run as 3).
+// With prm.streamk the K loops of all tiles are laid end to end in units of one channel block
+// (64 input channels x 9 taps) and every pair takes an equal contiguous share: a pair's share starts
+// with the tail of a tile, continues with whole tiles and ends with the head of a tile.  The pair that
+// computes a tile's TAIL does so first thing and parks its raw fp32 accumulator in global scratch;
+// the pair that computes the HEAD does so last, adds the parked partial in its epilogue and finishes
+// the tile.  The dependency always points from a pair's first segment to another pair's last one, so
+// with all pairs resident (grid = SM count) nothing can wait on work that has not been scheduled.
 #include "conv_epilogue.cuh"
 
 #include <stdlib.h>
@@ -39,6 +49,63 @@ constexpr uint32_t kPairDescHi = ((8u * kPairRowBytes) >> 4) | (1u << 14) | (2u 
 // c = F32, a = b = BF16, K-major, N = 256, M = 256 (both CTAs)
 constexpr uint32_t kPairIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPairN >> 3) << 17) |
                                 ((uint32_t)(256 >> 4) << 24);
+
+// one stretch of K iterations of one tile: channel blocks [cb0, cb1)
+struct PairSeg {
+    int tile, cb0, cb1;
+};
+
+struct PairSched {
+    int streamk, n_pairs, cblocks, cur, end;
+    __device__ PairSched(const SlabParams &prm, int pair, int n_pairs_)
+        : streamk(prm.streamk), n_pairs(n_pairs_), cblocks(prm.cblocks)
+    {
+        const int total_tiles = prm.tiles_m * prm.tiles_n;
+        if (streamk) {
+            const long long units = (long long)total_tiles * cblocks;
+            cur = (int)(units * pair / n_pairs);
+            end = (int)(units * (pair + 1) / n_pairs);
+        } else {
+            cur = pair;
+            end = total_tiles;
+        }
+    }
+    __device__ bool next(PairSeg &s)
+    {
+        if (cur >= end) return false;
+        if (streamk) {
+            s.tile = cur / cblocks;
+            s.cb0 = cur - s.tile * cblocks;
+            const int left = end - cur, room = cblocks - s.cb0;
+            const int n = left < room ? left : room;
+            s.cb1 = s.cb0 + n;
+            cur += n;
+        } else {
+            s.tile = cur;
+            s.cb0 = 0;
+            s.cb1 = cblocks;
+            cur += n_pairs;
+        }
+        return true;
+    }
+    __device__ bool peek(PairSeg &s) const
+    {
+        PairSched copy = *this;
+        return copy.next(s);
+    }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -70,8 +137,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
     const int n_pairs = gridDim.x >> 1;
-    const int total_tiles = prm.tiles_m * prm.tiles_n;
     const int cblocks = prm.cblocks;
+    PairSched sched(prm, pair, n_pairs);
+    PairSeg seg;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -107,10 +175,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t phase = 0;
         const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * kPairRowBytes;
         const uint32_t load_bytes = (uint32_t)prm.box_rows * kPairRowBytes;
-        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-            const int m_tile = tile / prm.tiles_n;
+        while (sched.next(seg)) {
+            const int m_tile = seg.tile / prm.tiles_n;
             const int row0 = m_tile * 256 + (int)rank * 128 - prm.halo;
-            for (int cb = 0; cb < cblocks; ++cb) {
+            for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
                 mbar_wait(&a_empty[stage], phase ^ 1, 1);
                 if (elect_one_sync()) {
                     uint8_t *sa = smem_a + (size_t)stage * prm.slab_bytes;
@@ -127,10 +195,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===================== weight producer (both CTAs, own 128 filters) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-            const int m_tile = tile / prm.tiles_n;
-            const int n0 = (tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
-            for (int cb = 0; cb < cblocks; ++cb) {
+        while (sched.next(seg)) {
+            const int m_tile = seg.tile / prm.tiles_n;
+            const int n0 = (seg.tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
+            for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     mbar_wait(&b_empty[stage], phase ^ 1, 2);
@@ -155,16 +223,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t slab16 = (uint32_t)prm.slab_bytes >> 4;
             constexpr uint32_t kRow16 = kPairRowBytes >> 4;
             const uint32_t wp16 = (uint32_t)prm.wp * kRow16;
-            for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+            for (; sched.next(seg); ++it) {
                 const int buf = it & 1;
                 const uint32_t buf_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[buf], buf_phase ^ 1, 3);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(buf * kPairN);
-                for (int cb = 0; cb < cblocks; ++cb) {
+                for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
                     mbar_wait(&a_full[sa_i], pa, 4);
                     const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
-                    const uint32_t acc_first = cb != 0;
+                    const uint32_t acc_first = cb != seg.cb0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&b_full[sb_i], pb, 5);
@@ -180,7 +248,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             umma_commit_pair(&b_empty[sb_i]);
                             if (tap == 8) {
                                 umma_commit_pair(&a_empty[sa_i]);
-                                if (cb == cblocks - 1) umma_commit_pair(&tfull_bar[buf]);
+                                if (cb == seg.cb1 - 1) umma_commit_pair(&tfull_bar[buf]);
                             }
                         }
                         __syncwarp();
@@ -198,24 +266,34 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int col0 = half * 128;
         const int img_pos = prm.hp * prm.wp;
         int it = 0;
-        if (pair < total_tiles) {
-            const int n0 = (pair % prm.tiles_n) * kPairN;
+        const int ewarp = (int)rank * 8 + (warp - 3);  // 0..15 within the pair
+        if (sched.peek(seg)) {
+            const int n0 = (seg.tile % prm.tiles_n) * kPairN;
             s_ab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
         }
-        for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+        for (; sched.next(seg); ++it) {
+            const int tile = seg.tile;
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
             const int m_tile = tile / prm.tiles_n;
             const int n0 = (tile - m_tile * prm.tiles_n) * kPairN;
+            // stream-K roles of this segment: the tail of a tile is parked, the head adds it and finishes
+            const bool park = seg.cb0 > 0;
+            const bool join = seg.cb0 == 0 && seg.cb1 < cblocks;
             const float2 *sab = s_ab + (prm.tiles_n > 1 ? buf * kPairN : 0);
             const bool reload = prm.tiles_n > 1 || it == 0;
             if (reload) asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int next = tile + n_pairs;
+            PairSeg nseg;
+            const bool has_next = sched.peek(nseg);
             float2 ab_next = make_float2(1.f, 0.f);
-            if (prm.tiles_n > 1 && next < total_tiles) {
-                const int nn = (next % prm.tiles_n) * kPairN;
+            if (prm.tiles_n > 1 && has_next) {
+                const int nn = (nseg.tile % prm.tiles_n) * kPairN;
                 ab_next = make_float2(__ldg(prm.alpha + nn + et), __ldg(prm.beta + nn + et));
             }
+            // scratch of a split tile belongs to the pair that parks it: this pair, or the next one
+            float *part = prm.sk_partial + (size_t)(park ? pair : pair + 1) * (kPairN * 256) + (int)rank * 128 +
+                          quarter * 32 + lane;
+            int *flag = prm.sk_flags + (park ? pair : pair + 1) * 16 + ewarp;
             const int p = m_tile * 256 + (int)rank * 128 + quarter * 32 + lane;
             const bool in_range = p < prm.total_pos;
             const int b = p / img_pos;
@@ -236,6 +314,28 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (c == 64) {  // accumulator drained into registers: hand it back to the leader's MMA warp
                     tc_fence_before();
                     mbar_arrive_cluster(&tempty_bar[buf], 0);
+                }
+                if (park) {  // raw partial sums, [filter][position]: a warp stores 128 contiguous bytes per filter
+                    float *dst = part + (size_t)(col0 + c) * 256;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        dst[j * 256] = __uint_as_float(v0[j]);
+                        dst[(32 + j) * 256] = __uint_as_float(v1[j]);
+                    }
+                    continue;
+                }
+                if (join) {
+                    if (c == 0) {
+                        if (lane == 0)
+                            while (ld_acquire_gpu(flag) == 0) __nanosleep(64);
+                        __syncwarp();
+                    }
+                    const float *src = part + (size_t)(col0 + c) * 256;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __ldcg(src + j * 256));
+                        v1[j] = __float_as_uint(__uint_as_float(v1[j]) + __ldcg(src + (32 + j) * 256));
+                    }
                 }
                 if (prm.tma_store) {  // bf16 tensor: staged, one TMA store per warp and 64 channels
                     uint4 w[8];
@@ -261,7 +361,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
                 }
             }
-            if (prm.tiles_n > 1 && next < total_tiles) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
+            if (park) {  // publish: every lane's stores, then the warp's flag
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(flag, 1);
+                }
+            } else if (join) {  // consumed: leave the flag clear for the next launch
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile int *>(flag) = 0;
+            }
+            if (prm.tiles_n > 1 && has_next) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
         }
         if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
@@ -340,6 +450,24 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int tiles = p.tiles_m * p.tiles_n;
     const int pairs = tiles < sms / 2 ? tiles : sms / 2;
     pl->grid = 2 * pairs;
+    // stream-K when whole tiles would leave the last wave badly filled (and there is a K loop to split)
+    p.streamk = 0;
+    p.sk_partial = nullptr;
+    p.sk_flags = nullptr;
+    if (tiles > pairs && p.cblocks >= 2) {
+        const int waves = (tiles + pairs - 1) / pairs;
+        const double fill = (double)tiles / ((double)waves * pairs);
+        p.streamk = fill < 0.95;
+        if (const char *e = getenv("Y2_PAIR_STREAMK")) p.streamk = atoi(e) != 0;
+    }
+    if (p.streamk) {
+        const size_t partial_bytes = (size_t)(pairs + 1) * kPairN * 256 * sizeof(float);
+        const size_t flag_bytes = (size_t)(pairs + 1) * 16 * sizeof(int);
+        Y2_CUDA_CHECK(cudaMalloc(&pl->sk_buf, partial_bytes + flag_bytes));
+        Y2_CUDA_CHECK(cudaMemset(pl->sk_buf, 0, partial_bytes + flag_bytes));
+        p.sk_partial = (float *)pl->sk_buf;
+        p.sk_flags = (int *)((char *)pl->sk_buf + partial_bytes);
+    }
     static bool attr_done[64] = {false};
     int dev = 0;
     Y2_CUDA_CHECK(cudaGetDevice(&dev));

@@ -41,6 +41,9 @@ struct SlabParams {
     int cout, act, out_mode, out_cs;
     int tma_store;         // bf16 output leaves through per-warp TMA stores (else direct 16-byte stores)
     int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
+    int streamk;           // pair kernel: K-split work distribution (conv_pair.cu), else whole tiles round-robin
+    float *sk_partial;     // [pairs][256 filters][256 positions] fp32 partial accumulators of split tiles
+    int *sk_flags;         // [pairs][16 epilogue warps] "partial written" flags, zero between launches
     const float *alpha;
     const float *beta;
     void *out;
@@ -86,6 +89,7 @@ struct y2_conv_plan {
     int block_n, block_k, taps;
     int grid;
     size_t smem_bytes;
+    void *sk_buf = nullptr;  // device scratch of the stream-K pair kernel (partials + flags), owned by the plan
 };
 
 namespace y2 {

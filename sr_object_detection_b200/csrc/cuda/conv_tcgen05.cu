@@ -461,7 +461,12 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
     return Y2_EINVAL;
 }
 
-extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl) { delete pl; }
+extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl)
+{
+    if (!pl) return;
+    if (pl->sk_buf) cudaFree(pl->sk_buf);
+    delete pl;
+}
 
 extern "C" int y2_conv_plan_variant(const y2_conv_plan *pl)
 {

@@ -55,6 +55,11 @@ CONV_CASES = [
     (1, 32, 208, 208, 64, 3, 64, 32, ACT_LEAKY),
     (3, 128, 52, 52, 256, 3, 256, 64, ACT_LEAKY),
     (5, 128, 17, 23, 64, 1, 64, 64, ACT_LINEAR),
+    # more tiles than CTA pairs with a badly filled last wave: the pair kernel switches to its stream-K
+    # schedule (tiles split between pairs along K, partial sums joined through global scratch)
+    (64, 256, 13, 13, 512, 3, 256, 64, ACT_LEAKY),
+    (64, 128, 13, 13, 1024, 3, 256, 64, ACT_LINEAR),
+    (48, 192, 13, 13, 768, 3, 256, 64, ACT_LEAKY),
 ]
 
 
@@ -87,8 +92,9 @@ def test_conv_bf16_matches_fp32_reference(case, conv_variant):
     x_p = G.to_padded_nhwc(x)
     wt_p = G.pack_weights(wt, cin, npad)
     out = torch.full((batch, h + 1, w + 1, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    # three launches of the same plan: scratch flags of the stream-K schedule must come back clean
     G.run_conv(x_p, cin, cin, batch, h, w, ksize, wt_p, cout, npad, block_n, block_k, alpha, beta, act,
-               out, cout, OUT_BF16)
+               out, cout, OUT_BF16, repeat=3)
     got = G.from_padded_nhwc(out, cout, h, w)
     ref = _ref_conv(x, wt, alpha[:cout], beta[:cout], act, ksize)
     scale = ref.abs().max().item()
