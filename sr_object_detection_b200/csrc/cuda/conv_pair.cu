@@ -107,6 +107,9 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// TAPS = 9: 3x3 layer (halo slab, nine row-shifted descriptors per channel block);
+// TAPS = 1: 1x1 layer (the "slab" is the plain 128-position tile, one descriptor per channel block)
+template <int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const SlabParams prm)
@@ -200,7 +203,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int n0 = (seg.tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
             for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(&b_empty[stage], phase ^ 1, 2);
                     if (elect_one_sync()) {
                         if (leader) mbar_expect_tx(&b_full[stage], 2u * kPairBHalfBytes);
@@ -234,7 +237,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
                     const uint32_t acc_first = cb != seg.cb0;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(&b_full[sb_i], pb, 5);
                         tc_fence_after();
                         if (elect_one_sync()) {
@@ -246,7 +249,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                                ((uint64_t)kPairDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(k * 2)),
                                                kPairIdesc, (tap == 0 && k == 0) ? acc_first : 1u);
                             umma_commit_pair(&b_empty[sb_i]);
-                            if (tap == 8) {
+                            if (tap == TAPS - 1) {
                                 umma_commit_pair(&a_empty[sa_i]);
                                 if (cb == seg.cb1 - 1) umma_commit_pair(&tfull_bar[buf]);
                             }
@@ -388,10 +391,23 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // -------------------------------------------------------------------------------------
 int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 {
-    if (d->ksize != 3 || d->block_k != kPairBK || d->block_n != 256 || d->npad % kPairN) return Y2_EINVAL;
+    if ((d->ksize != 3 && d->ksize != 1) || d->block_k != kPairBK || d->block_n != 256 || d->npad % kPairN ||
+        d->cin % kPairBK)
+        return Y2_EINVAL;
+    const int taps = d->ksize * d->ksize;
     const int hp = d->h + 1, wp = d->w + 1;
     const long long total = (long long)d->batch * hp * wp;
-    const int halo = wp + 1;
+    // 1x1 layers: only bf16 tensors through the TMA-store epilogue, and only when there is enough work to
+    // fill the pairs (small layers stay on the single-CTA kernels, which have more CTAs to spread over)
+    if (taps == 1 && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;
+    // Measured (yolo-voc L13 / L19, batch 64): the one-tap pair kernel runs 20.9 / 21.0 us against 18.8 / 20.1
+    // of the slab kernel - these layers are bound by L2 -> shared-memory operand traffic and by their few
+    // tiles, not by the tensor pipe - so it is only used when asked for (Y2_CONV_VARIANT=pair; tests).
+    if (taps == 1) {
+        const char *forced = getenv("Y2_CONV_VARIANT");
+        if (!forced || strcmp(forced, "pair")) return Y2_EINVAL;
+    }
+    const int halo = taps == 9 ? wp + 1 : 0;
     const int slab_rows = 128 + 2 * halo;
     const int loads = (slab_rows + 255) / 256;
     int box_rows = (slab_rows + loads - 1) / loads;
@@ -400,13 +416,13 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int slab_bytes = loads * box_rows * kPairRowBytes;
     const int aux = ((2 * kPairN * 8 + 512 + 1023) / 1024) * 1024 + 8 * 4096;  // alpha/beta, barriers | store staging
     const int budget = 227 * 1024 - 1024 - aux;
-    const int stages_a = 2;
+    const int stages_a = taps == 9 ? 2 : kPairMaxStagesA;  // 1x1: a fresh A tile every K step
     int stages_b = (budget - stages_a * slab_bytes) / kPairBHalfBytes;
     if (stages_b > kPairMaxStagesB) stages_b = kPairMaxStagesB;
     if (stages_b < 4) return Y2_EINVAL;
     const int sms = sm_count();
     if (sms < 2) return Y2_EINVAL;
-    const int ktot = 9 * d->cin;
+    const int ktot = taps * d->cin;
     int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
                             (uint32_t)kPairBK, (uint32_t)box_rows, kPairBK);
     if (rc == Y2_OK)
@@ -446,6 +462,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     pl->variant = kVariantPair;
     pl->block_n = kPairN;
     pl->block_k = kPairBK;
+    pl->taps = taps;
     pl->smem_bytes = (size_t)stages_a * slab_bytes + (size_t)stages_b * kPairBHalfBytes + aux + 1024;
     const int tiles = p.tiles_m * p.tiles_n;
     const int pairs = tiles < sms / 2 ? tiles : sms / 2;
@@ -454,7 +471,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.streamk = 0;
     p.sk_partial = nullptr;
     p.sk_flags = nullptr;
-    if (tiles > pairs && p.cblocks >= 2) {
+    if (tiles > pairs && p.cblocks >= 2 && taps == 9) {  // short K loops: the parked partials would cost more than they save
         const int waves = (tiles + pairs - 1) / pairs;
         const double fill = (double)tiles / ((double)waves * pairs);
         p.streamk = fill < 0.95;
@@ -472,7 +489,8 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     int dev = 0;
     Y2_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_pair_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        Y2_CUDA_CHECK(cudaFuncSetAttribute(conv_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done[dev] = true;
     }
     return Y2_OK;
@@ -480,7 +498,10 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 
 int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
-    conv_pair_kernel<<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
+    if (pl->taps == 9)
+        conv_pair_kernel<9><<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
+    else
+        conv_pair_kernel<1><<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

@@ -60,14 +60,17 @@ CONV_CASES = [
     (64, 256, 13, 13, 512, 3, 256, 64, ACT_LEAKY),
     (64, 128, 13, 13, 1024, 3, 256, 64, ACT_LINEAR),
     (48, 192, 13, 13, 768, 3, 256, 64, ACT_LEAKY),
+    # wide 1x1 layers (yolo-voc L13, L19): slab kernel by default, one-tap pair kernel under the "pair" variant
+    (64, 512, 26, 26, 256, 1, 256, 64, ACT_LEAKY),
+    (64, 1024, 13, 13, 512, 1, 256, 64, ACT_LEAKY),
 ]
 
 
-@pytest.fixture(params=["auto", "slab", "pertap"])
+@pytest.fixture(params=["auto", "slab", "pertap", "pair"])
 def conv_variant(request, monkeypatch):
-    """All three implicit-GEMM kernels stay under test: the default choice (CTA-pair kernel for wide 3x3
-    layers), the halo-slab kernel alone and the per-tap fallback (Y2_CONV_VARIANT is read at plan
-    creation)."""
+    """All three implicit-GEMM kernels stay under test: the default choice (CTA-pair kernel for wide
+    layers), the halo-slab kernel alone, the per-tap fallback, and the pair kernel wherever its shape
+    constraints allow it, however small the layer (Y2_CONV_VARIANT is read at plan creation)."""
     if request.param == "auto":  # CTA-pair kernel where it fits, then slab, then per-tap
         monkeypatch.delenv("Y2_CONV_VARIANT", raising=False)
     else:
