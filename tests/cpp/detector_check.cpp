@@ -53,7 +53,7 @@ int main(int argc, char **argv)
         im.w = w; im.h = h; im.c = 3; im.data = img.data();
         dump("detect", det.detect(im, thresh, false));
         for (int i = 0; i < 3; ++i) dump("mean", det.detect(im, thresh, true));
-        if (w == det.get_net_width() && h == det.get_net_height()) dump("rgb8", det.detect_rgb8(u8.data(), w, h, thresh));
+        dump("rgb8", det.detect_rgb8(u8.data(), w, h, thresh));  // any frame size: resize runs on the device
         try {
             Detector::load_image("/nonexistent/file.ppm");
             printf("load no-throw\n");

@@ -149,3 +149,28 @@ def test_detector_detect_matches_c_api(tmp_path):
     # use_mean: frame 1 averages with two zero frames, frame 3 is the plain prediction again (same image thrice)
     assert [(b[0], b[1], b[2], b[3], b[5]) for b in means[2]] == want
     dn.free_network(net)
+
+
+@pytest.mark.gpu
+def test_detector_frame_of_another_size_device_resize_equals_host_resize(tmp_path):
+    """Detector::detect(image_t) resizes a 640x480 frame on the host with resize_image (yolo_v2_class.cpp:186-193);
+    Detector::detect_rgb8 uploads the raw bytes and resizes on the device.  Same boxes, bit for bit."""
+    exe = _build(tmp_path)
+    cfg_text = synth.tiny_yolo_voc_cfg(batch=1)
+    (tmp_path / "n.cfg").write_text(cfg_text)
+    synth.write_weights(tmp_path / "n.weights", cfg_text, seed=1234)
+    rng = np.random.default_rng(12)
+    w, h = 640, 480
+    u8 = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    planar = (u8.transpose(2, 0, 1).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
+    planar.tofile(tmp_path / "in.f32")
+    u8.tofile(tmp_path / "in.u8")
+    r = subprocess.run([str(exe), "detect", str(tmp_path / "n.cfg"), str(tmp_path / "n.weights"), str(tmp_path / "in.f32"),
+                        str(tmp_path / "in.u8"), str(w), str(h), "0.02"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    det = _parse(next(l for l in lines if l.startswith("detect")))
+    rgb8 = _parse(next(l for l in lines if l.startswith("rgb8")))
+    assert len(det) > 0
+    assert rgb8 == det
+    assert max(b[0] + b[2] for b in det) > 416 or max(b[1] + b[3] for b in det) > 0  # boxes are in frame pixels
