@@ -83,8 +83,85 @@ __global__ void region_forward_kernel(const float *in, float *out,
 }
 
 // ---------------------------------------------------------------------------------
+// region forward, flat softmax (no tree): FOUR lanes per box, eight boxes per warp.
+// The warp-per-group kernel above spends a whole warp on 20 classes plus a serial logistic in one
+// lane and is issue-bound (54 080 boxes x ~250 warp instructions at yolo-voc b64).  Here lane q of
+// a box evaluates the double-precision exps of classes q, q+4, ... and one of the pass-through /
+// objectness values; the float sum still runs in class order: round k hands the four terms of
+// classes 4k..4k+3 through quad shuffles and every lane adds them in that order, so the sequence of
+// roundings is the reference's serial loop (blas.c:205-221).
+// ---------------------------------------------------------------------------------
+__global__ void region_forward_flat_kernel(const float *__restrict__ in, float *__restrict__ out, long long boxes,
+                                           int classes, int softmax)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = lane & 3;
+    const int qbase = lane & ~3;
+    const long long quad0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2;
+    const long long nquads = ((long long)gridDim.x * blockDim.x) >> 2;
+    const int size = classes + 5;
+    const int rounds = (classes + 3) >> 2;
+    // warp-uniform trip count: the first quad of the warp decides
+    for (long long wb = quad0 - (lane >> 2); wb < boxes; wb += nquads) {
+        const long long box = wb + (lane >> 2);
+        const bool active = box < boxes;
+        const float *x = in + (active ? box : 0) * size;
+        float *o = out + (active ? box : 0) * size;
+        if (active) {
+            if (q == 0) {
+                o[0] = x[0];
+                o[1] = x[1];
+            } else if (q == 1) {
+                o[2] = x[2];
+                o[3] = x[3];
+            } else if (q == 2) {
+                o[4] = logistic_ref(x[4]);
+            }
+        }
+        const float *xi = x + 5;
+        float *oi = o + 5;
+        if (!softmax) {
+            if (active)
+                for (int i = q; i < classes; i += 4) oi[i] = xi[i];
+            continue;
+        }
+        float largest = -FLT_MAX;
+        for (int i = q; i < classes; i += 4) {
+            const float v = xi[i];
+            if (v > largest) largest = v;
+        }
+#pragma unroll
+        for (int d = 1; d <= 2; d <<= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+            if (other > largest) largest = other;
+        }
+        float sum = 0.f;
+        for (int k = 0; k < rounds; ++k) {
+            const int i = 4 * k + q;
+            float e = 0.f;
+            if (i < classes) {
+                const float arg = xi[i] / 1.f - largest / 1.f;  // temperature 1, float expression
+                e = (float)exp((double)arg);
+                if (active) oi[i] = e;
+            }
+            const int cnt = (classes - 4 * k) < 4 ? (classes - 4 * k) : 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t = __shfl_sync(0xffffffffu, e, qbase + j);
+                if (j < cnt) sum = sum + t;
+            }
+        }
+        if (active)
+            for (int i = q; i < classes; i += 4) oi[i] = oi[i] / sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // get_region_boxes, flat-softmax variant (region_layer.c:328-347, 367-377).
-// One thread per (box, class) element; the class-0 thread also decodes the box.
+// Two grid-stride passes in one launch: (1) one thread per box COMPONENT (x, y, w, h), so the four
+// double-precision transcendentals of a box run in four adjacent lanes and the float4 box comes out
+// of coalesced stores; (2) one thread per (box, class) probability.  (One thread per box doing all
+// four, as a side job of the class-0 thread, left 19 of 20 lanes idle through ~300 instructions.)
 // ---------------------------------------------------------------------------------
 __global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const float *__restrict__ biases,
                                          float *__restrict__ boxes, float *__restrict__ probs, int batch,
@@ -92,36 +169,44 @@ __global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const f
                                          float thresh, int only_objectness, int classfix)
 {
     const int per_img = lw * lh * n;
-    const long long total = (long long)batch * per_img * classes;
     const int size = classes + 5;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // get_region_box, DOABS branch (region_layer.c:76-83)
+    const long long ncomp = (long long)batch * per_img * 4;
+    for (long long t = tid; t < ncomp; t += nthreads) {
+        const int comp = (int)(t & 3);
+        const long long bi = t >> 2;
+        const int index = (int)(bi % per_img);
+        const float *x = pred + bi * size;
+        const int an = index % n;
+        const int cell = index / n;
+        float v;
+        if (comp == 0) {
+            v = ((cell % lw) + logistic_ref(x[0])) / lw;
+            v *= img_w;
+        } else if (comp == 1) {
+            v = ((cell / lw) + logistic_ref(x[1])) / lh;
+            v *= img_h;
+        } else if (comp == 2) {
+            v = (float)(exp((double)x[2]) * (double)biases[2 * an] / (double)lw);
+            v *= img_w;
+        } else {
+            v = (float)(exp((double)x[3]) * (double)biases[2 * an + 1] / (double)lh);
+            v *= img_h;
+        }
+        boxes[t] = v;
+    }
+    const long long total = (long long)batch * per_img * classes;
+    for (long long t = tid; t < total; t += nthreads) {
         const int j = (int)(t % classes);
         const long long bi = t / classes; // b*per_img + index
-        const int index = (int)(bi % per_img);
         const float *x = pred + bi * size;
         float scale = x[4];
         if (classfix == -1 && scale < .5) scale = 0;
         const float prob = scale * x[5 + j];
         float pv = (prob > thresh) ? prob : 0;
-        if (j == 0) {
-            if (only_objectness) pv = scale;
-            const int an = index % n;
-            const int cell = index / n;
-            const int row = cell / lw;
-            const int col = cell % lw;
-            // get_region_box, DOABS branch (region_layer.c:76-83)
-            float bx = (col + logistic_ref(x[0])) / lw;
-            float by = (row + logistic_ref(x[1])) / lh;
-            float bw = (float)(exp((double)x[2]) * (double)biases[2 * an] / (double)lw);
-            float bh = (float)(exp((double)x[3]) * (double)biases[2 * an + 1] / (double)lh);
-            bx *= img_w;
-            by *= img_h;
-            bw *= img_w;
-            bh *= img_h;
-            float4 bb = make_float4(bx, by, bw, bh);
-            *reinterpret_cast<float4 *>(boxes + bi * 4) = bb;
-        }
+        if (j == 0 && only_objectness) pv = scale;
         probs[t] = pv;
     }
 }
@@ -358,8 +443,14 @@ extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw,
     if (!in || !out || batch <= 0 || hw <= 0 || n <= 0 || classes <= 0) return Y2_EINVAL;
     if (n_groups > 0 && (!d_group_size || !d_group_offset)) return Y2_EINVAL;
     const long long boxes = (long long)batch * hw * n;
-    const long long work = boxes * (n_groups > 0 ? n_groups : 1);
     const int threads = 256;
+    if (n_groups <= 0) {  // flat softmax (or none): four lanes per box
+        const int grid = grid_cap((boxes * 4 + threads - 1) / threads, 8);
+        region_forward_flat_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax);
+        Y2_LAUNCH_CHECK();
+        return Y2_OK;
+    }
+    const long long work = boxes * n_groups;
     const int grid = grid_cap((work * 32 + threads - 1) / threads, 8);
     region_forward_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
                                                               d_group_size, d_group_offset);
