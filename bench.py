@@ -107,7 +107,7 @@ def _write_inputs(tmp: Path, batch: int):
     return cfg, weights
 
 
-def cpu_baseline(tmp: Path, iters: int = 3, warmup: int = 1) -> dict:
+def cpu_baseline(tmp: Path, iters: int = 20, warmup: int = 1) -> dict:
     """The reference's own CPU path (oracle/_ref, compiled from the reference sources) on the
     host cores, bounded sample of the same workload: batch-1 forward + decode + NMS."""
     from sr_object_detection_b200 import synth
@@ -392,6 +392,9 @@ def main() -> int:
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (yolo-voc L23, ncu --set full,
         # profiles/r1j_ncu_conv_pair_L23.txt); algorithmic operand bytes of that launch: 70 MB
         "traffic": 47.0e6 if dom == 2 else None,
+        "traffic_of": "one launch of the dominant kernel, yolo-voc L23 (1024->1024 3x3 at 13x13, b64): DRAM read+write "
+                      "from ncu --set full; the algorithmic operand bytes of that launch are 70 MB (activations stay "
+                      "in L2 between layers)",
         "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / max(float(layer_ms.sum()), 1e-9), 3),
         "all_convolutions": {"launches": conv_launches, "ms_per_step": round(conv_ms, 4),
                              "achieved": round(achieved_tf, 1), "frac": round(achieved_tf / peaks["tflops"], 4)},

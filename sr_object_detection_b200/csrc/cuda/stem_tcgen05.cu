@@ -322,10 +322,27 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
             be[q] = sm.beta[cbase + q];
         }
         int it = 0;
+        // (image, tile row, tile column) advance by a constant stride: carry-propagate instead of dividing
+        // per tile (two runtime divisions were 9 % of this issue-bound kernel's instructions)
+        int b = (int)blockIdx.x / per_img;
+        int ty = ((int)blockIdx.x - b * per_img) / p.tiles_x;
+        int tx = (int)blockIdx.x - b * per_img - ty * p.tiles_x;
+        const int db = (int)gridDim.x / per_img;
+        const int dty = ((int)gridDim.x - db * per_img) / p.tiles_x;
+        const int dtx = (int)gridDim.x - db * per_img - dty * p.tiles_x;
+        const size_t row_elems = (size_t)(p.ow + 1) * p.out_cs;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int b = tile / per_img;
-            const int t = tile - b * per_img;
-            const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            if (it) {
+                tx += dtx;
+                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+                ty += dty;
+                if (ty >= p.tiles_y) { ty -= p.tiles_y; ++b; }
+                b += db;
+            }
+            const int ox = (tx * p.wt + m) >> 1;
+            __nv_bfloat16 *obase = p.out + ((size_t)b * (p.oh + 1) + (size_t)ty * (kStemRows / 2)) * row_elems +
+                                   (size_t)ox * p.out_cs + cbase;
+            const bool col_ok = m < p.wt && ox < p.ow;
             for (int jp = 2 * sgroup; jp < pairs; jp += 4)
             for (int j = jp; j < jp + 2; ++j) {
                 const int slot = j >> 1;
@@ -355,8 +372,7 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
                     mx[q] = fmaxf(keep, got);
                 }
                 const int oy = ty * (kStemRows / 2) + j;
-                const int ox = (tx * p.wt + m) >> 1;
-                if (m < p.wt && oy < p.oh && ox < p.ow) {
+                if (col_ok && oy < p.oh) {
                     uint32_t pk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -368,8 +384,7 @@ stem_conv_pool_kernel(const __grid_constant__ CUtensorMap tm_in, const StemParam
                         }
                         pk[q] = pack_bf16x2(y0, y1);
                     }
-                    __nv_bfloat16 *o = p.out + (((size_t)b * (p.oh + 1) + oy) * (p.ow + 1) + ox) * p.out_cs + cbase;
-                    *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(obase + (size_t)j * row_elems) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
         }
