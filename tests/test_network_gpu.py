@@ -33,7 +33,9 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
 @pytest.mark.parametrize("name,batch,side", [("tiny-yolo-voc", 2, 416), ("yolo-voc", 2, 416), ("yolo", 1, 608),
                                              ("darknet19_448", 1, 448), ("yolo-voc", 3, 320),
                                              ("resnet50", 2, 256), ("resnet50", 1, 224),
-                                             ("yolo9000", 1, 544)])
+                                             ("yolo9000", 1, 544),
+                                             # non-square and odd extents: 15x11 and 13x9 cells, 2/1 pool on an odd row count
+                                             ("tiny-yolo-voc", 2, (480, 352)), ("yolo-voc", 1, (416, 288))])
 def test_layer_activations_match_reference(tmp_path, name, batch, side):
     """BASELINE.json configs 1-5 (at a batch the CPU reference finishes in seconds): every layer of
     the B200 forward pass against the reference's CPU forward on the same weights and images."""
@@ -43,7 +45,8 @@ def test_layer_activations_match_reference(tmp_path, name, batch, side):
     if name == "yolo9000":  # config 4: 9418-way WordTree softmax (cfg/9k.tree of the reference is corrupt)
         synth.write_tree(tmp_path / "9k.tree")
         kw["tree"] = str(tmp_path / "9k.tree")
-    cfg, weights, x, inp = _setup(tmp_path, name, batch, w=side, h=side, **kw)
+    w, h = side if isinstance(side, tuple) else (side, side)
+    cfg, weights, x, inp = _setup(tmp_path, name, batch, w=w, h=h, **kw)
     ref_dir = tmp_path / "ref"
     R.forward(R.REF_BIN, cfg, weights, inp, ref_dir, thresh=0.24, nms=0.4)
 
