@@ -268,3 +268,41 @@ def test_frames_of_any_size_equal_host_resize_then_float_detect(tmp_path):
         for b in range(batch):
             assert arr[b * max_det:b * max_det + min(counts[b], max_det)].tobytes() == ref[b]
     dn.free_network(net)
+
+
+def test_set_batch_and_resize_replan_the_device_side(tmp_path):
+    """set_batch_network (network.c:308-320) down and UP (the device plan is rebuilt when the batch grows) and
+    resize_network (network.c:322-388): every image's output must be what a network parsed directly at that
+    batch / resolution produces - exactly, the kernels' accumulation order per output does not depend on either."""
+    cfg4, weights, x6, _ = _setup(tmp_path, "tiny-yolo-voc", 6)
+    cfg_text = synth.CFGS["tiny-yolo-voc"](batch=4, w=416, h=416)
+    (tmp_path / "b4.cfg").write_text(cfg_text)
+    dn.set_gpu_index(0)
+    net = dn.parse_network_cfg(tmp_path / "b4.cfg")
+    dn.load_weights(net, weights)
+    full = dn.network_predict(net, np.ascontiguousarray(x6[:4]))
+    dn.set_batch_network(net, 2)
+    assert net.batch == 2
+    assert np.array_equal(dn.network_predict(net, np.ascontiguousarray(x6[:2])), full[:2])
+    dn.set_batch_network(net, 6)  # beyond the cfg batch: buffers and plans are rebuilt
+    assert net.batch == 6
+    out6 = dn.network_predict(net, x6)
+    assert np.array_equal(out6[:4], full)
+    dets, _ = dn.network_detect_batch(net, x6, 0.02, 0.4, 256)
+    assert len(dets) == 6 and any(len(d) for d in dets)
+    # resize 416 -> 320 and compare with a network parsed at 320
+    assert dn.resize_network(net, 320, 320) == 0
+    assert (net.w, net.h) == (320, 320)
+    x320 = synth.images(6, 3, 320, 320, seed=77)
+    got = dn.network_predict(net, x320)
+    (tmp_path / "s320.cfg").write_text(synth.CFGS["tiny-yolo-voc"](batch=6, w=320, h=320))
+    ref_net = dn.parse_network_cfg(tmp_path / "s320.cfg")
+    dn.load_weights(ref_net, weights)
+    want = dn.network_predict(ref_net, x320)
+    assert got.shape == want.shape == (6, 10 * 10 * 125)
+    assert np.array_equal(got, want)
+    # two networks alive in one process: interleaved calls do not disturb each other
+    again = dn.network_predict(net, x320)
+    assert np.array_equal(again, got)
+    dn.free_network(ref_net)
+    dn.free_network(net)
