@@ -299,6 +299,11 @@ typedef struct { int h, w, c; float *data; } image;
 image make_image(int w, int h, int c);                             /* image.c:1436-1441 */
 void free_image(image m);
 image resize_image(image im, int w, int h);                        /* image.c:1950-1993 */
+/* classifier front end (classifier.c:676-730 predict_classifier) */
+void fill_image(image m, float s);                                 /* image.c:1601-1605 */
+void embed_image(image source, image dest, int dx, int dy);        /* image.c:1087-1098 */
+image letterbox_image(image im, int w, int h);                     /* image.c:1624-1644 */
+void top_k(float *a, int n, int k, int *index);                    /* utils.c:179-193 */
 
 /* =========================================================================================
  * B200 extensions (not in the reference): batched, device-resident detection.

@@ -184,6 +184,35 @@ static int cmd_resize(int argc, char **argv)
     return 0;
 }
 
+/* letterbox <in.f32> <c> <h> <w> <out_h> <out_w> <out.f32> : the reference's letterbox_image */
+static int cmd_letterbox(int argc, char **argv)
+{
+    if (argc < 9) return 1;
+    int c = atoi(argv[3]), h = atoi(argv[4]), w = atoi(argv[5]), oh = atoi(argv[6]), ow = atoi(argv[7]);
+    image im;
+    im.c = c; im.h = h; im.w = w;
+    im.data = read_f32(argv[2], (size_t)c * h * w);
+    image r = letterbox_image(im, ow, oh);
+    FILE *f = fopen(argv[8], "wb");
+    fwrite(r.data, sizeof(float), (size_t)c * oh * ow, f);
+    fclose(f);
+    return 0;
+}
+
+/* topk <in.f32> <n> <k> : the reference's top_k, indices printed as a JSON list */
+static int cmd_topk(int argc, char **argv)
+{
+    if (argc < 5) return 1;
+    int n = atoi(argv[3]), k = atoi(argv[4]), j;
+    float *a = read_f32(argv[2], (size_t)n);
+    int *index = (int *)calloc(k, sizeof(int));
+    top_k(a, n, k, index);
+    printf("[");
+    for (j = 0; j < k; ++j) printf("%s%d", j ? ", " : "", index[j]);
+    printf("]\n");
+    return 0;
+}
+
 static int cmd_layers(int argc, char **argv)
 {
     if (argc < 3) return 1;
@@ -210,6 +239,8 @@ int main(int argc, char **argv)
     if (!strcmp(argv[1], "time")) return cmd_time(argc, argv);
     if (!strcmp(argv[1], "resize")) return cmd_resize(argc, argv);
     if (!strcmp(argv[1], "layers")) return cmd_layers(argc, argv);
+    if (!strcmp(argv[1], "letterbox")) return cmd_letterbox(argc, argv);
+    if (!strcmp(argv[1], "topk")) return cmd_topk(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 1;
 }

@@ -497,3 +497,67 @@ image resize_image(image im, int w, int h)
     free_image(part);
     return resized;
 }
+
+/* ---- classifier front end (classifier.c:676-730 predict_classifier): letterbox + top-k ---------------- */
+
+/* image.c:1601-1605 */
+void fill_image(image m, float s)
+{
+    const size_t n = (size_t)m.h * m.w * m.c;
+    for (size_t i = 0; i < n; ++i) m.data[i] = s;
+}
+
+/* image.c:1087-1098: paste `source` into `dest` with its top-left corner at (dx, dy); pixels that fall
+ * outside dest are dropped (the reference asserts) */
+void embed_image(image source, image dest, int dx, int dy)
+{
+    for (int k = 0; k < source.c && k < dest.c; ++k)
+        for (int y = 0; y < source.h; ++y) {
+            const int ty = dy + y;
+            if (ty < 0 || ty >= dest.h) continue;
+            for (int x = 0; x < source.w; ++x) {
+                const int tx = dx + x;
+                if (tx < 0 || tx >= dest.w) continue;
+                dest.data[((size_t)k * dest.h + ty) * dest.w + tx] = px(source, x, y, k);
+            }
+        }
+}
+
+/* image.c:1624-1644: scale to fit inside w x h keeping the aspect ratio (integer arithmetic of the
+ * reference: the side that limits gets the target extent, the other im.h*w/im.w resp. im.w*h/im.h),
+ * centre on a 0.5-grey canvas */
+image letterbox_image(image im, int w, int h)
+{
+    int new_w, new_h;
+    if (((float)w / im.w) < ((float)h / im.h)) {
+        new_w = w;
+        new_h = (im.h * w) / im.w;
+    } else {
+        new_h = h;
+        new_w = (im.w * h) / im.h;
+    }
+    image resized = resize_image(im, new_w, new_h);
+    image boxed = make_image(w, h, im.c);
+    fill_image(boxed, .5f);
+    embed_image(resized, boxed, (w - new_w) / 2, (h - new_h) / 2);
+    free_image(resized);
+    return boxed;
+}
+
+/* utils.c:179-193: indices of the k largest entries, descending; among equal values the one met first
+ * stays ahead (the comparison that displaces an entry is a strict >) */
+void top_k(float *a, int n, int k, int *index)
+{
+    for (int j = 0; j < k; ++j) index[j] = -1;
+    for (int i = 0; i < n; ++i) {
+        int curr = i;
+        for (int j = 0; j < k; ++j) {
+            if (index[j] < 0 || a[curr] > a[index[j]]) {
+                const int displaced = index[j];
+                index[j] = curr;
+                curr = displaced;
+            }
+            if (curr < 0) break; /* nothing left to push down */
+        }
+    }
+}

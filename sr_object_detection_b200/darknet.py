@@ -165,6 +165,10 @@ def lib() -> C.CDLL:
         "network_input_staging": (fp, [Network]),
         "resize_image": (Image, [Image, i, i]),
         "free_image": (None, [Image]),
+        "letterbox_image": (Image, [Image, i, i]),
+        "embed_image": (None, [Image, Image, i, i]),
+        "fill_image": (None, [Image, f]),
+        "top_k": (None, [fp, i, i, _ip]),
         "read_tree": (C.POINTER(Tree), [C.c_char_p]),
         "max_index": (i, [fp, i]),
         "fill_cpu": (None, [i, f, fp, i]),

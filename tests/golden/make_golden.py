@@ -172,8 +172,34 @@ def main():
         im.tofile(t / "im.f32")
         subprocess.run([str(REF), "resize", "im.f32", "3", "20", "30", "13", "17", "out.f32"], cwd=t, check=True)
         np.savez_compressed(OUT / "resize.npz", image=im, resized=f32(t / "out.f32").reshape(3, 13, 17))
-    # 4. parser tables, incl. the reference's own cfg files
+    # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
+    classifier_front()
+    # 5. parser tables, incl. the reference's own cfg files
     parser_tables()
+
+
+def classifier_front():
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        rng = np.random.default_rng(8)
+        out = {}
+        for tag, (h, w, oh, ow) in {"wide": (20, 30, 32, 32), "tall": (31, 17, 24, 40), "same": (16, 16, 16, 16)}.items():
+            im = rng.random((3, h, w), dtype=np.float32)
+            im.tofile(t / "im.f32")
+            subprocess.run([str(REF), "letterbox"] + [str(v) for v in ("im.f32", 3, h, w, oh, ow, "out.f32")],
+                           cwd=t, check=True)
+            out[f"{tag}_image"] = im
+            out[f"{tag}_boxed"] = f32(t / "out.f32").reshape(3, oh, ow)
+        # top_k incl. exact ties and k > number of distinct values
+        a = rng.random(50, dtype=np.float32)
+        a[[3, 17, 29]] = 0.75
+        a[[5, 6]] = a.max() + 1
+        a.tofile(t / "a.f32")
+        for k in (1, 5, 12):
+            r = subprocess.run([str(REF), "topk", "a.f32", "50", str(k)], cwd=t, check=True, capture_output=True, text=True)
+            out[f"topk_{k}"] = np.array(json.loads(r.stdout.strip().splitlines()[-1]), dtype=np.int32)
+        out["topk_input"] = a
+        np.savez_compressed(OUT / "classifier_front.npz", **out)
 
 
 if __name__ == "__main__":

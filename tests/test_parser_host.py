@@ -273,3 +273,25 @@ def test_cuda_gridsize(n, want):
     d = dn.lib().cuda_gridsize(n)
     assert (d.x, d.y, d.z) == want
     assert d.x * d.y * 512 >= n
+
+
+def test_classifier_front_end_matches_reference_golden():
+    """letterbox_image (image.c:1624-1644) and top_k (utils.c:179-193) against outputs of the compiled
+    reference (tests/golden/classifier_front.npz, written by tests/golden/make_golden.py).  Bit-exact."""
+    lib = dn.lib()
+    d = np.load(GOLDEN / "classifier_front.npz")
+    for tag in ("wide", "tall", "same"):
+        im = np.ascontiguousarray(d[f"{tag}_image"])
+        want = d[f"{tag}_boxed"]
+        c, h, w = im.shape
+        _, oh, ow = want.shape
+        out = lib.letterbox_image(dn.Image(h, w, c, _fp(im)), ow, oh)
+        assert (out.h, out.w, out.c) == (oh, ow, c)
+        got = np.ctypeslib.as_array(out.data, shape=(c, oh, ow)).copy()
+        lib.free_image(out)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), tag
+    a = np.ascontiguousarray(d["topk_input"])
+    for k in (1, 5, 12):
+        idx = (C.c_int * k)()
+        lib.top_k(_fp(a), a.size, k, idx)
+        assert list(idx) == d[f"topk_{k}"].tolist()
