@@ -129,7 +129,21 @@ def mini_resnet_cfg(batch=2, w=32, h=32):
     return s + "[avgpool]\n\n[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
 
 
+def mini_dense_cfg(batch=2, w=64, h=64, classes=4, num=3):
+    """Toy DenseNet-style detector: every block's 3x3 output (growth 32) is concatenated with the running
+    feature map by a two-input route whose second input is itself a route (densenet201.cfg's pattern), so
+    the in-place concat has to fall back to a copy for the nested input."""
+    s = _net(batch, w, h) + _conv(32, 3) + _maxpool()                                   # 0-1
+    s += _conv(64, 1) + _conv(32, 3) + "[route]\nlayers=-1,-3\n\n"                      # 2-4: 32 + 32
+    s += _conv(64, 1) + _conv(32, 3) + "[route]\nlayers=-1,-3\n\n"                      # 5-7: 32 + 64
+    s += _conv(64, 1) + _conv(32, 3) + "[route]\nlayers=-1,-3\n\n"                      # 8-10: 32 + 96
+    s += _maxpool() + _conv(64, 3) + _conv(num * (classes + 5), 1, bn=0, act="linear")  # 11-13
+    anchors = ",".join(f"{0.6 + 0.7 * i:.2f},{0.8 + 0.5 * i:.2f}" for i in range(num))
+    return s + _region(anchors, classes, num)
+
+
 CFGS = {
+    "mini-dense": mini_dense_cfg,
     "mini-yolo": mini_yolo_cfg,
     "mini-resnet": mini_resnet_cfg,
     "tiny-yolo-voc": tiny_yolo_voc_cfg,

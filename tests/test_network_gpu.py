@@ -35,7 +35,9 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
                                              ("resnet50", 2, 256), ("resnet50", 1, 224),
                                              ("yolo9000", 1, 544),
                                              # non-square and odd extents: 15x11 and 13x9 cells, 2/1 pool on an odd row count
-                                             ("tiny-yolo-voc", 2, (480, 352)), ("yolo-voc", 1, (416, 288))])
+                                             ("tiny-yolo-voc", 2, (480, 352)), ("yolo-voc", 1, (416, 288)),
+                                             # nested routes (a route that concatenates another route's output)
+                                             ("mini-dense", 3, 64)])
 def test_layer_activations_match_reference(tmp_path, name, batch, side):
     """BASELINE.json configs 1-5 (at a batch the CPU reference finishes in seconds): every layer of
     the B200 forward pass against the reference's CPU forward on the same weights and images."""
