@@ -217,11 +217,31 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int m = quarter * 32 + lane;   // TMEM lane == position inside the tile row
         const int hsel = lane & 1;           // even lane finishes 8 of those channels, odd lane the other 8
         const int cbase = chalf * 16 + hsel * 8;
+        // 64-filter layers: this thread's 16 (alpha, beta) pairs live in registers, so the epilogue leaves
+        // the shared-memory pipe to the tensor core's operand reads (ncu on L2: LSU 12 % + tensor 70 % of it)
+        constexpr bool kAbRegs = BLOCK_N == 64;
+        float4 abr[kAbRegs ? 8 : 1];
+        if (kAbRegs) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                abr[q] = reinterpret_cast<const float4 *>(s_ab + (q >> 2) * 32 + cbase)[q & 3];
+        }
         int it = 0;
+        // (image, tile row, tile column) advance by a constant stride: carry-propagate instead of dividing
+        int b = (int)blockIdx.x / per_img;
+        int ty = ((int)blockIdx.x - b * per_img) / prm.tiles_x;
+        int tx = (int)blockIdx.x - b * per_img - ty * prm.tiles_x;
+        const int db = (int)gridDim.x / per_img;
+        const int dty = ((int)gridDim.x - db * per_img) / prm.tiles_x;
+        const int dtx = (int)gridDim.x - db * per_img - dty * prm.tiles_x;
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
-            const int b = tile / per_img;
-            const int t = tile - b * per_img;
-            const int ty = t / prm.tiles_x, tx = t - ty * prm.tiles_x;
+            if (it) {
+                tx += dtx;
+                if (tx >= prm.tiles_x) { tx -= prm.tiles_x; ++ty; }
+                ty += dty;
+                if (ty >= prm.tiles_y) { ty -= prm.tiles_y; ++b; }
+                b += db;
+            }
             for (int j = pgroup; j < pairs; j += 2) {
                 const int slot_it = it * pairs + j;
                 const int slot = slot_it % Cfg::kSlots;
@@ -233,7 +253,7 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 __nv_bfloat16 *o = prm.out + (((size_t)b * (prm.oh + 1) + oy) * (prm.ow + 1) + ox) * prm.out_cs + cbase;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                        (uint32_t)(slot * Cfg::kSlotCols + chalf * 16);
-#pragma unroll 1
+#pragma unroll(kAbRegs ? 2 : 1)
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                     uint32_t v[16], u[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
@@ -258,7 +278,7 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 ab = ab4[q];  // (alpha, beta) of two filters
+                            const float4 ab = kAbRegs ? abr[(c0 >> 5) * 4 + q] : ab4[q];  // (alpha, beta) of two filters
                             float y0 = fmaf(mx[2 * q], ab.x, ab.y);
                             float y1 = fmaf(mx[2 * q + 1], ab.z, ab.w);
                             if (prm.act == Y2_ACT_LEAKY) {
