@@ -105,11 +105,16 @@ typedef struct y2_conv_desc {
     void *out;        /* already offset to the first output channel */
     int out_cs;       /* channel stride of `out` (elements) */
     int out_mode;     /* Y2_OUT_* */
+    int in_order;     /* how the producer of `in` walked it: 0 = first position to last (or unknown), 1 = last to
+                       * first.  A plan over a tensor near / above the L2 capacity walks it the other way round so
+                       * that it starts with the part that is still L2-resident (y2_conv_plan_order tells which). */
 } y2_conv_desc;
 
 typedef struct y2_conv_plan y2_conv_plan; /* tensor maps + launch geometry */
 
 int y2_conv_plan_create(const y2_conv_desc *d, y2_conv_plan **plan);
+/* 0: the plan visits (and writes) positions first to last, 1: last to first */
+int y2_conv_plan_order(const y2_conv_plan *plan);
 int y2_conv_plan_launch(const y2_conv_plan *plan, y2_stream_t s);
 void y2_conv_plan_destroy(y2_conv_plan *plan);
 /* algorithmic flops of one launch: 2*cout*ksize^2*cin_real*B*H*W is the caller's

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ("wt", C.c_void_p), ("cout", C.c_int), ("npad", C.c_int),
         ("block_n", C.c_int), ("block_k", C.c_int),
         ("alpha", C.c_void_p), ("beta", C.c_void_p), ("act", C.c_int),
-        ("out", C.c_void_p), ("out_cs", C.c_int), ("out_mode", C.c_int),
+        ("out", C.c_void_p), ("out_cs", C.c_int), ("out_mode", C.c_int), ("in_order", C.c_int),
     ]
 
 
@@ -93,6 +93,7 @@ def _declare(lib: C.CDLL) -> None:
         "y2_conv_plan_destroy": (None, [vp]),
         "y2_conv_plan_tiles": (i, [vp]),
         "y2_conv_plan_variant": (i, [vp]),
+        "y2_conv_plan_order": (i, [vp]),
         "y2_stem_prepare": (i, []),
         "y2_stem_conv_pool": (i, [vp, i, i, i, i, vp, i, vp, vp, i, vp, i, vp]),
         "y2_stem_conv_pool_u8": (i, [vp, i, i, i, vp, i, vp, vp, i, vp, i, vp]),

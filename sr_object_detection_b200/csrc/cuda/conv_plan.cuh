@@ -41,6 +41,7 @@ struct SlabParams {
     int cout, act, out_mode, out_cs;
     int tma_store;         // bf16 output leaves through per-warp TMA stores (else direct 16-byte stores)
     int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
+    int reverse;           // slab kernel: walk the position tiles last-to-first (see slab_plan_init)
     int streamk;           // pair kernel: K-split work distribution (conv_pair.cu), else whole tiles round-robin
     float *sk_partial;     // [pairs][256 filters][256 positions] fp32 partial accumulators of split tiles
     int *sk_flags;         // [pairs][16 epilogue warps] "partial written" flags, zero between launches
@@ -63,6 +64,7 @@ struct PoolParams {
     const float *beta;
     __nv_bfloat16 *out;    // pooled padded NHWC [B][oh+1][ow+1][out_cs]
     int out_cs;
+    int reverse;           // walk the tiles last-to-first (input near / above the L2 capacity, see conv_slab.cu)
 };
 
 enum { kVariantPerTap = 0, kVariantSlab = 1, kVariantPair = 2, kVariantPool = 3 };

@@ -124,8 +124,9 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            const int b = tile / per_img;
-            const int t = tile - b * per_img;
+            const int vt = prm.reverse ? prm.total_tiles - 1 - tile : tile;
+            const int b = vt / per_img;
+            const int t = vt - b * per_img;
             const int ty = t / prm.tiles_x, tx = t - ty * prm.tiles_x;
             mbar_wait(&a_empty[s], ph ^ 1, 1);
             if (elect_one_sync()) {
@@ -228,19 +229,26 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         int it = 0;
         // (image, tile row, tile column) advance by a constant stride: carry-propagate instead of dividing
-        int b = (int)blockIdx.x / per_img;
-        int ty = ((int)blockIdx.x - b * per_img) / prm.tiles_x;
-        int tx = (int)blockIdx.x - b * per_img - ty * prm.tiles_x;
+        const int vt0 = prm.reverse ? prm.total_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+        int b = vt0 / per_img;
+        int ty = (vt0 - b * per_img) / prm.tiles_x;
+        int tx = vt0 - b * per_img - ty * prm.tiles_x;
         const int db = (int)gridDim.x / per_img;
         const int dty = ((int)gridDim.x - db * per_img) / prm.tiles_x;
         const int dtx = (int)gridDim.x - db * per_img - dty * prm.tiles_x;
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
-            if (it) {
+            if (it && !prm.reverse) {
                 tx += dtx;
                 if (tx >= prm.tiles_x) { tx -= prm.tiles_x; ++ty; }
                 ty += dty;
                 if (ty >= prm.tiles_y) { ty -= prm.tiles_y; ++b; }
                 b += db;
+            } else if (it) {
+                tx -= dtx;
+                if (tx < 0) { tx += prm.tiles_x; --ty; }
+                ty -= dty;
+                if (ty < 0) { ty += prm.tiles_y; --b; }
+                b -= db;
             }
             for (int j = pgroup; j < pairs; j += 2) {
                 const int slot_it = it * pairs + j;
@@ -410,6 +418,9 @@ int pool_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.beta = d->beta;
     p.out = (__nv_bfloat16 *)d->out;
     p.out_cs = d->out_cs;
+    // start with the part of a large input that is still in the L2 (see conv_slab.cu, `reverse`)
+    p.reverse = (double)d->batch * (d->h + 1) * (d->w + 1) * d->in_cs * 2.0 > 64e6 && !d->in_order;
+    if (const char *e = getenv("Y2_SLAB_REVERSE")) p.reverse = atoi(e) != 0;
     pl->variant = kVariantPool;
     pl->block_n = bn;
     pl->block_k = bk;

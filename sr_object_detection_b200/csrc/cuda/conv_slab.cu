@@ -131,7 +131,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * Cfg::kRowBytes;
         const uint32_t load_bytes = (uint32_t)prm.box_rows * Cfg::kRowBytes;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / prm.tiles_n;
+            const int mq = tile / prm.tiles_n;
+            const int m_tile = prm.reverse ? prm.tiles_m - 1 - mq : mq;
             const int row0 = m_tile * kTileM - prm.halo;
             for (int cb = 0; cb < cblocks; ++cb) {
                 mbar_wait(&a_empty[stage], phase ^ 1, 1);
@@ -151,8 +152,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / prm.tiles_n;
-            const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
+            const int mq = tile / prm.tiles_n;
+            const int m_tile = prm.reverse ? prm.tiles_m - 1 - mq : mq;
+            const int n0 = (tile - mq * prm.tiles_n) * BLOCK_N;
             for (int cb = 0; cb < cblocks; ++cb) {
 #pragma unroll 1
                 for (int g = 0; g < TAPS / TPS; ++g) {
@@ -246,8 +248,9 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
-            const int m_tile = tile / prm.tiles_n;
-            const int n0 = (tile - m_tile * prm.tiles_n) * BLOCK_N;
+            const int mq = tile / prm.tiles_n;
+            const int m_tile = prm.reverse ? prm.tiles_m - 1 - mq : mq;
+            const int n0 = (tile - mq * prm.tiles_n) * BLOCK_N;
             const float2 *sab = s_ab + (prm.tiles_n > 1 ? buf * BLOCK_N : 0);
             // one filter block per layer: (alpha, beta) never change and the epilogue warps stay decoupled
             const bool reload = prm.tiles_n > 1 || it == 0 || prm.couple;
@@ -437,6 +440,15 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // measured on B200: lock-stepped epilogue warps write 128-byte rows (<= 64 filters) 10% faster, wider
     // rows prefer free-running warps
     p.couple = bn <= 64;
+    // A layer reads what the layer before it has just written, first position first.  When that tensor is
+    // about as large as the 126 MB L2 (or larger: yolo-voc L5 at batch 64 reads 180 MB), only its most
+    // recently written end is still resident - so walk the position tiles last-to-first and take that part
+    // from the L2.  Measured at batch 64 (A/B of the whole step, same box): L9 (92 MB in) 34 -> 31 us, the
+    // step -1.0 %; layers with <= 48 MB inputs are all-L2 either way (L13: 25 -> 27 us reversed), hence the
+    // threshold.
+    // The producer may itself have walked last-to-first (in_order 1): then the resident end is the front.
+    p.reverse = (double)d->batch * hp * wp * d->in_cs * 2.0 > 64e6 && !d->in_order;
+    if (const char *e = getenv("Y2_SLAB_REVERSE")) p.reverse = atoi(e) != 0;
     pl->variant = kVariantSlab;
     pl->block_n = bn;
     pl->block_k = bk;

@@ -468,6 +468,14 @@ extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl)
     delete pl;
 }
 
+extern "C" int y2_conv_plan_order(const y2_conv_plan *pl)
+{
+    if (!pl) return 0;
+    if (pl->variant == y2::kVariantSlab) return pl->slab.reverse;
+    if (pl->variant == y2::kVariantPool) return pl->pool.reverse;
+    return 0;
+}
+
 extern "C" int y2_conv_plan_variant(const y2_conv_plan *pl)
 {
     return pl ? pl->variant : -1;

@@ -49,6 +49,7 @@ typedef struct y2_layer_rt {
     void *packed_in;
     /* reorg */
     int *reorg_table;   /* gather table of the layer (y2_reorg_table) */
+    int write_order;    /* 1: this layer's kernel wrote its output last position first (y2_conv_plan_order) */
     float *stream_f32;  /* shortcut layers: fp32 copy of the output [B][H+1][W+1][cpad] (residual stream) */
     /* region */
     float *boxes_dev, *probs_dev;

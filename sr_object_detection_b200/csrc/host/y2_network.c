@@ -642,6 +642,12 @@ static void build_conv_plan(network *net, int i, int batch)
         d.in_cs = v.cs;
         d.cin = r->cin_pad;
         d.ksize = l->size;
+        /* order in which the producer's kernel wrote this tensor (a fused maxpool was written by its conv) */
+        int src = i - 1;
+        if (src >= 1 && net->layers[src].type == MAXPOOL && ((y2_layer_rt *)net->layers[src].b200)->fused_into_prev)
+            --src;
+        if (src >= 0 && net->layers[src].type == CONVOLUTIONAL)
+            d.in_order = ((y2_layer_rt *)net->layers[src].b200)->write_order;
     }
     d.batch = batch;
     d.h = l->out_h;
@@ -669,6 +675,7 @@ static void build_conv_plan(network *net, int i, int batch)
         d.cout = r->cpad;
     }
     Y2_CHECK(y2_conv_plan_create(&d, &r->plan));
+    r->write_order = y2_conv_plan_order(r->plan);
 }
 
 static void build_plans(network *net, int batch)
