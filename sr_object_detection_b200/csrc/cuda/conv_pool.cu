@@ -250,7 +250,12 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (ty < 0) { ty += prm.tiles_y; --b; }
                 b -= db;
             }
-            for (int j = pgroup; j < pairs; j += 2) {
+            // A pair group owns the TMEM slots of its parity for the whole kernel (kSlots is even, so the slot
+            // parity is the parity of the running row-pair count): every phase of a slot's barriers is seen
+            // by the same 256 threads.  Splitting by j instead lets a group return to a slot whose previous
+            // phase - drained by the other group - it never waited for, and a parity wait then passes one
+            // phase early (row-pair counts per patch that are odd; hung tiny-yolo-voc at batch 64).
+            for (int j = (it * pairs + pgroup) & 1; j < pairs; j += 2) {
                 const int slot_it = it * pairs + j;
                 const int slot = slot_it % Cfg::kSlots;
                 mbar_wait_relaxed(&tfull_bar[slot], (uint32_t)(slot_it / Cfg::kSlots) & 1u, 6);

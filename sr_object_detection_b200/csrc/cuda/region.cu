@@ -10,6 +10,7 @@
 #include "y2_common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace y2 {
 
@@ -79,6 +80,102 @@ __global__ void region_forward_kernel(const float *in, float *out,
             for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
         }
         for (int i = lane; i < n; i += 32) oi[i] = oi[i] / sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// region forward, WordTree softmax (softmax_tree, softmax_layer.c:35-47): one LANE per (box, group).
+// The groups of a WordTree are small (9k.tree: 1723 groups, median 3, 99th percentile 28 classes), so a
+// warp per group (region_forward_kernel above) wastes 29 of 32 lanes on 26 million warp tasks at
+// yolo9000 batch 16 (8 ms).  Here every lane runs the reference's three serial loops over its own
+// group; the few groups wider than a warp are then finished by the whole warp, lanes over classes, the
+// float sum still accumulated in class order.
+// ---------------------------------------------------------------------------------
+__global__ void region_forward_tree_kernel(const float *__restrict__ in, float *__restrict__ out, long long boxes,
+                                           int classes, int softmax, int n_groups,
+                                           const int *__restrict__ group_size, const int *__restrict__ group_offset)
+{
+    const int lane = threadIdx.x & 31;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const int size = classes + 5;
+    const long long work = boxes * n_groups;
+    for (long long wb = t0 - lane; wb < work; wb += nthreads) {  // warp-uniform trip count
+        const long long t = wb + lane;
+        const bool active = t < work;
+        const long long box = active ? t / n_groups : 0;
+        const int g = active ? (int)(t - box * n_groups) : 0;
+        const int off = group_offset[g];
+        const int n = active ? group_size[g] : 0;
+        const float *x = in + box * size;
+        float *o = out + box * size;
+        if (active && g == 0) {
+            o[0] = x[0];
+            o[1] = x[1];
+            o[2] = x[2];
+            o[3] = x[3];
+            o[4] = logistic_ref(x[4]);
+        }
+        const float *xi = x + 5 + off;
+        float *oi = o + 5 + off;
+        const bool wide = n > 32;
+        if (!wide) {
+            if (!softmax) {
+                for (int i = 0; i < n; ++i) oi[i] = xi[i];
+            } else {
+                float largest = -FLT_MAX;
+                for (int i = 0; i < n; ++i) {
+                    const float v = xi[i];
+                    if (v > largest) largest = v;
+                }
+                float sum = 0.f;
+                for (int i = 0; i < n; ++i) {
+                    const float arg = xi[i] / 1.f - largest / 1.f;  // temperature 1, float expression
+                    const float e = (float)exp((double)arg);
+                    sum = sum + e;
+                    oi[i] = e;
+                }
+                for (int i = 0; i < n; ++i) oi[i] = oi[i] / sum;
+            }
+        }
+        // groups wider than a warp: all lanes, one such group at a time
+        unsigned todo = __ballot_sync(0xffffffffu, wide);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long wbox = __shfl_sync(0xffffffffu, box, src);
+            const int woff = __shfl_sync(0xffffffffu, off, src);
+            const int wn = __shfl_sync(0xffffffffu, n, src);
+            const float *wx = in + wbox * size + 5 + woff;
+            float *wo = out + wbox * size + 5 + woff;
+            if (!softmax) {
+                for (int i = lane; i < wn; i += 32) wo[i] = wx[i];
+                continue;
+            }
+            float largest = -FLT_MAX;
+            for (int i = lane; i < wn; i += 32) {
+                const float v = wx[i];
+                if (v > largest) largest = v;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+                if (other > largest) largest = other;
+            }
+            float sum = 0.f;
+            for (int base = 0; base < wn; base += 32) {
+                const int i = base + lane;
+                float e = 0.f;
+                if (i < wn) {
+                    const float arg = wx[i] / 1.f - largest / 1.f;
+                    e = (float)exp((double)arg);
+                    wo[i] = e;
+                }
+                const int cnt = (wn - base) < 32 ? (wn - base) : 32;
+                for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
+            }
+            for (int i = lane; i < wn; i += 32) wo[i] = wo[i] / sum;
+        }
     }
 }
 
@@ -451,6 +548,13 @@ extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw,
         return Y2_OK;
     }
     const long long work = boxes * n_groups;
+    if (!getenv("Y2_REGION_WARP_PER_GROUP")) {
+        const int grid = grid_cap((work + threads - 1) / threads, 8);
+        region_forward_tree_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
+                                                                       d_group_size, d_group_offset);
+        Y2_LAUNCH_CHECK();
+        return Y2_OK;
+    }
     const int grid = grid_cap((work * 32 + threads - 1) / threads, 8);
     region_forward_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
                                                               d_group_size, d_group_offset);

@@ -96,7 +96,7 @@ def tree_text(n, fanout, roots):
         return Path(f.name).read_text()
 
 
-def tree_region_inputs(batch, n, classes, side, fanout, roots, seed):
+def tree_region_inputs(batch, n, classes, side, fanout, roots, seed, shared_path=False):
     """Region inputs for a softmax tree: on hot cells boost one root-to-leaf path so that the
     hierarchical product exceeds .5 somewhere below the root."""
     rng = np.random.default_rng(seed)
@@ -105,9 +105,11 @@ def tree_region_inputs(batch, n, classes, side, fanout, roots, seed):
     x[:, :, 2:4] *= 0.25
     hot = rng.random((batch, side, side)) < 0.2
     bi, hi, wi = np.nonzero(hot)
+    # shared_path: hot cells pick among four leaves only, so overlapping boxes of neighbouring cells meet in the NMS
+    cell_node = rng.choice(rng.integers(roots + fanout * roots, classes, 4), len(bi)) if shared_path else None
     for a in range(n):
         x[bi, a, 4, hi, wi] += 6.0
-        node = rng.integers(roots + fanout * roots, classes, len(bi))
+        node = cell_node.copy() if shared_path else rng.integers(roots + fanout * roots, classes, len(bi))
         for _ in range(8):
             x[bi, a, 5 + node, hi, wi] += 9.0
             parent = np.where(node < roots, node, (node - roots) // fanout)
@@ -160,6 +162,12 @@ def main():
     xt = tree_region_inputs(2, 3, 220, 5, 5, 4, seed=14)
     region_case("region_tree_220", region_only_cfg(2, 5, 3, 220, synth.Y9K_ANCHORS, "tree=t.tree\n"), xt, 0.24, 0.4,
                 aux_files={"t.tree": tt})
+    # groups wider than a warp (fanout 40; the root group has 3 nodes, every other group 40 or the tail)
+    tw = tree_text(330, 40, 3)
+    xw = tree_region_inputs(2, 3, 330, 4, 40, 3, seed=15, shared_path=True)
+    # nms .05: the concentric boxes of a cell's three anchors (IoU .07 ... .3) suppress one another
+    region_case("region_tree_wide", region_only_cfg(2, 4, 3, 330, synth.Y9K_ANCHORS, "tree=t.tree\n"), xw, 0.24, 0.05,
+                aux_files={"t.tree": tw})
     with tempfile.NamedTemporaryFile("r", suffix=".map") as f:
         synth.write_map(f.name, 220)
         mt = Path(f.name).read_text()

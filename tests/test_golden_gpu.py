@@ -30,7 +30,7 @@ def _bits(a):
 
 
 @pytest.mark.parametrize("name", ["region_voc_13", "region_voc_7_lowthresh", "region_coco_9", "region_tree_220",
-                                  "region_tree_220_map"])
+                                  "region_tree_220_map", "region_tree_wide"])
 def test_decode_nms_bit_exact_vs_reference_golden(tmp_path, monkeypatch, name):
     d = np.load(GOLDEN / f"{name}.npz")
     _materialise(d, tmp_path)

@@ -15,7 +15,7 @@ from tests import ref_util as R
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 FORWARD = ["mini_yolo", "mini_resnet", "mini_yolo_tree"]
-REGION = ["region_voc_13", "region_voc_7_lowthresh", "region_coco_9", "region_tree_220", "region_tree_220_map"]
+REGION = ["region_voc_13", "region_voc_7_lowthresh", "region_coco_9", "region_tree_220", "region_tree_220_map", "region_tree_wide"]
 SKIP_KEYS = {"cfg", "weights", "input", "thresh", "nms", "layers", "region_in", "use_map"}
 
 
