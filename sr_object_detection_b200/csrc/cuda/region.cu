@@ -395,9 +395,40 @@ __global__ void region_boxes_tree_kernel(float *__restrict__ pred, const float *
 // maximum over classes; keep when prob > thresh; emit in box-index order.
 // One block per image, one warp per box, ordered compaction by a block scan.
 // ---------------------------------------------------------------------------------
+// Wide class rows (yolo9000: 9418 classes): the first-maximum scan of one box is spread over a warp and the
+// boxes of ALL images over the grid; collect_kernel then only compacts.  Lane l scans classes l, l+32, ...
+// in increasing order with strict > (its first maximum), the warp keeps the largest value and, among equal
+// values, the smallest index - the result of the reference's serial scan.
+__global__ void box_argmax_kernel(const float *__restrict__ probs, long long nboxes, int classes,
+                                  float *__restrict__ best_out, int *__restrict__ arg_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = w0; i < nboxes; i += nw) {
+        const float *p = probs + i * classes;
+        float best = -FLT_MAX;
+        int arg = 0x7fffffff;
+        for (int j = lane; j < classes; j += 32) {
+            const float v = __ldg(p + j);
+            if (arg == 0x7fffffff || v > best) { best = v; arg = j; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, d);
+            if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+        }
+        if (lane == 0) {
+            best_out[i] = best;
+            arg_out[i] = arg;
+        }
+    }
+}
+
 __global__ void collect_kernel(const float *__restrict__ boxes, const float *__restrict__ probs, int total,
                                int classes, float thresh, y2_det *__restrict__ det, int *__restrict__ count,
-                               int max_det)
+                               int max_det, const float *__restrict__ pre_best, const int *__restrict__ pre_arg)
 {
     extern __shared__ int s_flag[]; // [total] obj id or -1, then prefix
     float *s_prob = reinterpret_cast<float *>(s_flag + total);
@@ -407,6 +438,12 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
     // one thread per box: max_index (utils.c:533-545) is a sequential scan with strict >, the first
     // maximum wins; a box's class row is contiguous, so the scan runs on 16-byte loads where it can
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        if (pre_best) {  // box_argmax_kernel did the scan
+            const float bv = pre_best[(size_t)b * total + i];
+            s_flag[i] = (bv > thresh) ? pre_arg[(size_t)b * total + i] : -1;
+            s_prob[i] = bv;
+            continue;
+        }
         const float *p = pb + (size_t)i * classes;
         float best = p[0];
         int arg = 0;
@@ -607,8 +644,37 @@ extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int
         set_error("y2_collect: %d boxes per image exceed the staging buffer", total);
         return Y2_EINVAL;
     }
+    const float *pre_best = nullptr;
+    const int *pre_arg = nullptr;
+    if (classes >= 256) {
+        // per-device scratch for the per-box maxima (grown on demand, never shrunk)
+        struct Scratch {
+            void *buf = nullptr;
+            size_t cap = 0;
+        };
+        static thread_local Scratch scratch[16];
+        int dev = 0;
+        Y2_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 16) return Y2_EINVAL;
+        Scratch &sc = scratch[dev];
+        const size_t nb = (size_t)batch * total;
+        if (sc.cap < nb * 8) {
+            if (sc.buf) cudaFree(sc.buf);
+            sc.buf = nullptr;
+            sc.cap = 0;
+            Y2_CUDA_CHECK(cudaMalloc(&sc.buf, nb * 8));
+            sc.cap = nb * 8;
+        }
+        float *best = (float *)sc.buf;
+        int *arg = (int *)(best + nb);
+        box_argmax_kernel<<<grid_cap((long long)(nb * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(
+            probs, (long long)nb, classes, best, arg);
+        Y2_LAUNCH_CHECK();
+        pre_best = best;
+        pre_arg = arg;
+    }
     collect_kernel<<<batch, 256, smem, to_stream(s)>>>(boxes, probs, total, classes, thresh, det, count,
-                                                       max_det);
+                                                       max_det, pre_best, pre_arg);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

@@ -527,3 +527,43 @@ def test_device_resize_is_bit_identical_to_load_image_plus_resize_image(tmp_path
         host = np.ctypeslib.as_array(out.data, shape=(3, h, w)).copy()
         dl.free_image(out)
         assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("classes", [20, 80, 300, 1001])
+def test_collect_final_pick_matches_max_index(classes):
+    """y2_collect = the final loop of Detector::detect (yolo_v2_class.cpp:221-239): per box max_index
+    (utils.c:533-545: the FIRST maximum), keep if prob > thresh, emit in box order.  Rows of >= 256 classes
+    take the warp-per-box scan (box_argmax_kernel); ties and all-zero rows are planted on purpose."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, total, max_det, thresh = 3, 150, 64, 0.3
+    rng = np.random.default_rng(classes)
+    probs = np.zeros((batch, total, classes), dtype=np.float32)
+    hot = rng.random((batch, total)) < 0.3
+    for b, i in zip(*np.nonzero(hot)):
+        k = rng.integers(1, 4)
+        idx = rng.choice(classes, k, replace=False)
+        probs[b, i, idx] = rng.random(k).astype(np.float32)
+        if rng.random() < 0.3:  # an exact tie for the maximum: the lower index must win
+            j = rng.choice(classes, 2, replace=False)
+            probs[b, i, j] = probs[b, i].max() + np.float32(0.1)
+    boxes = rng.random((batch, total, 4)).astype(np.float32)
+    d_boxes, d_probs = torch.from_numpy(boxes).to(dev), torch.from_numpy(probs).to(dev)
+    det = torch.zeros(batch * max_det * 7, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(batch, dtype=torch.int32, device=dev)
+    _lib.check(lib.y2_collect(d_boxes.data_ptr(), d_probs.data_ptr(), batch, total, classes, thresh, det.data_ptr(),
+                              cnt.data_ptr(), max_det, _stream()))
+    torch.cuda.synchronize()
+    raw = det.cpu().numpy().reshape(batch, max_det, 7)
+    counts = cnt.cpu().numpy()
+    for b in range(batch):
+        arg = probs[b].argmax(axis=1)  # numpy argmax returns the first maximum, like max_index
+        best = probs[b, np.arange(total), arg]
+        keep = np.nonzero(best > np.float32(thresh))[0]
+        assert counts[b] == len(keep)
+        n = min(len(keep), max_det)
+        got = raw[b, :n]
+        assert np.array_equal(got[:, 6], keep[:n])                      # box_index, in box order
+        assert np.array_equal(got[:, 5], arg[keep[:n]])                 # obj_id
+        assert np.array_equal(got[:, 4].view(np.float32), best[keep[:n]])
+        assert np.array_equal(got[:, :4].view(np.float32), boxes[b, keep[:n]])
