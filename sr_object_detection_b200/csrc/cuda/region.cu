@@ -315,7 +315,7 @@ __global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const f
 // v(j) = x[j] * v(parent) is reproduced exactly), then either the coco9k map lookup or
 // the "highest index above .5" selection runs.  pred is mutated like the reference.
 // ---------------------------------------------------------------------------------
-__global__ void region_boxes_tree_kernel(float *__restrict__ pred, const float *__restrict__ biases,
+__global__ void __launch_bounds__(1024) region_boxes_tree_kernel(float *__restrict__ pred, const float *__restrict__ biases,
                                          float *__restrict__ boxes, float *__restrict__ probs, int batch,
                                          int lw, int lh, int n, int classes, float img_w, float img_h,
                                          float thresh, int only_objectness, int classfix,
@@ -337,19 +337,26 @@ __global__ void region_boxes_tree_kernel(float *__restrict__ pred, const float *
         __syncthreads();
         float scale = x[4];
         if (classfix == -1 && scale < .5) scale = 0;
-        for (int j = threadIdx.x; j < classes; j += blockDim.x) {
-            int path[64];
-            int depth = 0;
-            int c = j;
-            while (c >= 0 && depth < 64) {
-                path[depth++] = c;
-                c = parent[c];
+        // hierarchy_predictions (tree.c:37-51): v[j] = x[j] * v[parent[j]], parents precede children.  Walked
+        // in chunks of blockDim classes: a node climbs only to its first ancestor BELOW the chunk, whose value
+        // is final, and multiplies back down in the reference's association (a WordTree is nearly
+        // breadth-first, so that is one or two steps instead of the whole path to the root).
+        for (int base = 0; base < classes; base += blockDim.x) {
+            const int j = base + threadIdx.x;
+            if (j < classes) {
+                int path[64];
+                int depth = 0;
+                int c = j;
+                while (c >= base && depth < 64) {
+                    path[depth++] = c;
+                    c = parent[c];
+                }
+                float v = (c >= 0) ? hv[c] : 1.f;  // x * 1.f is exact: a root keeps its own value
+                for (int d = depth - 1; d >= 0; --d) v = sx[path[d]] * v;
+                hv[j] = v;
             }
-            float v = sx[path[depth - 1]];
-            for (int d = depth - 2; d >= 0; --d) v = sx[path[d]] * v;
-            hv[j] = v;
+            __syncthreads();
         }
-        __syncthreads();
         float *pr = probs + bi * out_classes;
         if (map) {
             for (int j = threadIdx.x; j < classes; j += blockDim.x) x[5 + j] = hv[j];
@@ -622,7 +629,9 @@ extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes,
             set_error("y2_region_boxes: %d classes exceed the shared-memory staging", classes);
             return Y2_EINVAL;
         }
-        region_boxes_tree_kernel<<<grid_cap(nboxes, 4), 256, smem, to_stream(s)>>>(
+        // one block per box; wide trees get wide blocks (fewer chunk rounds of the hierarchy walk)
+        const int tree_threads = classes > 2048 ? 1024 : 256;
+        region_boxes_tree_kernel<<<grid_cap(nboxes, 4), tree_threads, smem, to_stream(s)>>>(
             pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh, only_objectness,
             classfix, d_tree_parent, d_map, map_n);
     } else {
