@@ -308,3 +308,36 @@ def test_set_batch_and_resize_replan_the_device_side(tmp_path):
     assert np.array_equal(again, got)
     dn.free_network(ref_net)
     dn.free_network(net)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name,side,batch", [("tiny-yolo-voc", 416, 64), ("tiny-yolo-voc", 608, 33), ("yolo-voc", 544, 48),
+                                             ("yolo", 608, 16), ("darknet19_448", 448, 32), ("resnet50", 224, 32)])
+def test_networks_at_serving_batches(tmp_path, name, side, batch):
+    """Whole networks at batch sizes where every CTA walks many tiles (the parity tests above use batches the
+    CPU reference finishes in seconds): must complete - an epilogue race in the conv+pool kernel once hung
+    tiny-yolo-voc at batch 64 - and image 0's output must equal the batch-1 network's up to bf16 roundings
+    (kernel variant, stream-K split and tile order change with the batch)."""
+    text1 = synth.CFGS[name](batch=1, w=side, h=side)
+    textb = synth.CFGS[name](batch=batch, w=side, h=side)
+    (tmp_path / "b1.cfg").write_text(text1)
+    (tmp_path / "bn.cfg").write_text(textb)
+    synth.write_weights(tmp_path / "n.weights", text1, seed=1234)
+    x = synth.images(batch, 3, side, side, seed=42)
+    dn.set_gpu_index(0)
+    net1 = dn.parse_network_cfg(tmp_path / "b1.cfg")
+    dn.load_weights(net1, tmp_path / "n.weights")
+    row = dn.network_predict(net1, np.ascontiguousarray(x[:1]))[0]
+    dn.free_network(net1)
+    net = dn.parse_network_cfg(tmp_path / "bn.cfg")
+    dn.load_weights(net, tmp_path / "n.weights")
+    out = dn.network_predict(net, x)
+    assert np.isfinite(out).all()
+    err = float(np.abs(out[0] - row).max() / np.abs(row).max())
+    assert err <= 5e-3, f"image 0 at batch {batch} differs from batch 1 by {err:.2e} of the row maximum"
+    again = dn.network_predict(net, x)
+    assert np.array_equal(again, out), "two runs of the same batch must be bit-identical"
+    if net.layers[net.n - 1].type == dn.REGION:
+        dets, counts = dn.network_detect_batch(net, x, 0.02, 0.4, 256)
+        assert len(dets) == batch
+    dn.free_network(net)
