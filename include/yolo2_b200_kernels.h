@@ -165,6 +165,10 @@ int y2_gather_patches_f32(const float *src, void *dst, int batch, int c, int h, 
                           int stride, int pad, int oh, int ow, int kpad, y2_stream_t s);
 int y2_gather_patches_bf16(const void *in, int in_cs, int cin_pad, int h, int w, void *dst, int batch,
                            int ksize, int stride, int pad, int oh, int ow, y2_stream_t s);
+/* _rows_f32: first layer with a 5..8-wide kernel (resnet50's 7x7/2): K index = (c*ksize + r)*8 + s, one
+ * aligned 16-byte group per kernel row (s >= ksize zero), kpad >= c*ksize*8. */
+int y2_gather_rows_f32(const float *src, void *dst, int batch, int c, int h, int w, int ksize, int stride,
+                       int pad, int oh, int ow, int kpad, y2_stream_t s);
 
 /* Decoded frames -> network input on the device: uint8 interleaved RGB [B][src_h][src_w][3] ->
  * fp32 planar [B][3][h][w], = load_image_stb's byte/255. (yolo_v2_class.cpp:129-149) followed by

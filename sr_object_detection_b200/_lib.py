@@ -101,6 +101,7 @@ def _declare(lib: C.CDLL) -> None:
         "y2_pack_patches_f32": (i, [vp, vp, i, i, i, i, i, i, vp]),
         "y2_gather_patches_f32": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
         "y2_gather_patches_bf16": (i, [vp, i, i, i, i, vp, i, i, i, i, i, i, vp]),
+        "y2_gather_rows_f32": (i, [vp, vp, i, i, i, i, i, i, i, i, i, i, vp]),
         "y2_resize_u8_to_f32": (i, [vp, vp, i, i, i, i, i, vp]),
         "y2_unpack_to_nchw_f32": (i, [vp, vp, i, i, i, i, i, vp]),
         "y2_flat_to_nchw_f32": (i, [vp, vp, i, i, i, i, vp]),

@@ -499,7 +499,15 @@ void y2_push_convolutional_layer(layer *l)
     const int kk = l->size * l->size;
     const size_t elems = (size_t)r->npad * r->ktot;
     uint16_t *w = (uint16_t *)calloc(elems, sizeof(uint16_t));
-    if (r->use_patches == 1) {
+    if (r->use_patches == 3) {
+        /* K index = (c*k + r)*8 + s (y2_gather_rows_f32) */
+        for (int f = 0; f < l->n; ++f)
+            for (int c = 0; c < l->c; ++c)
+                for (int rr = 0; rr < l->size; ++rr)
+                    for (int ss = 0; ss < l->size; ++ss)
+                        w[(size_t)f * r->ktot + (size_t)(c * l->size + rr) * 8 + ss] =
+                            y2_f32_to_bf16(l->weights[(((size_t)f * l->c + c) * l->size + rr) * l->size + ss]);
+    } else if (r->use_patches == 1) {
         /* K index = c*kk + r*k + s : the reference's own [c][kh][kw] order (im2col.c:26-28) */
         for (int f = 0; f < l->n; ++f)
             for (int k = 0; k < l->c * kk; ++k)
@@ -734,7 +742,11 @@ void y2_plan_network(network *net)
             if (r->cpad > r->npad) r->npad = round_up(r->cpad, r->block_n);
             const int kk = l->size * l->size;
             if (!native) {
-                if (i == 0) {
+                if (i == 0 && l->size >= 5 && l->size <= 8) {
+                    r->use_patches = 3; /* K = (c*k + r)*8 + s: one aligned 16-byte group per kernel row */
+                    r->kpad = round_up(l->c * l->size * 8, 64);
+                    r->cin_pad = r->kpad;
+                } else if (i == 0) {
                     r->use_patches = 1; /* K = c*k*k + r*k + s, zero-padded to a K block */
                     r->kpad = (l->c * kk <= 32) ? 32 : round_up(l->c * kk, 64);
                     r->cin_pad = r->kpad;
@@ -1002,6 +1014,10 @@ void forward_convolutional_layer_gpu(layer l, network_state state)
         y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
         Y2_CHECK(y2_gather_patches_bf16(pr->out, pr->out_cs, r->cin_pad, l.h, l.w, r->patches, l.batch, l.size,
                                         l.stride, l.pad, l.out_h, l.out_w, s));
+        count_launch(state.net, 1);
+    } else if (r->use_patches == 3) {
+        Y2_CHECK(y2_gather_rows_f32(state.input, r->patches, l.batch, l.c, l.h, l.w, l.size, l.stride, l.pad, l.out_h,
+                                    l.out_w, r->kpad, s));
         count_launch(state.net, 1);
     } else if (r->use_patches) {
         Y2_CHECK(y2_gather_patches_f32(state.input, r->patches, l.batch, l.c, l.h, l.w, l.size, l.stride, l.pad,
