@@ -186,18 +186,19 @@ def test_pipelined_submit_wait_equals_synchronous_detect(tmp_path):
     dn.free_network(net)
 
 
-def test_u8_input_detections_equal_float_input(tmp_path):
+@pytest.mark.parametrize("side", [416, 320, 608])
+def test_u8_input_detections_equal_float_input(tmp_path, side):
     """network_detect_batch_u8 / network_detect_submit_u8 on raw uint8 RGB images must give exactly the
     detections of the float calls on the image the reference's loaders derive from it (byte / 255.)."""
     import ctypes as C
     batch, max_det = 3, 256
-    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", batch)
+    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", batch, w=side, h=side)
     dn.set_gpu_index(0)
     net = dn.parse_network_cfg(cfg)
     dn.load_weights(net, weights)
     lib = dn.lib()
     rng = np.random.default_rng(3)
-    u8 = rng.integers(0, 256, size=(batch, 416, 416, 3), dtype=np.uint8)
+    u8 = rng.integers(0, 256, size=(batch, side, side, 3), dtype=np.uint8)
     planar = (u8.transpose(0, 3, 1, 2).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
     thresh, nms = 0.02, 0.4
     want, _ = dn.network_detect_batch(net, np.ascontiguousarray(planar), thresh, nms, max_det)
