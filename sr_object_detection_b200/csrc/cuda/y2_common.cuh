@@ -102,10 +102,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, int tag)
 {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
+    // watchdog by probe count (every probe sleeps >= 64 ns: 2^25 probes are > 2 s), cheaper in issue slots
+    // than reading the clock in kernels whose working warps are issue-bound (first layer, conv+pool)
+    unsigned probes = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(64);
-        if (clock64() - t0 > 4000000000LL) {
+        if (++probes > (1u << 25)) {
             printf("y2: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
                    (int)blockIdx.x, (int)threadIdx.x, parity);
             __trap();
