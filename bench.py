@@ -401,13 +401,13 @@ def main() -> int:
         "achieved": round(dom_tf, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": round(dom_tf / peaks["tflops"], 4), "peak_burst": peaks["tflops_burst"],
         "peak_source": peaks["source"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (yolo-voc L23, stream-K schedule:
-        # 50.4 MB read + 13.4 MB written incl. the parked partial sums; profiles/r1u_ncu_stem_and_streamk.txt;
-        # 47.6 MB with whole-tile scheduling, profiles/r1r_ncu_conv_kernels.txt); algorithmic operand bytes: 70 MB
-        "traffic": 63.8e6 if dom == 2 else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (yolo-voc L23, whole-tile schedule = the
+        # default: 44.7 MB read + 3.0 MB written, profiles/r1r_ncu_conv_kernels.txt; 63.8 MB with the opt-in
+        # stream-K schedule, profiles/r1u_ncu_stem_and_streamk.txt); algorithmic operand bytes: 70 MB
+        "traffic": 47.6e6 if dom == 2 else None,
         "traffic_of": "one launch of the dominant kernel, yolo-voc L23 (1024->1024 3x3 at 13x13, b64): DRAM read+write "
-                      "from ncu (stream-K schedule, parked partial sums included); the algorithmic operand bytes of "
-                      "that launch are 70 MB (activations stay in L2 between layers)",
+                      "from ncu --set full; the algorithmic operand bytes of that launch are 70 MB (activations stay "
+                      "in L2 between layers)",
         "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / max(float(layer_ms.sum()), 1e-9), 3),
         "all_convolutions": {"launches": conv_launches, "ms_per_step": round(conv_ms, 4),
                              "achieved": round(achieved_tf, 1), "frac": round(achieved_tf / peaks["tflops"], 4)},

@@ -471,11 +471,13 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.streamk = 0;
     p.sk_partial = nullptr;
     p.sk_flags = nullptr;
-    if (tiles > pairs && p.cblocks >= 2 && taps == 9) {  // short K loops: the parked partials would cost more than they save
-        const int waves = (tiles + pairs - 1) / pairs;
-        const double fill = (double)tiles / ((double)waves * pairs);
-        p.streamk = fill < 0.95;
-        if (const char *e = getenv("Y2_PAIR_STREAMK")) p.streamk = atoi(e) != 0;
+    // Opt-in (Y2_PAIR_STREAMK=1).  Measured on yolo-voc b64: it removes 5 % of the L23 kernel's cycles and gains
+    // 1 % on the step during the first ~70 ms after idle, but under sustained load the chip sits at its 1 kW cap,
+    // where only energy per step counts: the parked partial sums cost more than the idle SMs did and the
+    // sustained step is 0.8 % SLOWER with it (1.912 / 1.932 vs 1.901 / 1.913 ms, tools/ab_sustained.sh).
+    if (tiles > pairs && p.cblocks >= 2 && taps == 9) {  // short K loops: the parked partials would cost even more
+        const char *e = getenv("Y2_PAIR_STREAMK");
+        p.streamk = e && atoi(e) != 0;
     }
     if (p.streamk) {
         const size_t partial_bytes = (size_t)(pairs + 1) * kPairN * 256 * sizeof(float);
