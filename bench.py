@@ -424,7 +424,11 @@ def main() -> int:
                    "thresh": THRESH, "nms": NMS,
                    "l2": "inputs larger than L2 (133 MB fp32 batch, 2.5 GB activations per step)",
                    "weights": "random-init synthetic .weights (seed 1234)", "schedule": "CUDA graph replay",
-                   "algorithmic_gflop_per_image": round(flops_img / 1e9, 3)},
+                   "algorithmic_gflop_per_image": round(flops_img / 1e9, 3),
+                   "regime": ("sustained: timed region of %.2f s under the 1 kW power cap" % (ms_dev / 1000.0))
+                   if ms_dev >= 400.0 else
+                   ("burst window: timed region of %.0f ms; the power limiter settles after ~70 ms of this load, "
+                    "the sustained rate is ~10%% lower (default --steps 300 measures it)" % ms_dev)},
         "model_tflops": round(value / world * flops_img / 1e12, 1),
         "model_frac_of_peak": round(value / world * flops_img / 1e12 / peaks["tflops"], 4),
         "roofline": roofline,
