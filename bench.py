@@ -34,15 +34,49 @@ THRESH = 0.24   # detector.c:602 default -thresh
 NMS = 0.4       # detector.c:456 / yolo_v2_class.hpp:45
 MAX_DET = 256
 SEED_W, SEED_X = 1234, 42
+# The detection head of the random-init weights is scaled by this factor (synth.write_weights): with the plain
+# init no box of a random network reaches the 0.24 threshold and decode / NMS / pick would run on an empty
+# candidate set; at 13 about 8 % of the 845 boxes of an image clear it (SURVEY.md section 8d asks for ~5 %) and
+# NMS keeps ~8 of them.  The reference arm reads the same weights file.
+HEAD_GAIN = 13.0
+GATHER_CAP = 32  # detections per image carried by the fixed-size host gather of the multi-rank e2e loop
 
 
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return {"tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "tflops_burst": d["bf16_tflops"],
-                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "tflops_burst": d["bf16_tflops"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def _ncu_evidence():
+    """DRAM traffic and tensor-pipe utilisation of the dominant kernel from the committed ncu capture
+    (profiles/dominant_kernel_ncu.json names the raw summary it was taken from)."""
+    p = ROOT / "profiles" / "dominant_kernel_ncu.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return None
+
+
+def _cpu_model() -> str:
+    try:
+        for line in Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -103,33 +137,54 @@ def _write_inputs(tmp: Path, batch: int):
     cfg.write_text(cfg_text)
     weights = tmp / f"{CFG_NAME}.weights"
     if not weights.exists():
-        synth.write_weights(weights, cfg_text, seed=SEED_W)
+        synth.write_weights(weights, cfg_text, seed=SEED_W, head_gain=HEAD_GAIN)
     return cfg, weights
+
+
+def _ref_binary():
+    ref = ROOT / "oracle" / "_ref" / "darknet_ref"
+    if ref.exists():
+        return ref, "reference"
+    ref = ROOT / "oracle" / "_build" / "y2_oracle"
+    return (ref, "port") if ref.exists() else (None, "unavailable")
+
+
+def _time_reference(ref, cfg, weights, inp, warmup, iters, threads):
+    """One timed run of the CPU path.  torchrun exports OMP_NUM_THREADS=1 to its workers: the thread count is
+    always set explicitly here."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(threads)
+    env.pop("OMP_PROC_BIND", None)
+    r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS), str(warmup),
+                        str(iters)], capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-200:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
 
 
 def cpu_baseline(tmp: Path, iters: int = 20, warmup: int = 1) -> dict:
     """The reference's own CPU path (oracle/_ref, compiled from the reference sources) on the
-    host cores, bounded sample of the same workload: batch-1 forward + decode + NMS."""
+    host cores, bounded sample of the same workload: batch-1 forward + decode + NMS, with all host
+    threads and with one."""
     from sr_object_detection_b200 import synth
-    ref = ROOT / "oracle" / "_ref" / "darknet_ref"
-    kind = "reference"
-    if not ref.exists():
-        ref = ROOT / "oracle" / "_build" / "y2_oracle"
-        kind = "port"
-    if not ref.exists():
+    ref, kind = _ref_binary()
+    if ref is None:
         return {"value": None, "unit": "images/s", "cores": 0, "kind": "unavailable",
                 "sample": "oracle binaries not built (run __graft_entry__.build())"}
     cfg, weights = _write_inputs(tmp, 1)
     inp = tmp / "cpu_input.f32"
     synth.images(1, 3, SIDE, SIDE, seed=SEED_X).tofile(inp)
-    r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS), str(warmup),
-                        str(iters)], capture_output=True, text=True)
-    if r.returncode != 0:
-        return {"value": None, "unit": "images/s", "cores": 0, "kind": kind, "sample": "failed: " + r.stderr[-200:]}
-    d = json.loads(r.stdout.strip().splitlines()[-1])
-    return {"value": round(d["images_per_s"], 4), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+    threads = _host_threads()
+    try:
+        d = _time_reference(ref, cfg, weights, inp, warmup, iters, threads)
+        d1 = _time_reference(ref, cfg, weights, inp, 0, 1, 1)
+    except RuntimeError as e:
+        return {"value": None, "unit": "images/s", "cores": 0, "kind": kind, "sample": "failed: " + str(e)}
+    return {"value": round(d["images_per_s"], 4), "unit": "images/s", "cores": threads, "kind": kind,
+            "one_thread_value": round(d1["images_per_s"], 4), "cpu_model": _cpu_model(),
             "sample": f"{iters} x batch-1 {CFG_NAME} {SIDE}x{SIDE} forward+decode+NMS after {warmup} warm-up, "
-                      f"OpenMP over all host threads ({d['seconds']:.1f} s)"}
+                      f"OMP_NUM_THREADS={threads} ({d['seconds']:.1f} s); one image with OMP_NUM_THREADS=1 "
+                      f"({d1['seconds']:.1f} s)"}
 
 
 def run_reference(args) -> int:
@@ -139,29 +194,30 @@ def run_reference(args) -> int:
     with tempfile.TemporaryDirectory(prefix="y2bench_") as t:
         tmp = Path(t)
         from sr_object_detection_b200 import synth
-        ref = ROOT / "oracle" / "_ref" / "darknet_ref"
-        kind = "reference"
-        if not ref.exists():
-            ref = ROOT / "oracle" / "_build" / "y2_oracle"
-            kind = "port"
+        ref, kind = _ref_binary()
+        if ref is None:
+            _emit({"impl": "reference", "unavailable": "oracle binaries not built"})
+            return 0
         cfg, weights = _write_inputs(tmp, 1)
         inp = tmp / "cpu_input.f32"
         synth.images(1, 3, SIDE, SIDE, seed=SEED_X).tofile(inp)
-        r = subprocess.run([str(ref), "time", str(cfg), str(weights), str(inp), str(THRESH), str(NMS),
-                            str(args.warmup), str(args.steps)], capture_output=True, text=True)
-        if r.returncode != 0:
-            _emit({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-160:]})
+        threads = _host_threads()
+        try:
+            d = _time_reference(ref, cfg, weights, inp, args.warmup, args.steps, threads)
+        except RuntimeError as e:
+            _emit({"impl": "reference", "unavailable": "oracle run failed: " + str(e)[-160:]})
             return 0
-        d = json.loads(r.stdout.strip().splitlines()[-1])
         ips = d["images_per_s"]
         line = {
             "impl": "reference", "metric": "images/sec", "value": round(ips, 4), "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1000.0 * d["seconds"] / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "one image per step (batch 1), host CPU"},
-            "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
-                             "sample": f"{args.steps} steps x 1 image, forward+decode+NMS"},
+            "config": {"workload": WORKLOAD, "sample": "one image per step (batch 1), host CPU",
+                       "omp_threads": threads, "cpu_model": _cpu_model(), "head_gain": HEAD_GAIN},
+            "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": threads, "kind": kind,
+                             "cpu_model": _cpu_model(),
+                             "sample": f"{args.steps} steps x 1 image, forward+decode+NMS, OMP_NUM_THREADS={threads}"},
             "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -221,6 +277,7 @@ def main() -> int:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    host_group = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -228,12 +285,15 @@ def main() -> int:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the detection lists live on the host when network_detect_wait returns: they are gathered there
+        host_group = dist.new_group(backend="gloo")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
 
     from sr_object_detection_b200 import _lib, synth
     from sr_object_detection_b200 import darknet as dn
+    from sr_object_detection_b200 import dp
 
     lib = dn.lib()
     B = args.batch
@@ -242,9 +302,11 @@ def main() -> int:
     cfg, weights = _write_inputs(tmp, B)
     dn.set_gpu_index(local_rank)
     lib.cuda_set_device(local_rank)
+    # this rank's host thread (submits, staging copies, detection gather) stays on the CPUs next to its GPU
+    lib.y2_bind_thread_to_device.restype = C.c_int
+    cpus_bound = int(lib.y2_bind_thread_to_device(local_rank))
     net = dn.parse_network_cfg(cfg)
     dn.load_weights(net, weights)
-    from sr_object_detection_b200 import dp
     lo, hi = dp.shard_range(rank, world, B * world)  # this rank's slice of the global batch (weak scaling)
     assert hi - lo == B
     images = synth.images(B, 3, SIDE, SIDE, seed=SEED_X + lo)
@@ -256,13 +318,28 @@ def main() -> int:
     lib.network_upload_input(net, staging)
     dets = (dn.Detection * (B * MAX_DET))()
     counts = (C.c_int * B)()
+    dets_np = np.ctypeslib.as_array(dets)
+    counts_np = np.ctypeslib.as_array(counts)
 
     def step_device():
         lib.network_forward_device(net)
         lib.network_detect_device(net, THRESH, NMS, dets, counts, MAX_DET)
 
+    gathered = {"images": 0, "detections": 0}
+
+    def gather():
+        """multi-rank runs: the per-image detection lists of every rank end up on rank 0, in image order (the only
+        thing that crosses ranks); a fixed-size host gather over gloo, inside the e2e timed region"""
+        if world == 1:
+            return
+        res = dp.gather_detection_arrays(dets_np, counts_np, MAX_DET, GATHER_CAP, group=host_group)
+        if res is not None:
+            gathered["images"] += len(res[1])
+            gathered["detections"] += int(res[1].sum())
+
     def step_e2e_sync():
         lib.network_detect_batch(net, staging, THRESH, NMS, dets, counts, MAX_DET)
+        gather()
 
     # pipelined public API: every step uploads its own batch from pinned host memory (slots
     # alternate), runs forward + decode + NMS and reads the detection lists back; two batches are in
@@ -279,7 +356,9 @@ def main() -> int:
         for _ in range(1, steps):
             submit()
             lib.network_detect_wait(net, dets, counts, MAX_DET)
+            gather()
         lib.network_detect_wait(net, dets, counts, MAX_DET)
+        gather()
 
     def barrier():
         if world > 1:
@@ -290,12 +369,12 @@ def main() -> int:
     for e in ev:
         _lib.check(lib.y2_event_create(C.byref(e)))
 
-    def timed(fn, steps):
+    def timed(fn, steps, on_stream=stream):
         barrier()
-        _lib.check(lib.y2_event_record(ev[0], stream))
+        _lib.check(lib.y2_event_record(ev[0], on_stream))
         for _ in range(steps):
             fn()
-        _lib.check(lib.y2_event_record(ev[1], stream))
+        _lib.check(lib.y2_event_record(ev[1], on_stream))
         torch.cuda.synchronize()
         ms = C.c_float()
         _lib.check(lib.y2_event_elapsed_ms(ev[0], ev[1], C.byref(ms)))
@@ -310,6 +389,7 @@ def main() -> int:
         step_device()
     torch.cuda.synchronize()
     launches_fwd = lib.network_launch_count(net)
+    det_per_image = float(np.mean([min(c, MAX_DET) for c in counts]))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -342,15 +422,32 @@ def main() -> int:
         for _ in range(1, steps):
             submit_u8()
             lib.network_detect_wait(net, dets, counts, MAX_DET)
+            gather()
         lib.network_detect_wait(net, dets, counts, MAX_DET)
+        gather()
 
     for _ in range(3):
         step_e2e_sync()
     ms_e2e_sync = timed(step_e2e_sync, args.steps)
     run_e2e_pipelined(3)
+    gathered["images"] = gathered["detections"] = 0
     ms_e2e = timed(lambda: run_e2e_pipelined(args.steps), 1)
+    gathered_e2e = dict(gathered)
     run_e2e_u8(3)
     ms_e2e_u8 = timed(lambda: run_e2e_u8(args.steps), 1)
+
+    # host -> device ceiling of this box with the same ranks copying at the same time: plain pinned
+    # cudaMemcpyAsync of the fp32 batch, nothing else running (what the fp32 e2e entry is bound by)
+    h2d_reps = max(5, min(args.steps, 20))
+
+    def h2d_copy():
+        _lib.check(lib.y2_memcpy_h2d(lib.network_input_device(net), pipe_stage[0], images.nbytes, stream))
+
+    for _ in range(2):
+        h2d_copy()
+    ms_h2d = timed(h2d_copy, h2d_reps)
+    h2d_gbs_per_gpu = images.nbytes * h2d_reps / (ms_h2d * 1e6)
+    lib.network_upload_input(net, staging)  # restore the resident batch for the layer profile below
 
     # per-layer device times (eager pass with CUDA events on the network stream), for the
     # roofline of the dominant kernel: the tcgen05 convolution
@@ -388,33 +485,46 @@ def main() -> int:
     value = total_images / (ms_dev / 1000.0)
     e2e_value = total_images / (ms_e2e / 1000.0)
     peaks = _peaks()
+    # the peak that matches the regime of THIS run: a timed region shorter than ~0.4 s sits in the window before
+    # the power limiter settles (compare with the burst cuBLAS figure), a longer one runs at the sustained clocks
+    sustained = ms_dev >= 400.0
+    peak = peaks["tflops_sustained"] if sustained else peaks["tflops_burst"]
     step_flops = flops_img * B
     achieved_tf = step_flops / (conv_ms * 1e9) if conv_ms > 0 else 0.0
-    detect_launches = 6  # region_boxes, nms memset+count+mark+clear, collect
+    detect_launches = 3  # region_boxes (+ candidate count), nms_mark, collect (+ argmax for wide class rows)
     # dominant kernel = the convolution kernel with the largest share of the step (the CTA-pair kernel on
     # yolo-voc): algorithmic FLOPs of the layers it runs / the CUDA-event time of those launches
     dom = max(per_kernel, key=lambda k: per_kernel[k][0]) if per_kernel else None
     dom_ms, dom_fl, dom_n = per_kernel.get(dom, [0.0, 0.0, 0])
     dom_tf = dom_fl / (dom_ms * 1e9) if dom_ms > 0 else 0.0
+    ncu = _ncu_evidence() or {}
+    ncu_ok = dom == 2 and str(ncu.get("kernel", "")).startswith("conv_pair")
     roofline = {
         "bound": "tensor", "kernel": f"{KERNELS.get(dom)} ({dom_n} launches per step)",
-        "achieved": round(dom_tf, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-        "frac": round(dom_tf / peaks["tflops"], 4), "peak_burst": peaks["tflops_burst"],
+        "achieved": round(dom_tf, 1), "peak": peak, "unit": "TFLOP/s",
+        "frac": round(dom_tf / peak, 4),
+        "peak_regime": "sustained" if sustained else "burst",
+        "frac_vs_burst_peak": round(dom_tf / peaks["tflops_burst"], 4),
+        "frac_vs_sustained_peak": round(dom_tf / peaks["tflops_sustained"], 4),
+        "peak_burst": peaks["tflops_burst"], "peak_sustained": peaks["tflops_sustained"],
         "peak_source": peaks["source"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (yolo-voc L23, whole-tile schedule = the
-        # default: 44.7 MB read + 3.0 MB written, profiles/r1r_ncu_conv_kernels.txt; 63.8 MB with the opt-in
-        # stream-K schedule, profiles/r1u_ncu_stem_and_streamk.txt); algorithmic operand bytes: 70 MB
-        "traffic": 47.6e6 if dom == 2 else None,
-        "traffic_of": "one launch of the dominant kernel, yolo-voc L23 (1024->1024 3x3 at 13x13, b64): DRAM read+write "
-                      "from ncu --set full; the algorithmic operand bytes of that launch are 70 MB (activations stay "
-                      "in L2 between layers)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch and the tensor-pipe utilisation, from the
+        # committed ncu capture of the dominant kernel (BASELINE.json's second metric)
+        "traffic": (ncu.get("dram_bytes_read", 0) + ncu.get("dram_bytes_write", 0)) if ncu_ok else None,
+        "tensor_pipe_pct": ncu.get("tensor_pipe_pct_elapsed") if ncu_ok else None,
+        "tensor_pipe_pct_of_active_cycles": ncu.get("tensor_pipe_pct_active") if ncu_ok else None,
+        "traffic_of": (f"{ncu.get('launch')}; ncu --set full, {ncu.get('source')}; algorithmic operand bytes of that "
+                       f"launch: {ncu.get('algorithmic_operand_bytes')}") if ncu_ok else None,
         "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / max(float(layer_ms.sum()), 1e-9), 3),
         "all_convolutions": {"launches": conv_launches, "ms_per_step": round(conv_ms, 4),
-                             "achieved": round(achieved_tf, 1), "frac": round(achieved_tf / peaks["tflops"], 4)},
+                             "achieved": round(achieved_tf, 1), "frac": round(achieved_tf / peak, 4)},
         "per_kernel": {KERNELS.get(k): {"launches": v[2], "ms": round(v[0], 4),
                                         "tflops": round(v[1] / (v[0] * 1e9), 1) if v[0] > 0 else None}
                        for k, v in sorted(per_kernel.items())},
         "step_ms_eager": round(float(layer_ms.sum()), 4)}
+    d2h_bytes = int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4)
+    gather_note = ("; the detection lists of all ranks are gathered on rank 0 every step (host-side gloo gather, "
+                   f"{GATHER_CAP} detections per image per message)") if world > 1 else ""
     line = {
         "metric": "images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
@@ -423,30 +533,41 @@ def main() -> int:
                    "global_batch": B * world, "input": f"{SIDE}x{SIDE}x3 fp32", "parallelism": f"dp{world}",
                    "thresh": THRESH, "nms": NMS,
                    "l2": "inputs larger than L2 (133 MB fp32 batch, 2.5 GB activations per step)",
-                   "weights": "random-init synthetic .weights (seed 1234)", "schedule": "CUDA graph replay",
+                   "weights": f"random-init synthetic .weights (seed 1234), detection head scaled x{HEAD_GAIN:g} so "
+                              "that decode / NMS / pick have candidates to work on",
+                   "detections_per_image": round(det_per_image, 2),
+                   "schedule": "CUDA graph replay",
+                   "host_thread_cpus": cpus_bound or "unbound (PCI topology not visible)",
                    "algorithmic_gflop_per_image": round(flops_img / 1e9, 3),
                    "regime": ("sustained: timed region of %.2f s under the 1 kW power cap" % (ms_dev / 1000.0))
-                   if ms_dev >= 400.0 else
+                   if sustained else
                    ("burst window: timed region of %.0f ms; the power limiter settles after ~70 ms of this load, "
                     "the sustained rate is ~10%% lower (default --steps 300 measures it)" % ms_dev)},
         "model_tflops": round(value / world * flops_img / 1e12, 1),
-        "model_frac_of_peak": round(value / world * flops_img / 1e12 / peaks["tflops"], 4),
+        "model_frac_of_peak": round(value / world * flops_img / 1e12 / peak, 4),
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "h2d_bytes_per_step": int(images.nbytes),
-                "d2h_bytes_per_step": int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4),
+                "d2h_bytes_per_step": d2h_bytes,
                 "api": "network_detect_submit(net, pinned_host_images, thresh, nms, max_det) / network_detect_wait(net, "
-                       "dets, counts, max_det), two batches in flight",
+                       "dets, counts, max_det), two batches in flight" + gather_note,
+                "h2d_ceiling_gbs_per_gpu": round(h2d_gbs_per_gpu, 2),
+                "h2d_ceiling_gbs_total": round(h2d_gbs_per_gpu * world, 2),
+                "h2d_ceiling_how": f"{h2d_reps} back-to-back pinned cudaMemcpyAsync of the {images.nbytes >> 20} MB fp32 "
+                                   f"batch on all {world} rank(s) at once, max over ranks",
+                "frac_of_h2d_ceiling": round(e2e_value / world * (images.nbytes / B) / (h2d_gbs_per_gpu * 1e9), 4),
                 "sync_value": round(total_images / (ms_e2e_sync / 1000.0), 1),
                 "sync_api": "network_detect_batch(net, host_images, thresh, nms, dets, counts, max_det)"},
         "e2e_u8": {"value": round(total_images / (ms_e2e_u8 / 1000.0), 1), "unit": "images/s",
                    "ms_per_step": round(ms_e2e_u8 / args.steps, 4), "h2d_bytes_per_step": int(u8_images.nbytes),
-                   "d2h_bytes_per_step": int(B * MAX_DET * C.sizeof(dn.Detection) + B * 4),
+                   "d2h_bytes_per_step": d2h_bytes,
                    "api": "network_detect_submit_u8(net, pinned_uint8_rgb_images, ...) / network_detect_wait: raw decoded "
-                          "images, byte/255 on the device (bit-identical detections to the float call)"},
+                          "images, byte/255 on the device (bit-identical detections to the float call)" + gather_note},
         "gpu_launches": int((launches_fwd + detect_launches) * args.steps),
         "clocks": clocks,
     }
+    if world > 1:
+        line["e2e"]["gathered_on_rank0"] = gathered_e2e
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(tmp)

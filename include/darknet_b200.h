@@ -84,6 +84,7 @@ struct layer {
     float coord_scale, object_scale, noobject_scale, class_scale;
     float temperature, dot;
     int dontload, dontloadscales;
+    int adam;         /* [net] adam=1: the .weights file carries m and v behind every filter bank */
     tree *softmax_tree;
     int *map;
     float *cost;
@@ -93,6 +94,7 @@ struct layer {
     float *weights;
     float *rolling_mean;
     float *rolling_variance;
+    float *m, *v;     /* adam moments, only stored and re-saved (parser.c:788-791, 992-995) */
     int *input_layers;
     int *input_sizes;
     /* host activations, fp32 NCHW (REGION: flattened [hw][n][5+classes]).  Always present for
@@ -321,6 +323,8 @@ void network_upload_input(network net, const float *input);
 /* Pinned host staging buffer ([batch][c][h][w] fp32) that network_upload_input copies from;
  * fill it directly and pass it (or NULL) to network_upload_input to skip the extra host copy. */
 float *network_input_staging(network net);
+/* Device address of that input buffer (fp32 [batch][c][h][w]), e.g. for a caller that decodes on the GPU. */
+float *network_input_device(network net);
 /* Forward pass on the already-uploaded input; nothing is copied back. */
 void network_forward_device(network net);
 /* Region decode + NMS + final pick on the device for every image of the batch; copies only

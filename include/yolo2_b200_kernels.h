@@ -44,6 +44,11 @@ const char *y2_last_error(void);
  *      cuda_push_array / cuda_pull_array / cuda_free) -------------------------------- */
 int y2_device_count(int *count);
 int y2_set_device(int dev);
+int y2_get_device(int *dev);
+/* keep the calling host thread on the CPUs next to GPU `dev` (PCI local_cpulist); returns the size of the new
+ * CPU mask, 0 when the topology is not visible and nothing changed.  y2_host_alloc does the same temporarily so
+ * that pinned staging buffers live in the GPU's own NUMA node. */
+int y2_bind_thread_to_device(int dev);
 int y2_malloc(void **dptr, size_t bytes);
 int y2_free(void *dptr);
 int y2_memset(void *dptr, int value, size_t bytes, y2_stream_t s);
@@ -139,6 +144,7 @@ int y2_stem_conv_pool(const float *in, int batch, int c, int h, int w, const voi
  * (float)(byte / 255.) exactly as the reference's loaders do on the host (yolo_v2_class.cpp:129-149
  * load_image_stb, yolo_v2_class.hpp:95-115 mat_to_image), so the result is bit-identical to
  * y2_stem_conv_pool on the converted planar image at a quarter of the upload.  w % 16 == 0. */
+int y2_stem_u8_supported(int h, int w); /* 1 when y2_stem_conv_pool_u8 accepts this image size */
 int y2_stem_conv_pool_u8(const unsigned char *in_hwc, int batch, int h, int w, const void *wt, int npad,
                          const float *alpha, const float *beta, int act, void *out, int out_cs,
                          y2_stream_t s);
@@ -228,10 +234,27 @@ int y2_region_boxes(float *pred, const float *d_biases, float *boxes, float *pro
                     int tree_n, const int *d_tree_parent, const int *d_map, int map_n,
                     y2_stream_t s);
 
+/* Same decode that also counts the non-zero probabilities per (image, class) into nz_count[B][classes_out]
+ * (atomic increments: the caller zeroes the counters once, y2_collect_ws hands them back zeroed): the
+ * candidate counts y2_nms_mark needs, without a separate pass over the probabilities. */
+int y2_region_boxes_counted(float *pred, const float *d_biases, float *boxes, float *probs,
+                            int batch, int lw, int lh, int n, int classes, float img_w,
+                            float img_h, float thresh, int only_objectness, int classfix,
+                            int tree_n, const int *d_tree_parent, const int *d_map, int map_n,
+                            int *nz_count, y2_stream_t s);
+
 /* ---- do_nms_sort (replaces box.c:249-277) ------------------------------------------- */
 /* boxes [B][total][4], probs [B][total][classes] updated in place. */
 int y2_nms_sort(const float *boxes, float *probs, int batch, int total, int classes,
                 float thresh, y2_stream_t s);
+/* The suppression pass alone, on caller-owned candidate counters nz_count[B][classes]: suppressed entries
+ * are left NEGATIVE (-|p|) instead of zero; y2_collect / y2_collect_ws read a negative entry as 0. */
+int y2_nms_mark(const float *boxes, float *probs, const int *nz_count, int batch, int total, int classes,
+                float thresh, y2_stream_t s);
+/* do_nms (box.c:279-297, the unsorted variant used by demo.c / validate_detector_recall): for every pair
+ * i < j with box_iou > thresh, per class the smaller of the two probabilities is zeroed, pairs visited in
+ * the reference's order.  boxes [total][4], probs [total][classes] updated in place. */
+int y2_nms_unsorted(const float *boxes, float *probs, int total, int classes, float thresh, y2_stream_t s);
 
 /* ---- final pick (replaces yolo_v2_class.cpp:221-239): per box max_index over classes,
  *      keep prob > thresh; compacts to det[B][max_det] + count[B] --------------------- */
@@ -243,6 +266,12 @@ typedef struct y2_det {
 } y2_det;
 int y2_collect(const float *boxes, const float *probs, int batch, int total, int classes,
                float thresh, y2_det *det, int *count, int max_det, y2_stream_t s);
+/* The same with caller-owned scratch `ws` of y2_collect_ws_bytes() bytes (may be NULL when that is 0) and,
+ * optionally, the NMS candidate counters nz_count[B][classes] to be zeroed for the next batch. */
+size_t y2_collect_ws_bytes(int batch, int total, int classes);
+int y2_collect_ws(const float *boxes, const float *probs, int batch, int total, int classes,
+                  float thresh, y2_det *det, int *count, int max_det, void *ws, int *nz_count,
+                  y2_stream_t s);
 
 /* ---- classifier tail (config 5) ----------------------------------------------------- */
 int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs,

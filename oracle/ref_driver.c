@@ -14,8 +14,14 @@
  *   darknet_ref time    <cfg> <weights> <input.f32> <thresh> <nms> <warmup> <iters>
  *   darknet_ref resize  <in.f32> <c> <h> <w> <out_h> <out_w> <out.f32>
  *   darknet_ref layers  <cfg>                     (layer table as JSON, parser parity)
+ *   darknet_ref donms   <boxes.f32> <probs.f32> <total> <classes> <thresh> <out.f32>   (do_nms, box.c:279-297)
  *
- * Environment: Y2_USE_MAP=1 passes the region layer's `map` to get_region_boxes (the 200-class
+ * `forward` and `region` also write dets.f32: the final pick of Detector::detect
+ * (yolo_v2_class.cpp:221-227: max_index over the post-NMS probabilities, keep prob > thresh) as rows of
+ * 8 floats [image, box_index, obj_id, prob, x, y, w, h], in image / box order.
+ *
+ * Environment: Y2_DUMP_MAX_MB=N skips the per-layer dump of layers larger than N MB (big batches);
+ * Y2_USE_MAP=1 passes the region layer's `map` to get_region_boxes (the 200-class
  * branch of region_layer.c:352-356, as validate_detector does, detector.c:344-347).
  *
  * <cfg> must carry batch=B subdivisions=1 (set_batch_network does not reallocate,
@@ -78,6 +84,9 @@ static void decode_and_nms(network net, const char *outdir, float thresh, float 
     float *all_boxes = calloc((size_t)l.batch * total * 4, sizeof(float));
     float *pre = calloc((size_t)l.batch * total * l.classes, sizeof(float));
     float *post = calloc((size_t)l.batch * total * l.classes, sizeof(float));
+    float *dets = calloc((size_t)l.batch * total * 8, sizeof(float));
+    size_t n_dets = 0;
+    int out_classes = map ? 200 : l.classes;
     for (b = 0; b < l.batch; ++b) {
         layer lb = l;
         lb.output = l.output + (size_t)b * l.outputs;
@@ -88,6 +97,15 @@ static void decode_and_nms(network net, const char *outdir, float thresh, float 
         if (nms > 0) do_nms_sort(boxes, probs, total, l.classes, nms);
         for (j = 0; j < total; ++j)
             memcpy(post + ((size_t)b * total + j) * l.classes, probs[j], l.classes * sizeof(float));
+        for (j = 0; j < total; ++j) { /* yolo_v2_class.cpp:221-227 */
+            int obj_id = max_index(probs[j], out_classes);
+            float prob = probs[j][obj_id];
+            if (prob > thresh) {
+                float *d = dets + 8 * n_dets++;
+                d[0] = (float)b; d[1] = (float)j; d[2] = (float)obj_id; d[3] = prob;
+                d[4] = boxes[j].x; d[5] = boxes[j].y; d[6] = boxes[j].w; d[7] = boxes[j].h;
+            }
+        }
     }
     if (write) {
         write_f32(outdir, "boxes.f32", all_boxes, (size_t)l.batch * total * 4);
@@ -95,7 +113,9 @@ static void decode_and_nms(network net, const char *outdir, float thresh, float 
         write_f32(outdir, "probs_post.f32", post, (size_t)l.batch * total * l.classes);
         /* region output after get_region_boxes (mutated in the tree case) */
         write_f32(outdir, "region_after_boxes.f32", l.output, (size_t)l.batch * l.outputs);
+        write_f32(outdir, "dets.f32", dets, n_dets * 8);
     }
+    free(dets);
     for (j = 0; j < total; ++j) free(probs[j]);
     free(probs); free(boxes); free(all_boxes); free(pre); free(post);
 }
@@ -121,6 +141,8 @@ static int cmd_forward(int argc, char **argv)
         for (i = 0; i < net.n; ++i) {
             layer l = net.layers[i];
             if (!l.output || l.type == COST) continue;
+            if (getenv("Y2_DUMP_MAX_MB") &&
+                (double)l.batch * l.outputs * 4 > 1048576.0 * atof(getenv("Y2_DUMP_MAX_MB"))) continue;
             char name[64];
             snprintf(name, sizeof(name), "layer_%03d.f32", i);
             write_f32(outdir, name, l.output, (size_t)l.batch * l.outputs);
@@ -213,6 +235,23 @@ static int cmd_topk(int argc, char **argv)
     return 0;
 }
 
+/* the reference's unsorted do_nms (box.c:279-297) on given boxes [total][4] / probs [total][classes] */
+static int cmd_donms(int argc, char **argv)
+{
+    if (argc < 8) return 1;
+    int total = atoi(argv[4]), classes = atoi(argv[5]), j;
+    float thresh = atof(argv[6]);
+    box *boxes = (box *)read_f32(argv[2], (size_t)total * 4);
+    float *flat = read_f32(argv[3], (size_t)total * classes);
+    float **probs = calloc(total, sizeof(float *));
+    for (j = 0; j < total; ++j) probs[j] = flat + (size_t)j * classes;
+    do_nms(boxes, probs, total, classes, thresh);
+    FILE *f = fopen(argv[7], "wb");
+    fwrite(flat, sizeof(float), (size_t)total * classes, f);
+    fclose(f);
+    return 0;
+}
+
 static int cmd_layers(int argc, char **argv)
 {
     if (argc < 3) return 1;
@@ -239,6 +278,7 @@ int main(int argc, char **argv)
     if (!strcmp(argv[1], "time")) return cmd_time(argc, argv);
     if (!strcmp(argv[1], "resize")) return cmd_resize(argc, argv);
     if (!strcmp(argv[1], "layers")) return cmd_layers(argc, argv);
+    if (!strcmp(argv[1], "donms")) return cmd_donms(argc, argv);
     if (!strcmp(argv[1], "letterbox")) return cmd_letterbox(argc, argv);
     if (!strcmp(argv[1], "topk")) return cmd_topk(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);

@@ -819,6 +819,25 @@ static void nms_sort(obox *boxes, float **probs, int total, int classes, float t
     free(tmp);
 }
 
+/* do_nms, box.c:279-297 (the unsorted variant): a row is skipped when none of its probabilities is positive at
+ * the moment it is visited; for an overlapping later row the smaller entry of each class is zeroed */
+static void nms_unsorted(obox *boxes, float **probs, int total, int classes, float thresh)
+{
+    for (int i = 0; i < total; ++i) {
+        int any = 0;
+        for (int k = 0; k < classes; ++k) any = any || (probs[i][k] > 0);
+        if (!any) continue;
+        for (int j = i + 1; j < total; ++j) {
+            if (iou(boxes[i], boxes[j]) > thresh) {
+                for (int k = 0; k < classes; ++k) {
+                    if (probs[i][k] < probs[j][k]) probs[i][k] = 0;
+                    else probs[j][k] = 0;
+                }
+            }
+        }
+    }
+}
+
 /* resize_image, image.c:1950-1993 (planar CHW, two-pass bilinear) */
 static void resize_planar(const float *im, int c, int ih, int iw, int h, int w, float *out)
 {
@@ -895,6 +914,9 @@ static void decode_and_nms(onet *net, const char *outdir, float thresh, float nm
     float *all_boxes = calloc((size_t)l->batch * total * 4, sizeof(float));
     float *pre = calloc((size_t)l->batch * total * l->classes, sizeof(float));
     float *post = calloc((size_t)l->batch * total * l->classes, sizeof(float));
+    float *dets = calloc((size_t)l->batch * total * 8, sizeof(float));
+    size_t n_dets = 0;
+    const int out_classes = map ? 200 : l->classes;
     for (int b = 0; b < l->batch; ++b) {
         region_boxes(l, l->output + (size_t)b * l->outputs, 1, 1, thresh, probs, boxes, 0, map);
         memcpy(all_boxes + (size_t)b * total * 4, boxes, (size_t)total * sizeof(obox));
@@ -903,13 +925,27 @@ static void decode_and_nms(onet *net, const char *outdir, float thresh, float nm
         if (nms > 0) nms_sort(boxes, probs, total, l->classes, nms);
         for (int j = 0; j < total; ++j)
             memcpy(post + ((size_t)b * total + j) * l->classes, probs[j], (size_t)l->classes * sizeof(float));
+        /* final pick, yolo_v2_class.cpp:221-227 with max_index of utils.c:533-545 (strict >, first maximum) */
+        for (int j = 0; j < total; ++j) {
+            int obj_id = 0;
+            float prob = probs[j][0];
+            for (int k = 1; k < out_classes; ++k)
+                if (probs[j][k] > prob) { prob = probs[j][k]; obj_id = k; }
+            if (prob > thresh) {
+                float *d = dets + 8 * n_dets++;
+                d[0] = (float)b; d[1] = (float)j; d[2] = (float)obj_id; d[3] = prob;
+                d[4] = boxes[j].x; d[5] = boxes[j].y; d[6] = boxes[j].w; d[7] = boxes[j].h;
+            }
+        }
     }
     if (write) {
         write_f32(outdir, "boxes.f32", all_boxes, (size_t)l->batch * total * 4);
         write_f32(outdir, "probs_pre.f32", pre, (size_t)l->batch * total * l->classes);
         write_f32(outdir, "probs_post.f32", post, (size_t)l->batch * total * l->classes);
         write_f32(outdir, "region_after_boxes.f32", l->output, (size_t)l->batch * l->outputs);
+        write_f32(outdir, "dets.f32", dets, n_dets * 8);
     }
+    free(dets);
     for (int j = 0; j < total; ++j) free(probs[j]);
     free(probs); free(boxes); free(all_boxes); free(pre); free(post);
 }
@@ -932,6 +968,8 @@ static int cmd_forward(int argc, char **argv)
         for (int i = 0; i < net.n; ++i) {
             olayer *l = &net.l[i];
             if (!l->output || l->type == T_COST) continue;
+            if (getenv("Y2_DUMP_MAX_MB") &&
+                (double)l->batch * l->outputs * 4 > 1048576.0 * atof(getenv("Y2_DUMP_MAX_MB"))) continue;
             char name[64];
             snprintf(name, sizeof(name), "layer_%03d.f32", i);
             write_f32(outdir, name, l->output, (size_t)l->batch * l->outputs);
@@ -990,6 +1028,23 @@ static int cmd_resize(int argc, char **argv)
     return 0;
 }
 
+static int cmd_donms(int argc, char **argv)
+{
+    if (argc < 8) return 1;
+    const int total = atoi(argv[4]), classes = atoi(argv[5]);
+    const float thresh = atof(argv[6]);
+    obox *boxes = (obox *)read_f32(argv[2], (size_t)total * 4);
+    float *flat = read_f32(argv[3], (size_t)total * classes);
+    float **probs = calloc(total, sizeof(float *));
+    for (int j = 0; j < total; ++j) probs[j] = flat + (size_t)j * classes;
+    nms_unsorted(boxes, probs, total, classes, thresh);
+    FILE *f = fopen(argv[7], "wb");
+    if (!f) return 2;
+    fwrite(flat, sizeof(float), (size_t)total * classes, f);
+    fclose(f);
+    return 0;
+}
+
 static int cmd_layers(int argc, char **argv)
 {
     if (argc < 3) return 1;
@@ -1017,6 +1072,7 @@ int main(int argc, char **argv)
     if (!strcmp(argv[1], "time")) return cmd_time(argc, argv);
     if (!strcmp(argv[1], "resize")) return cmd_resize(argc, argv);
     if (!strcmp(argv[1], "layers")) return cmd_layers(argc, argv);
+    if (!strcmp(argv[1], "donms")) return cmd_donms(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 1;
 }

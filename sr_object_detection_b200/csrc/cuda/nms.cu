@@ -73,15 +73,17 @@ __global__ void nms_count_kernel(const float *__restrict__ probs, int *__restric
     }
 }
 
-// grid = (classes, batch).  Dynamic smem: idx[cap] int, key[cap] float, sorted[cap] int,
-// alive[cap] int, box[cap] float4.
+// Persistent grid: every block walks the (image, class) counter array with a grid stride and works on the
+// pairs that have at least two candidates (yolo9000: 9418 classes x batch pairs, a handful of them live).
+// Dynamic smem: idx[cap] int, key[cap] float, sorted[cap] int, alive[cap] int, box[cap] float4.
 __global__ void nms_mark_kernel(const float4 *__restrict__ boxes, float *probs, const int *__restrict__ cnt,
-                                int total, int classes, float thresh, int cap)
+                                int batch, int total, int classes, float thresh, int cap)
 {
-    const int k = blockIdx.x, b = blockIdx.y;
-    const int n = cnt[(size_t)b * classes + k];
-    if (n <= 1) return; // a lone candidate only "suppresses" zeros
     extern __shared__ __align__(16) unsigned char nms_smem[];
+    const long long pairs = (long long)batch * classes;
+  for (long long pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    if (cnt[pair] <= 1) continue; // a lone candidate only "suppresses" zeros (uniform per block)
+    const int b = (int)(pair / classes), k = (int)(pair - (long long)b * classes);
     float4 *s_box = reinterpret_cast<float4 *>(nms_smem);
     int *s_idx = reinterpret_cast<int *>(s_box + cap);
     float *s_key = reinterpret_cast<float *>(s_idx + cap);
@@ -160,6 +162,8 @@ __global__ void nms_mark_kernel(const float4 *__restrict__ boxes, float *probs, 
             *q = -fabsf(*q);
         }
     }
+    __syncthreads(); // the shared arrays are reused by this block's next pair
+  }
 }
 
 // negative == suppressed -> 0
@@ -171,60 +175,141 @@ __global__ void nms_clear_kernel(float *__restrict__ probs, long long n)
     }
 }
 
-struct NmsScratch {
-    int *cnt = nullptr;
-    size_t cap = 0;
-};
+// ---- do_nms (box.c:279-297), the unsorted variant --------------------------------------------------
+// bit j of mask[i][j / 32] : j > i and box_iou(boxes[i], boxes[j]) > thresh
+__global__ void iou_mask_kernel(const float4 *__restrict__ boxes, int total, float thresh, unsigned *__restrict__ mask,
+                                int words)
+{
+    const long long n = (long long)total * words;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / words), w = (int)(t - (long long)i * words);
+        const float4 a = boxes[i];
+        unsigned bits = 0;
+        for (int bit = 0; bit < 32; ++bit) {
+            const int j = w * 32 + bit;
+            if (j > i && j < total && box_iou_ref(a, boxes[j]) > thresh) bits |= 1u << bit;
+        }
+        mask[t] = bits;
+    }
+}
+
+// One block.  The reference walks rows i in order, skips a row none of whose probabilities is positive AT THAT
+// MOMENT (a test that couples all classes), then for every later overlapping row j zeroes, per class, the
+// smaller of the two entries.  Here a thread owns whole class columns (no two threads ever touch the same
+// entry); only the row test needs the block.
+__global__ void __launch_bounds__(1024) nms_unsorted_kernel(float *probs, const unsigned *__restrict__ mask, int total,
+                                                            int classes, int words)
+{
+    for (int i = 0; i < total; ++i) {
+        float *pi = probs + (size_t)i * classes;
+        int mine = 0;
+        for (int k = threadIdx.x; k < classes; k += blockDim.x) mine |= (pi[k] > 0);
+        if (!__syncthreads_or(mine)) continue;
+        for (int w = (i + 1) >> 5; w < words; ++w) {
+            unsigned bits = mask[(size_t)i * words + w];
+            while (bits) {
+                const int j = (w << 5) + __ffs(bits) - 1;
+                bits &= bits - 1;
+                float *pj = probs + (size_t)j * classes;
+                for (int k = threadIdx.x; k < classes; k += blockDim.x) {
+                    if (pi[k] < pj[k]) pi[k] = 0;
+                    else pj[k] = 0;
+                }
+            }
+        }
+    }
+}
 
 } // namespace y2
 
 using namespace y2;
 
-extern "C" int y2_nms_sort(const float *boxes, float *probs, int batch, int total, int classes, float thresh,
-                           y2_stream_t s)
+extern "C" int y2_nms_unsorted(const float *boxes, float *probs, int total, int classes, float thresh, y2_stream_t s)
 {
-    if (!boxes || !probs || batch <= 0 || total <= 0 || classes <= 0) return Y2_EINVAL;
+    if (!boxes || !probs || total <= 0 || classes <= 0) return Y2_EINVAL;
     cudaStream_t st = to_stream(s);
-    // per-device scratch for the candidate counters (grown on demand, never shrunk)
-    static thread_local NmsScratch scratch[16];
-    int dev = 0;
-    Y2_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return Y2_EINVAL;
-    NmsScratch &sc = scratch[dev];
-    const size_t need = (size_t)batch * classes;
-    if (sc.cap < need) {
-        if (sc.cnt) cudaFree(sc.cnt);
-        sc.cnt = nullptr;
-        sc.cap = 0;
-        Y2_CUDA_CHECK(cudaMalloc(&sc.cnt, need * sizeof(int)));
-        sc.cap = need;
-    }
-    Y2_CUDA_CHECK(cudaMemsetAsync(sc.cnt, 0, need * sizeof(int), st));
-    const long long n = (long long)batch * total * classes;
+    const int words = (total + 31) / 32;
+    unsigned *mask = nullptr;
+    Y2_CUDA_CHECK(cudaMalloc(&mask, (size_t)total * words * sizeof(unsigned)));
+    const long long n = (long long)total * words;
     long long blocks = (n + 255) / 256;
     const long long capb = (long long)sm_count() * 16;
     if (blocks > capb) blocks = capb;
-    nms_count_kernel<<<(int)blocks, 256, 0, st>>>(probs, sc.cnt, batch, total, classes);
-    Y2_LAUNCH_CHECK();
+    iou_mask_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(boxes), total, thresh, mask, words);
+    int rc = cudaGetLastError() == cudaSuccess ? Y2_OK : Y2_ECUDA;
+    if (rc == Y2_OK) {
+        int threads = classes < 1024 ? (classes + 31) / 32 * 32 : 1024;
+        nms_unsorted_kernel<<<1, threads, 0, st>>>(probs, mask, total, classes, words);
+        if (cudaGetLastError() != cudaSuccess) rc = Y2_ECUDA;
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(mask);
+    return rc;
+}
 
+static int nms_mark_launch(const float *boxes, float *probs, const int *cnt, int batch, int total, int classes,
+                           float thresh, cudaStream_t st)
+{
     const int cap = total;
     const size_t smem = (size_t)cap * (sizeof(float4) + 4 * sizeof(int));
     if (smem > 200 * 1024) {
         set_error("y2_nms_sort: %d boxes per image exceed the shared-memory staging", total);
         return Y2_EINVAL;
     }
-    static bool attr_done[16] = {false};
-    if (!attr_done[dev] && smem > 48 * 1024) {
+    int dev = 0;
+    Y2_CUDA_CHECK(cudaGetDevice(&dev));
+    static bool attr_done[64] = {false};
+    if (dev >= 0 && dev < 64 && !attr_done[dev] && smem > 48 * 1024) {
         Y2_CUDA_CHECK(cudaFuncSetAttribute(nms_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            200 * 1024));
         attr_done[dev] = true;
     }
-    if (classes > 65535 * 32 || batch > 65535) return Y2_EINVAL;
-    dim3 grid((unsigned)classes, (unsigned)batch);
-    nms_mark_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const float4 *>(boxes), probs, sc.cnt, total,
-                                             classes, thresh, cap);
-    Y2_LAUNCH_CHECK();
-    nms_clear_kernel<<<(int)blocks, 256, 0, st>>>(probs, n);
+    const long long pairs = (long long)batch * classes;
+    const int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;
+    long long blocks = (long long)sm_count() * per_sm;
+    if (blocks > pairs) blocks = pairs;
+    nms_mark_kernel<<<(int)blocks, 256, smem, st>>>(reinterpret_cast<const float4 *>(boxes), probs, cnt, batch, total,
+                                                    classes, thresh, cap);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
+}
+
+// Suppression only, for callers that own the candidate counters (the network's detection path: the box
+// decode counts while it writes the probabilities, the final pick reads "negative" as suppressed).
+extern "C" int y2_nms_mark(const float *boxes, float *probs, const int *cnt, int batch, int total, int classes,
+                           float thresh, y2_stream_t s)
+{
+    if (!boxes || !probs || !cnt || batch <= 0 || total <= 0 || classes <= 0) return Y2_EINVAL;
+    return nms_mark_launch(boxes, probs, cnt, batch, total, classes, thresh, to_stream(s));
+}
+
+// Stand-alone do_nms_sort: owns nothing between calls (the counters live for the duration of the call), so any
+// number of networks, streams and host threads may use it concurrently.
+extern "C" int y2_nms_sort(const float *boxes, float *probs, int batch, int total, int classes, float thresh,
+                           y2_stream_t s)
+{
+    if (!boxes || !probs || batch <= 0 || total <= 0 || classes <= 0) return Y2_EINVAL;
+    cudaStream_t st = to_stream(s);
+    const size_t need = (size_t)batch * classes;
+    int *cnt = nullptr;
+    Y2_CUDA_CHECK(cudaMalloc(&cnt, need * sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(cnt, 0, need * sizeof(int), st);
+    int rc = Y2_OK;
+    if (e != cudaSuccess) rc = Y2_ECUDA;
+    const long long n = (long long)batch * total * classes;
+    long long blocks = (n + 255) / 256;
+    const long long capb = (long long)sm_count() * 16;
+    if (blocks > capb) blocks = capb;
+    if (rc == Y2_OK) {
+        nms_count_kernel<<<(int)blocks, 256, 0, st>>>(probs, cnt, batch, total, classes);
+        if (cudaGetLastError() != cudaSuccess) rc = Y2_ECUDA;
+    }
+    if (rc == Y2_OK) rc = nms_mark_launch(boxes, probs, cnt, batch, total, classes, thresh, st);
+    if (rc == Y2_OK) {
+        nms_clear_kernel<<<(int)blocks, 256, 0, st>>>(probs, n);
+        if (cudaGetLastError() != cudaSuccess) rc = Y2_ECUDA;
+    }
+    cudaStreamSynchronize(st); // the counters are freed below
+    cudaFree(cnt);
+    return rc;
 }

@@ -263,7 +263,7 @@ __global__ void region_forward_flat_kernel(const float *__restrict__ in, float *
 __global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const float *__restrict__ biases,
                                          float *__restrict__ boxes, float *__restrict__ probs, int batch,
                                          int lw, int lh, int n, int classes, float img_w, float img_h,
-                                         float thresh, int only_objectness, int classfix)
+                                         float thresh, int only_objectness, int classfix, int *__restrict__ nz_count)
 {
     const int per_img = lw * lh * n;
     const int size = classes + 5;
@@ -305,6 +305,9 @@ __global__ void region_boxes_flat_kernel(const float *__restrict__ pred, const f
         float pv = (prob > thresh) ? prob : 0;
         if (j == 0 && only_objectness) pv = scale;
         probs[t] = pv;
+        // candidate counters of the NMS behind it (nms_count_kernel's job, folded in): non-zero entries per
+        // (image, class)
+        if (nz_count && pv != 0.f) atomicAdd(&nz_count[(bi / per_img) * classes + j], 1);
     }
 }
 
@@ -319,7 +322,8 @@ __global__ void __launch_bounds__(1024) region_boxes_tree_kernel(float *__restri
                                          float *__restrict__ boxes, float *__restrict__ probs, int batch,
                                          int lw, int lh, int n, int classes, float img_w, float img_h,
                                          float thresh, int only_objectness, int classfix,
-                                         const int *__restrict__ parent, const int *__restrict__ map, int map_n)
+                                         const int *__restrict__ parent, const int *__restrict__ map, int map_n,
+                                         int *__restrict__ nz_count)
 {
     extern __shared__ float sh[]; // [classes] raw, [classes] hierarchical
     float *sx = sh;
@@ -362,7 +366,10 @@ __global__ void __launch_bounds__(1024) region_boxes_tree_kernel(float *__restri
             for (int j = threadIdx.x; j < classes; j += blockDim.x) x[5 + j] = hv[j];
             for (int j = threadIdx.x; j < map_n; j += blockDim.x) {
                 const float prob = scale * hv[map[j]];
-                pr[j] = (prob > thresh) ? prob : 0;
+                const float pv = (prob > thresh) ? prob : 0;
+                pr[j] = pv;
+                if (nz_count && pv != 0.f && !(only_objectness && j == 0))
+                    atomicAdd(&nz_count[(bi / per_img) * out_classes + j], 1);
             }
         } else {
             int best = -1;
@@ -374,11 +381,17 @@ __global__ void __launch_bounds__(1024) region_boxes_tree_kernel(float *__restri
             for (int j = threadIdx.x; j < classes; j += blockDim.x) {
                 const float v = (j == found) ? hv[j] : 0.f;
                 x[5 + j] = v;
-                pr[j] = (scale > thresh) ? v : 0;
+                const float pv = (scale > thresh) ? v : 0;
+                pr[j] = pv;
+                if (nz_count && pv != 0.f && !(only_objectness && j == 0))
+                    atomicAdd(&nz_count[(bi / per_img) * out_classes + j], 1);
             }
         }
         if (threadIdx.x == 0) {
-            if (only_objectness) pr[0] = scale;
+            if (only_objectness) {
+                pr[0] = scale;
+                if (nz_count && scale != 0.f) atomicAdd(&nz_count[(bi / per_img) * out_classes], 1);
+            }
             const int an = index % n;
             const int cell = index / n;
             const int row = cell / lw;
@@ -417,7 +430,7 @@ __global__ void box_argmax_kernel(const float *__restrict__ probs, long long nbo
         float best = -FLT_MAX;
         int arg = 0x7fffffff;
         for (int j = lane; j < classes; j += 32) {
-            const float v = __ldg(p + j);
+            const float v = fmaxf(__ldg(p + j), 0.f);  // negative = suppressed by nms_mark_kernel = 0
             if (arg == 0x7fffffff || v > best) { best = v; arg = j; }
         }
 #pragma unroll
@@ -435,7 +448,8 @@ __global__ void box_argmax_kernel(const float *__restrict__ probs, long long nbo
 
 __global__ void collect_kernel(const float *__restrict__ boxes, const float *__restrict__ probs, int total,
                                int classes, float thresh, y2_det *__restrict__ det, int *__restrict__ count,
-                               int max_det, const float *__restrict__ pre_best, const int *__restrict__ pre_arg)
+                               int max_det, const float *__restrict__ pre_best, const int *__restrict__ pre_arg,
+                               int *__restrict__ nz_count)
 {
     extern __shared__ int s_flag[]; // [total] obj id or -1, then prefix
     float *s_prob = reinterpret_cast<float *>(s_flag + total);
@@ -452,13 +466,16 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
             continue;
         }
         const float *p = pb + (size_t)i * classes;
-        float best = p[0];
+        // probabilities are >= 0; a negative entry is one nms_mark_kernel suppressed (the reference has
+        // written 0 there, box.c:271): the fmaxf below is nms_clear_kernel folded into this scan
+        float best = fmaxf(p[0], 0.f);
         int arg = 0;
         int j = 1;
         if ((classes & 3) == 0 && ((uintptr_t)p & 15) == 0) {
             const float4 *p4 = reinterpret_cast<const float4 *>(p);
             for (int q = 0; q < classes / 4; ++q) {
-                const float4 v = __ldg(p4 + q);
+                float4 v = __ldg(p4 + q);
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                 if (q > 0 && v.x > best) { best = v.x; arg = 4 * q; }
                 if (v.y > best) { best = v.y; arg = 4 * q + 1; }
                 if (v.z > best) { best = v.z; arg = 4 * q + 2; }
@@ -467,7 +484,7 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
             j = classes;
         }
         for (; j < classes; ++j) {
-            const float v = __ldg(p + j);
+            const float v = fmaxf(__ldg(p + j), 0.f);
             if (v > best) { best = v; arg = j; }
         }
         s_flag[i] = (best > thresh) ? arg : -1;
@@ -509,6 +526,10 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
         __syncthreads();
     }
     if (threadIdx.x == 0) count[b] = s_running;
+    // hand the NMS candidate counters of this image back zeroed for the next batch (they are only ever
+    // incremented by the box decode, which runs before this kernel on the same stream)
+    if (nz_count)
+        for (int j = threadIdx.x; j < classes; j += blockDim.x) nz_count[(size_t)b * classes + j] = 0;
 }
 
 // classifier tail ------------------------------------------------------------------
@@ -606,10 +627,10 @@ extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw,
     return Y2_OK;
 }
 
-extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes, float *probs, int batch,
-                               int lw, int lh, int n, int classes, float img_w, float img_h, float thresh,
-                               int only_objectness, int classfix, int tree_n, const int *d_tree_parent,
-                               const int *d_map, int map_n, y2_stream_t s)
+extern "C" int y2_region_boxes_counted(float *pred, const float *d_biases, float *boxes, float *probs, int batch,
+                                       int lw, int lh, int n, int classes, float img_w, float img_h, float thresh,
+                                       int only_objectness, int classfix, int tree_n, const int *d_tree_parent,
+                                       const int *d_map, int map_n, int *nz_count, y2_stream_t s)
 {
     if (!pred || !d_biases || !boxes || !probs || batch <= 0) return Y2_EINVAL;
     const long long nboxes = (long long)batch * lw * lh * n;
@@ -619,11 +640,14 @@ extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes,
             return Y2_EINVAL;
         }
         const size_t smem = (size_t)classes * 2 * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done && smem > 48 * 1024) {
+        // the attribute is per device: a second network on another GPU needs it raised there too
+        static bool attr_done[64] = {false};
+        int dev = 0;
+        Y2_CUDA_CHECK(cudaGetDevice(&dev));
+        if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || !attr_done[dev])) {
             Y2_CUDA_CHECK(cudaFuncSetAttribute(region_boxes_tree_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
         if (smem > 200 * 1024) {
             set_error("y2_region_boxes: %d classes exceed the shared-memory staging", classes);
@@ -633,19 +657,36 @@ extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes,
         const int tree_threads = classes > 2048 ? 1024 : 256;
         region_boxes_tree_kernel<<<grid_cap(nboxes, 4), tree_threads, smem, to_stream(s)>>>(
             pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh, only_objectness,
-            classfix, d_tree_parent, d_map, map_n);
+            classfix, d_tree_parent, d_map, map_n, nz_count);
     } else {
         const long long total = nboxes * classes;
         region_boxes_flat_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, to_stream(s)>>>(
             pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh, only_objectness,
-            classfix);
+            classfix, nz_count);
     }
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }
 
-extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int total, int classes,
-                          float thresh, y2_det *det, int *count, int max_det, y2_stream_t s)
+extern "C" int y2_region_boxes(float *pred, const float *d_biases, float *boxes, float *probs, int batch,
+                               int lw, int lh, int n, int classes, float img_w, float img_h, float thresh,
+                               int only_objectness, int classfix, int tree_n, const int *d_tree_parent,
+                               const int *d_map, int map_n, y2_stream_t s)
+{
+    return y2_region_boxes_counted(pred, d_biases, boxes, probs, batch, lw, lh, n, classes, img_w, img_h, thresh,
+                                   only_objectness, classfix, tree_n, d_tree_parent, d_map, map_n, nullptr, s);
+}
+
+// ws: caller-owned scratch of y2_collect_ws_bytes(batch, total, classes) bytes (per-box maxima of wide class
+// rows), nz_count: the NMS candidate counters to hand back zeroed (or NULL).
+extern "C" size_t y2_collect_ws_bytes(int batch, int total, int classes)
+{
+    return classes >= 256 ? (size_t)batch * total * 8 : 0;
+}
+
+extern "C" int y2_collect_ws(const float *boxes, const float *probs, int batch, int total, int classes,
+                             float thresh, y2_det *det, int *count, int max_det, void *ws, int *nz_count,
+                             y2_stream_t s)
 {
     if (!boxes || !probs || !det || !count || batch <= 0 || total <= 0) return Y2_EINVAL;
     const size_t smem = (size_t)total * 8;
@@ -656,25 +697,9 @@ extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int
     const float *pre_best = nullptr;
     const int *pre_arg = nullptr;
     if (classes >= 256) {
-        // per-device scratch for the per-box maxima (grown on demand, never shrunk)
-        struct Scratch {
-            void *buf = nullptr;
-            size_t cap = 0;
-        };
-        static thread_local Scratch scratch[16];
-        int dev = 0;
-        Y2_CUDA_CHECK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 16) return Y2_EINVAL;
-        Scratch &sc = scratch[dev];
+        if (!ws) return Y2_EINVAL;
         const size_t nb = (size_t)batch * total;
-        if (sc.cap < nb * 8) {
-            if (sc.buf) cudaFree(sc.buf);
-            sc.buf = nullptr;
-            sc.cap = 0;
-            Y2_CUDA_CHECK(cudaMalloc(&sc.buf, nb * 8));
-            sc.cap = nb * 8;
-        }
-        float *best = (float *)sc.buf;
+        float *best = (float *)ws;
         int *arg = (int *)(best + nb);
         box_argmax_kernel<<<grid_cap((long long)(nb * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(
             probs, (long long)nb, classes, best, arg);
@@ -683,9 +708,24 @@ extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int
         pre_arg = arg;
     }
     collect_kernel<<<batch, 256, smem, to_stream(s)>>>(boxes, probs, total, classes, thresh, det, count,
-                                                       max_det, pre_best, pre_arg);
+                                                       max_det, pre_best, pre_arg, nz_count);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
+}
+
+// stand-alone form: the scratch lives for the duration of the call
+extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int total, int classes,
+                          float thresh, y2_det *det, int *count, int max_det, y2_stream_t s)
+{
+    void *ws = nullptr;
+    const size_t bytes = y2_collect_ws_bytes(batch, total, classes);
+    if (bytes) Y2_CUDA_CHECK(cudaMalloc(&ws, bytes));
+    const int rc = y2_collect_ws(boxes, probs, batch, total, classes, thresh, det, count, max_det, ws, nullptr, s);
+    if (ws) {
+        cudaStreamSynchronize(to_stream(s));
+        cudaFree(ws);
+    }
+    return rc;
 }
 
 extern "C" int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs, y2_stream_t s)

@@ -4,7 +4,11 @@
 // cudaMalloc+cudaFree of network_kernels.cu:392-407.
 #include "y2_common.cuh"
 
+#include <ctype.h>
+#include <sched.h>
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace y2 {
@@ -34,9 +38,54 @@ int sm_count()
     return cached[dev];
 }
 
+// CPUs next to a GPU: /sys/bus/pci/devices/<bus id>/local_cpulist ("0-31,64-95"), intersected with the CPUs this
+// thread may run on.  False when the topology is not visible (containers without sysfs) or the intersection is empty.
+static bool device_local_cpus(int dev, cpu_set_t *out)
+{
+    char bus[64] = "";
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    char line[1024] = "";
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    cpu_set_t allowed, local;
+    CPU_ZERO(&local);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return false;
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int n = sscanf(tok, "%d-%d", &lo, &hi);
+        if (n < 1) continue;
+        if (n == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+            if (c >= 0 && CPU_ISSET(c, &allowed)) CPU_SET(c, &local);
+    }
+    if (CPU_COUNT(&local) == 0) return false;
+    *out = local;
+    return true;
+}
+
 } // namespace y2
 
 using namespace y2;
+
+// Keep the calling host thread on the CPUs next to `dev` (its NUMA node): the pinned staging buffers it allocates
+// afterwards land in that node's memory and its H2D copies do not cross the socket interconnect.  Returns the
+// number of CPUs in the new mask, 0 when the topology is unknown (nothing changed).
+extern "C" int y2_bind_thread_to_device(int dev)
+{
+    cpu_set_t local;
+    if (getenv("Y2_NO_NUMA_BIND") || !device_local_cpus(dev, &local)) return 0;
+    if (sched_setaffinity(0, sizeof(local), &local) != 0) return 0;
+    return CPU_COUNT(&local);
+}
 
 extern "C" const char *y2_last_error(void) { return g_err; }
 extern "C" const char *y2_version(void) { return "yolo2-b200 0.1 (sm_100a)"; }
@@ -50,6 +99,12 @@ extern "C" int y2_device_count(int *count)
 extern "C" int y2_set_device(int dev)
 {
     Y2_CUDA_CHECK(cudaSetDevice(dev));
+    return Y2_OK;
+}
+extern "C" int y2_get_device(int *dev)
+{
+    if (!dev) return Y2_EINVAL;
+    Y2_CUDA_CHECK(cudaGetDevice(dev));
     return Y2_OK;
 }
 extern "C" int y2_malloc(void **dptr, size_t bytes)
@@ -71,7 +126,18 @@ extern "C" int y2_memset(void *dptr, int value, size_t bytes, y2_stream_t s)
 extern "C" int y2_host_alloc(void **hptr, size_t bytes)
 {
     if (!hptr) return Y2_EINVAL;
-    Y2_CUDA_CHECK(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    // page-lock the buffer from a CPU of the current device's NUMA node (first touch decides where the pages live);
+    // the caller's affinity mask is restored afterwards
+    int dev = 0;
+    cpu_set_t saved, local;
+    bool moved = false;
+    if (bytes >= (1u << 20) && !getenv("Y2_NO_NUMA_BIND") && cudaGetDevice(&dev) == cudaSuccess &&
+        sched_getaffinity(0, sizeof(saved), &saved) == 0 && device_local_cpus(dev, &local))
+        moved = sched_setaffinity(0, sizeof(local), &local) == 0;
+    const unsigned flags = getenv("Y2_STAGING_WC") && bytes >= (1u << 20) ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+    const cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 16, flags);
+    if (moved) sched_setaffinity(0, sizeof(saved), &saved);
+    Y2_CUDA_CHECK(e);
     return Y2_OK;
 }
 extern "C" int y2_host_free(void *hptr)

@@ -415,6 +415,27 @@ extern "C" int y2_stem_prepare(void)
     return Y2_OK;
 }
 
+// column tile of the first-layer kernel: equal tiles of at most 124 image columns, a multiple of 4 wide
+static int stem_tile_cols(int w)
+{
+    const int ow = w / 2;
+    const int wmax = kStemMaxP - 4;
+    const int nx = (2 * ow + wmax - 1) / wmax;
+    int wt_cols = (2 * ow + nx - 1) / nx;
+    return (wt_cols + 3) / 4 * 4;
+}
+
+static int stem_u8_boxw(int w) { return ((stem_tile_cols(w) + 3) * 3 + 15 + 15) / 16 * 16; }
+
+// the image sizes y2_stem_conv_pool_u8 accepts (callers fall back to the resize / float path otherwise)
+extern "C" int y2_stem_u8_supported(int h, int w)
+{
+    if (h < 2 || w < 2) return 0;
+    const int boxw = stem_u8_boxw(w);
+    return (3 * w) % 16 == 0 && boxw <= 3 * w && kStemRows + 2 <= h &&
+           (size_t)(kStemRows + 2) * boxw <= sizeof(StemSmem::Raw);
+}
+
 // in: fp32 planar [B][c][h][w] when !u8, uint8 interleaved [B][h][w][3] when u8
 static int stem_launch(const void *in, bool u8, int batch, int c, int h, int w, const void *wt, int npad,
                        const float *alpha, const float *beta, int act, void *out, int out_cs, y2_stream_t s)
@@ -435,10 +456,7 @@ static int stem_launch(const void *in, bool u8, int batch, int c, int h, int w, 
     p.oh = h / 2;
     p.ow = w / 2;
     // equal column tiles of at most 124 image columns, a multiple of 4 wide (16-byte aligned TMA boxes)
-    const int wmax = kStemMaxP - 4;
-    const int nx = (2 * p.ow + wmax - 1) / wmax;
-    int wt_cols = (2 * p.ow + nx - 1) / nx;
-    wt_cols = (wt_cols + 3) / 4 * 4;
+    const int wt_cols = stem_tile_cols(w);
     p.wt = wt_cols;
     p.tiles_x = (2 * p.ow + wt_cols - 1) / wt_cols;
     p.tiles_y = (p.oh + kStemRows / 2 - 1) / (kStemRows / 2);
@@ -462,9 +480,8 @@ static int stem_launch(const void *in, bool u8, int batch, int c, int h, int w, 
     EncodeTiledFn enc = get_encode_fn();
     if (u8) {
         // bytes (x0 - 1)*3 .. (x0 + wt + 2)*3 of a row, from the 16-byte boundary below the first one
-        p.boxw = ((wt_cols + 3) * 3 + 15 + 15) / 16 * 16;
-        if (!enc || c != 3 || (3 * w) % 16 || ((uintptr_t)in & 15) || p.boxw > 3 * w || kStemRows + 2 > h ||
-            (size_t)(kStemRows + 2) * p.boxw > sizeof(StemSmem::Raw)) {
+        p.boxw = stem_u8_boxw(w);
+        if (!enc || c != 3 || ((uintptr_t)in & 15) || !y2_stem_u8_supported(h, w)) {
             set_error("y2_stem_conv_pool_u8: needs 3 channels, a width that is a multiple of 16 and at least %d rows "
                       "(h=%d w=%d c=%d)", kStemRows + 2, h, w, c);
             return Y2_EINVAL;

@@ -67,7 +67,20 @@ static void scratch_reserve(scratch_t *s, size_t bytes)
     }
 }
 
-static __thread scratch_t g_pred, g_boxes, g_probs;
+/* per host thread AND per device: a thread that drives several GPUs (Detector objects on different
+ * gpu_ids) must not hand one device's scratch to another */
+#define Y2_MAX_DEV 16
+static __thread scratch_t g_pred_d[Y2_MAX_DEV], g_boxes_d[Y2_MAX_DEV], g_probs_d[Y2_MAX_DEV];
+static int cur_dev(void)
+{
+    int dev = 0;
+    Y2_CHECK(y2_get_device(&dev));
+    if (dev < 0 || dev >= Y2_MAX_DEV) error("device index beyond the scratch table");
+    return dev;
+}
+#define g_pred g_pred_d[cur_dev()]
+#define g_boxes g_boxes_d[cur_dev()]
+#define g_probs g_probs_d[cur_dev()]
 
 /* region_layer.c:328-379.  Reads l.output on the HOST (callers may have replaced it, e.g. the
  * 3-frame mean of yolo_v2_class.cpp:208-213), decodes on the device, writes the caller's arrays.
@@ -126,15 +139,22 @@ void do_nms_sort(box *boxes, float **probs, int total, int classes, float thresh
         memcpy(probs[j], (float *)g_probs.host + (size_t)j * classes, (size_t)classes * sizeof(float));
 }
 
-/* box.c:279-297 is only reached from demo.c / validate_detector_recall, outside the hot path */
+/* box.c:279-297, the unsorted variant demo.c and validate_detector_recall call */
 void do_nms(box *boxes, float **probs, int total, int classes, float thresh)
 {
-    (void)boxes;
-    (void)probs;
-    (void)total;
-    (void)classes;
-    (void)thresh;
-    error("do_nms (unsorted variant) is outside the B200 hot path; use do_nms_sort");
+    if (total <= 0 || classes <= 0) return;
+    scratch_reserve(&g_boxes, (size_t)total * 4 * sizeof(float));
+    scratch_reserve(&g_probs, (size_t)total * classes * sizeof(float));
+    memcpy(g_boxes.host, boxes, (size_t)total * sizeof(box));
+    for (int j = 0; j < total; ++j)
+        memcpy((float *)g_probs.host + (size_t)j * classes, probs[j], (size_t)classes * sizeof(float));
+    Y2_CHECK(y2_memcpy_h2d(g_boxes.dev, g_boxes.host, (size_t)total * 4 * sizeof(float), 0));
+    Y2_CHECK(y2_memcpy_h2d(g_probs.dev, g_probs.host, (size_t)total * classes * sizeof(float), 0));
+    Y2_CHECK(y2_nms_unsorted((const float *)g_boxes.dev, (float *)g_probs.dev, total, classes, thresh, 0));
+    Y2_CHECK(y2_memcpy_d2h(g_probs.host, g_probs.dev, (size_t)total * classes * sizeof(float), 0));
+    Y2_CHECK(y2_stream_sync(0));
+    for (int j = 0; j < total; ++j)
+        memcpy(probs[j], (float *)g_probs.host + (size_t)j * classes, (size_t)classes * sizeof(float));
 }
 
 /* ---- batched, device-resident detection (extension) -------------------------------------------- */
@@ -145,15 +165,31 @@ static layer *region_of(network net)
     return l;
 }
 
+/* get_region_boxes + do_nms_sort + the final pick for the whole batch on the network's stream: the decode
+ * counts the NMS candidates while it writes the probabilities, the suppression pass marks losers negative
+ * and the pick reads negative as zero (3 launches; the counters and scratch are the network's own) */
+static void detect_tail(y2_net_rt *rt, layer *l, float thresh, float nms, y2_det *det_dev, int *cnt_dev, int det_cap)
+{
+    y2_layer_rt *r = (y2_layer_rt *)l->b200;
+    const int B = l->batch;
+    const int total = l->w * l->h * l->n;
+    Y2_CHECK(y2_region_boxes_counted((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
+                                     l->classes, 1.f, 1.f, thresh, 0, l->classfix,
+                                     l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0,
+                                     r->nms_cnt_dev, rt->stream));
+    if (nms > 0)
+        Y2_CHECK(y2_nms_mark(r->boxes_dev, r->probs_dev, r->nms_cnt_dev, B, total, l->classes, nms, rt->stream));
+    Y2_CHECK(y2_collect_ws(r->boxes_dev, r->probs_dev, B, total, l->classes, thresh, det_dev, cnt_dev, det_cap,
+                           r->collect_ws, r->nms_cnt_dev, rt->stream));
+}
+
 void network_detect_device(network net, float thresh, float nms, y2_detection *dets, int *counts, int max_det)
 {
     y2_net_rt *rt = y2_rt(net);
     if (!rt) error("network_detect: network has no device plan");
     Y2_CHECK(y2_set_device(rt->device));
     layer *l = region_of(net);
-    y2_layer_rt *r = (y2_layer_rt *)l->b200;
     const int B = net.batch;
-    const int total = l->w * l->h * l->n;
     if (rt->det_cap < max_det || rt->det_batch < B) {
         y2_free(rt->det_dev);
         y2_host_free(rt->det_pinned);
@@ -167,13 +203,7 @@ void network_detect_device(network net, float thresh, float nms, y2_detection *d
         Y2_CHECK(y2_malloc((void **)&rt->cnt_dev, (size_t)rt->det_batch * sizeof(int)));
         Y2_CHECK(y2_host_alloc((void **)&rt->cnt_pinned, (size_t)rt->det_batch * sizeof(int)));
     }
-    Y2_CHECK(y2_region_boxes((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
-                             l->classes, 1.f, 1.f, thresh, 0, l->classfix,
-                             l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0, rt->stream));
-    if (nms > 0)
-        Y2_CHECK(y2_nms_sort(r->boxes_dev, r->probs_dev, B, total, l->classes, nms, rt->stream));
-    Y2_CHECK(y2_collect(r->boxes_dev, r->probs_dev, B, total, l->classes, thresh, rt->det_dev, rt->cnt_dev,
-                        rt->det_cap, rt->stream));
+    detect_tail(rt, l, thresh, nms, rt->det_dev, rt->cnt_dev, rt->det_cap);
     Y2_CHECK(y2_memcpy_d2h(rt->cnt_pinned, rt->cnt_dev, (size_t)B * sizeof(int), rt->stream));
     Y2_CHECK(y2_memcpy_d2h(rt->det_pinned, rt->det_dev, (size_t)B * rt->det_cap * sizeof(y2_det), rt->stream));
     Y2_CHECK(y2_stream_sync(rt->stream));
@@ -254,9 +284,9 @@ static void pipe_init_u8(network net)
     if (rt->pipe[0].in_u8_dev) return;
     layer *l0 = &net.layers[0];
     y2_layer_rt *r0 = (y2_layer_rt *)l0->b200;
-    if (!r0 || !r0->stem_fused || l0->c != 3)
+    if (!r0 || !r0->stem_fused || l0->c != 3 || !y2_stem_u8_supported(net.h, net.w))
         error("uint8 input needs a network whose first layer runs the fused first-layer kernel (3x3 conv over 3 "
-              "channels followed by a 2x2/2 maxpool)");
+              "channels followed by a 2x2/2 maxpool) and a width that is a multiple of 16; use the frames entry");
     const size_t bytes = (size_t)rt->cap_batch * net.h * net.w * 3;
     for (int s = 0; s < 2; ++s) {
         Y2_CHECK(y2_malloc((void **)&rt->pipe[s].in_u8_dev, bytes));
@@ -299,9 +329,7 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
     const int s = (rt->pipe_head + rt->pipe_inflight) & 1;
     struct y2_pipe_slot *ps = &rt->pipe[s];
     layer *l = region_of(net);
-    y2_layer_rt *r = (y2_layer_rt *)l->b200;
     const int B = net.batch;
-    const int total = l->w * l->h * l->n;
     pipe_reserve_dets(rt, s, B, max_det);
     /* pageable caller memory is staged through the slot's pinned buffer (a host copy; fill the slot's
      * staging buffer directly to avoid it) */
@@ -332,12 +360,7 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
     } else {
         y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
     }
-    Y2_CHECK(y2_region_boxes((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
-                             l->classes, 1.f, 1.f, thresh, 0, l->classfix,
-                             l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0, rt->stream));
-    if (nms > 0) Y2_CHECK(y2_nms_sort(r->boxes_dev, r->probs_dev, B, total, l->classes, nms, rt->stream));
-    Y2_CHECK(y2_collect(r->boxes_dev, r->probs_dev, B, total, l->classes, thresh, ps->det_dev, ps->cnt_dev,
-                        ps->det_cap, rt->stream));
+    detect_tail(rt, l, thresh, nms, ps->det_dev, ps->cnt_dev, ps->det_cap);
     Y2_CHECK(y2_memcpy_d2h(ps->cnt_pinned, ps->cnt_dev, (size_t)B * sizeof(int), rt->stream));
     Y2_CHECK(y2_memcpy_d2h(ps->det_pinned, ps->det_dev, (size_t)B * ps->det_cap * sizeof(y2_det), rt->stream));
     Y2_CHECK(y2_event_record(ps->ev_done, rt->stream));
@@ -396,7 +419,7 @@ int network_detect_submit_frames(network net, const unsigned char *frames_hwc, i
     y2_net_rt *rt = y2_rt(net);
     if (!rt) error("network_detect_submit_frames: network has no device plan");
     y2_layer_rt *r0 = (y2_layer_rt *)net.layers[0].b200;
-    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3)
+    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3 && y2_stem_u8_supported(net.h, net.w))
         return submit_common(net, frames_hwc, 1, 0, 0, thresh, nms, max_det);
     return submit_common(net, frames_hwc, 2, frame_w, frame_h, thresh, nms, max_det);
 }
@@ -407,7 +430,7 @@ unsigned char *network_pipeline_staging_frames(network net, int slot, int frame_
     if (!rt || slot < 0 || slot > 1 || frame_w <= 0 || frame_h <= 0)
         error("network_pipeline_staging_frames: bad slot, frame size or unplanned network");
     y2_layer_rt *r0 = (y2_layer_rt *)net.layers[0].b200;
-    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3)
+    if (frame_w == net.w && frame_h == net.h && r0 && r0->stem_fused && net.c == 3 && y2_stem_u8_supported(net.h, net.w))
         return network_pipeline_staging_u8(net, slot);
     pipe_init(net);
     Y2_CHECK(y2_set_device(rt->device));

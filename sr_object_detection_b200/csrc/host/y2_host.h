@@ -56,6 +56,9 @@ typedef struct y2_layer_rt {
     float *biases_dev;
     int *tree_parent_dev, *group_size_dev, *group_offset_dev, *map_dev;
     int probs_classes;
+    int *nms_cnt_dev;   /* [B][classes] NMS candidate counters, zero between batches (owned per network: two
+                           networks in flight on one GPU must not share them) */
+    void *collect_ws;   /* per-box maxima scratch of the final pick (wide class rows) */
     /* profiling */
     y2_event_t ev0, ev1;
 } y2_layer_rt;

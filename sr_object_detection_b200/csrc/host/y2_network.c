@@ -50,6 +50,7 @@ float *cuda_make_array(float *x, size_t n)
         Y2_CHECK(y2_stream_sync(0));
     } else {
         Y2_CHECK(y2_memset(d, 0, n * sizeof(float), 0));
+        Y2_CHECK(y2_stream_sync(0));
     }
     return (float *)d;
 }
@@ -147,7 +148,6 @@ static float rand_uniform_pm1(uint32_t *st)
 layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, int stride, int padding,
                                ACTIVATION activation, int batch_normalize, int binary, int xnor, int adam)
 {
-    (void)adam;
     layer l;
     memset(&l, 0, sizeof(l));
     l.type = CONVOLUTIONAL;
@@ -166,6 +166,11 @@ layer make_convolutional_layer(int batch, int h, int w, int c, int n, int size, 
     size_t nw = (size_t)c * n * size * size;
     l.weights = (float *)calloc(nw, sizeof(float));
     l.biases = (float *)calloc(n, sizeof(float));
+    if (adam) { /* convolutional_layer.c:226-231: moments travel with the checkpoint */
+        l.adam = 1;
+        l.m = (float *)calloc(nw, sizeof(float));
+        l.v = (float *)calloc(nw, sizeof(float));
+    }
     /* same init scale as convolutional_layer.c:207-208 (values differ: own generator) */
     float scale = sqrtf(2.f / (size * size * c));
     uint32_t st = 0x9E3779B9u ^ (uint32_t)(n * 131 + c * 31 + size);
@@ -409,6 +414,8 @@ static void *dev_alloc_zero(size_t bytes)
     void *d = 0;
     Y2_CHECK(y2_malloc(&d, bytes));
     Y2_CHECK(y2_memset(d, 0, bytes, 0));
+    /* the network's own stream is non-blocking: nothing orders it behind the legacy stream's memset */
+    Y2_CHECK(y2_stream_sync(0));
     return d;
 }
 
@@ -448,6 +455,8 @@ static void free_layer_rt(layer *l)
     y2_free(r->boxes_dev);
     y2_free(r->probs_dev);
     y2_free(r->biases_dev);
+    y2_free(r->nms_cnt_dev);
+    y2_free(r->collect_ws);
     y2_free(r->tree_parent_dev);
     y2_free(r->group_size_dev);
     y2_free(r->group_offset_dev);
@@ -959,6 +968,9 @@ void y2_plan_network(network *net)
             Y2_CHECK(y2_malloc((void **)&r->boxes_dev, (size_t)B * total * 4 * sizeof(float)));
             Y2_CHECK(y2_malloc((void **)&r->probs_dev, (size_t)B * total * l->classes * sizeof(float)));
             r->biases_dev = (float *)dev_upload(l->biases, (size_t)l->n * 2 * sizeof(float));
+            r->nms_cnt_dev = (int *)dev_alloc_zero((size_t)B * l->classes * sizeof(int));
+            if (y2_collect_ws_bytes(B, (int)total, l->classes))
+                Y2_CHECK(y2_malloc(&r->collect_ws, y2_collect_ws_bytes(B, (int)total, l->classes)));
             if (l->softmax_tree) {
                 tree *t = l->softmax_tree;
                 if (t->n != l->classes) unsupported(i, "softmax tree whose size differs from classes");
@@ -1266,6 +1278,12 @@ float *network_input_staging(network net)
     return rt ? rt->in_pinned : 0;
 }
 
+float *network_input_device(network net)
+{
+    y2_net_rt *rt = y2_rt(net);
+    return rt ? rt->in_dev : 0;
+}
+
 void network_upload_input(network net, const float *input)
 {
     ensure_ready(net);
@@ -1502,6 +1520,8 @@ void free_layer(layer l)
     free(l.weights);
     free(l.rolling_mean);
     free(l.rolling_variance);
+    free(l.m);
+    free(l.v);
     free(l.input_layers);
     free(l.input_sizes);
     free(l.output);

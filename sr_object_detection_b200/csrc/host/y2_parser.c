@@ -432,6 +432,10 @@ static void load_convolutional_weights(layer *l, FILE *fp)
         read_floats(l->rolling_variance, l->n, fp);
     }
     read_floats(l->weights, num, fp);
+    if (l->adam) { /* parser.c:992-995 */
+        read_floats(l->m, num, fp);
+        read_floats(l->v, num, fp);
+    }
     if (l->flipped) transpose_matrix(l->weights, l->c * l->size * l->size, l->n);
     if (gpu_index >= 0 && l->b200) y2_push_convolutional_layer(l);
 }
@@ -491,6 +495,10 @@ void save_weights_upto(network net, char *filename, int cutoff)
             fwrite(l.rolling_variance, sizeof(float), l.n, fp);
         }
         fwrite(l.weights, sizeof(float), num, fp);
+        if (l.adam) { /* parser.c:788-791 */
+            fwrite(l.m, sizeof(float), num, fp);
+            fwrite(l.v, sizeof(float), num, fp);
+        }
     }
     fclose(fp);
 }

@@ -59,10 +59,10 @@ Layer._fields_ = [
     ("jitter", C.c_float), ("thresh", C.c_float),
     ("coord_scale", C.c_float), ("object_scale", C.c_float), ("noobject_scale", C.c_float),
     ("class_scale", C.c_float), ("temperature", C.c_float), ("dot", C.c_float),
-    ("dontload", C.c_int), ("dontloadscales", C.c_int),
+    ("dontload", C.c_int), ("dontloadscales", C.c_int), ("adam", C.c_int),
     ("softmax_tree", C.POINTER(Tree)), ("map", _ip), ("cost", _fp),
     ("biases", _fp), ("scales", _fp), ("weights", _fp), ("rolling_mean", _fp),
-    ("rolling_variance", _fp), ("input_layers", _ip), ("input_sizes", _ip),
+    ("rolling_variance", _fp), ("m", _fp), ("v", _fp), ("input_layers", _ip), ("input_sizes", _ip),
     ("output", _fp), ("workspace_size", C.c_size_t),
     ("output_gpu", _fp), ("weights_gpu", _fp), ("biases_gpu", _fp), ("scales_gpu", _fp),
     ("b200", C.c_void_p),
@@ -163,6 +163,8 @@ def lib() -> C.CDLL:
         "network_profile_layers": (i, [Network, fp, i]),
         "network_set_eager": (None, [Network, i]),
         "network_input_staging": (fp, [Network]),
+        "network_input_device": (C.c_void_p, [Network]),
+        "y2_bind_thread_to_device": (i, [i]),
         "resize_image": (Image, [Image, i, i]),
         "free_image": (None, [Image]),
         "letterbox_image": (Image, [Image, i, i]),

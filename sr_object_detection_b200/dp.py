@@ -64,3 +64,37 @@ def detect_sharded(images: np.ndarray, detect: Callable[[np.ndarray], Sequence],
     if len(local) != hi - lo:
         raise RuntimeError(f"rank {rank}: detector returned {len(local)} lists for {hi - lo} images")
     return gather_detections(local, group=group, dst=dst)
+
+
+def gather_detection_arrays(dets: np.ndarray, counts: np.ndarray, max_det: int, cap: int, group=None,
+                            dst: int = 0):
+    """Fixed-size gather of one batch's detections for the steady-state loop (no pickling, one collective):
+    `dets` is the flat record array network_detect_wait filled ([B * max_det] records of the 28-byte
+    `y2_detection`), `counts` the per-image totals.  Every rank sends `counts` and the first `cap` records of
+    each of its images; `dst` receives them in rank order = global image order.
+
+    Returns on `dst` (dets_all [world * B][cap] records, counts_all [world * B], n_truncated) where n_truncated is
+    the number of images that had more than `cap` detections (their lists are cut at `cap`, exactly as `max_det`
+    cuts them in the C API); None on the other ranks.  Without a process group it returns the local arrays."""
+    import torch
+    import torch.distributed as dist
+
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    B = counts.shape[0]
+    rec = dets.dtype.itemsize
+    cap = min(cap, max_det)
+    rows = dets.reshape(B, max_det)[:, :cap]
+    if not (dist.is_available() and dist.is_initialized()):
+        return np.ascontiguousarray(rows), counts.copy(), int((counts > cap).sum())
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    msg = torch.empty(B * 4 + B * cap * rec, dtype=torch.uint8)
+    m = msg.numpy()
+    m[:B * 4] = counts.view(np.uint8)
+    m[B * 4:] = np.ascontiguousarray(rows).view(np.uint8).reshape(-1)
+    bucket = [torch.empty_like(msg) for _ in range(world)] if rank == dst else None
+    dist.gather(msg, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    all_counts = np.concatenate([b.numpy()[:B * 4].view(np.int32) for b in bucket])
+    all_dets = np.concatenate([b.numpy()[B * 4:].view(dets.dtype).reshape(B, cap) for b in bucket])
+    return all_dets, all_counts, int((all_counts > cap).sum())

@@ -142,6 +142,21 @@ def mini_dense_cfg(batch=2, w=64, h=64, classes=4, num=3):
     return s + _region(anchors, classes, num)
 
 
+def region_only_cfg(batch, cells_w, cells_h, anchors, classes, num, extra=""):
+    """A network that is ONLY the region layer over a [num*(5+classes)][cells_h][cells_w] input: lets the CPU
+    checkers decode a given head output without allocating the whole detector (parse_region asserts
+    l.outputs == inputs, parser.c:243, which holds for exactly this input shape)."""
+    return _net(batch, cells_w, cells_h, c=num * (classes + 5)) + _region(anchors, classes, num, extra)
+
+
+REGION_PARAMS = {  # anchors, classes, num of the detector cfgs above
+    "tiny-yolo-voc": (TINY_VOC_ANCHORS, 20, 5),
+    "yolo-voc": (VOC_ANCHORS, 20, 5),
+    "yolo": (COCO_ANCHORS, 80, 5),
+    "yolo9000": (Y9K_ANCHORS, 9418, 3),
+}
+
+
 CFGS = {
     "mini-dense": mini_dense_cfg,
     "mini-yolo": mini_yolo_cfg,
@@ -196,10 +211,16 @@ def conv_specs_from_cfg(cfg_text: str) -> list[ConvSpec]:
     return specs
 
 
-def write_weights(path: str | Path, cfg_text: str, seed: int = 1234) -> int:
+def write_weights(path: str | Path, cfg_text: str, seed: int = 1234, head_gain: float = 1.0) -> int:
     """Seeded synthetic `.weights` in the v0.1 layout read by load_weights_upto
     (parser.c:1009-1082): int32 major, minor, revision, seen; per conv: biases, [scales,
-    rolling_mean, rolling_variance], weights[n][c][k][k]."""
+    rolling_mean, rolling_variance], weights[n][c][k][k].
+
+    head_gain multiplies the weights of the LAST convolution (the detection head).  With the plain
+    init every box of a random network scores objectness ~0.5 x class ~1/classes, far below the
+    detector's 0.24 threshold, so decode and NMS would run on an empty candidate set; a gain of a few
+    units spreads the head's logits so that a few per cent of the boxes clear the threshold and NMS
+    has overlapping candidates to work on."""
     specs = conv_specs_from_cfg(cfg_text)
     total = 0
     with open(path, "wb") as f:
@@ -217,6 +238,8 @@ def write_weights(path: str | Path, cfg_text: str, seed: int = 1234) -> int:
                 total += 3 * n
             s = np.sqrt(2.0 / (k * k * c))
             w = rng.uniform(-s, s, n * c * k * k).astype(np.float32)
+            if head_gain != 1.0 and li == len(specs) - 1:
+                w = (w * np.float32(head_gain)).astype(np.float32)
             f.write(w.tobytes())
             total += n + w.size
     return total

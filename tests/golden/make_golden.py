@@ -180,6 +180,25 @@ def main():
         im.tofile(t / "im.f32")
         subprocess.run([str(REF), "resize", "im.f32", "3", "20", "30", "13", "17", "out.f32"], cwd=t, check=True)
         np.savez_compressed(OUT / "resize.npz", image=im, resized=f32(t / "out.f32").reshape(3, 13, 17))
+    # 3b. do_nms (the unsorted variant, box.c:279-297) on the decoded boxes of a region case plus exact ties
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        d = np.load(OUT / "region_voc_7_lowthresh.npz")
+        boxes = d["boxes"].reshape(2, -1, 4)[0].copy()
+        probs = d["probs_pre"].reshape(2, boxes.shape[0], -1)[0].copy()
+        probs[5] = probs[6]            # equal rows: the `<` of box.c:290 decides
+        boxes[6] = boxes[5]
+        probs[40:60, 3] = 0.5          # ties inside a class
+        boxes.tofile(t / "b.f32")
+        probs.tofile(t / "p.f32")
+        for tag, thr in (("a", 0.4), ("b", 0.1)):
+            subprocess.run([str(REF), "donms", "b.f32", "p.f32", str(boxes.shape[0]), str(probs.shape[1]), str(thr),
+                            f"o{tag}.f32"], cwd=t, check=True)
+        np.savez_compressed(OUT / "do_nms.npz", boxes=boxes, probs=probs, thresh_a=np.float32(0.4),
+                            out_a=f32(t / "oa.f32").reshape(probs.shape), thresh_b=np.float32(0.1),
+                            out_b=f32(t / "ob.f32").reshape(probs.shape))
+        print("do_nms: nonzero before/after", int((probs != 0).sum()), int((f32(t / "oa.f32") != 0).sum()),
+              int((f32(t / "ob.f32") != 0).sum()))
     # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
     classifier_front()
     # 5. parser tables, incl. the reference's own cfg files

@@ -74,3 +74,23 @@ def test_toy_network_layers_match_reference_golden(tmp_path, monkeypatch, name):
     ref_out = d["output"].reshape(out.shape)
     assert float(np.abs(out - ref_out).max() / np.abs(ref_out).max()) <= ACT_TOL
     dn.free_network(net)
+
+
+def test_do_nms_unsorted_bit_exact_vs_reference_golden():
+    """do_nms (box.c:279-297) through the drop-in entry: caller-owned boxes[total], probs[total][classes]"""
+    import ctypes as C
+    d = np.load(GOLDEN / "do_nms.npz")
+    lib = dn.lib()
+    dn.set_gpu_index(0)
+    lib.cuda_set_device(0)
+    fp = C.POINTER(C.c_float)
+    lib.do_nms.restype = None
+    lib.do_nms.argtypes = [C.POINTER(dn.Box), C.POINTER(fp), C.c_int, C.c_int, C.c_float]
+    total, classes = d["probs"].shape
+    for tag in ("a", "b"):
+        boxes = np.ascontiguousarray(d["boxes"], np.float32).copy()
+        probs = np.ascontiguousarray(d["probs"], np.float32).copy()
+        rows = (fp * total)(*[C.cast(probs.ctypes.data + j * classes * 4, fp) for j in range(total)])
+        lib.do_nms(boxes.ctypes.data_as(C.POINTER(dn.Box)), rows, total, classes, float(d[f"thresh_{tag}"]))
+        assert np.array_equal(_bits(probs), _bits(d[f"out_{tag}"])), \
+            f"do_nms {tag}: {(probs != d[f'out_{tag}']).sum()} values differ"

@@ -317,8 +317,9 @@ def test_set_batch_and_resize_replan_the_device_side(tmp_path):
 def test_networks_at_serving_batches(tmp_path, name, side, batch):
     """Whole networks at batch sizes where every CTA walks many tiles (the parity tests above use batches the
     CPU reference finishes in seconds): must complete - an epilogue race in the conv+pool kernel once hung
-    tiny-yolo-voc at batch 64 - and image 0's output must equal the batch-1 network's up to bf16 roundings
-    (kernel variant, stream-K split and tile order change with the batch)."""
+    tiny-yolo-voc at batch 64 - and EVERY image's output must equal what the batch-1 network computes for that
+    image up to bf16 roundings (kernel variant, stream-K split and tile order change with the batch; against the
+    reference itself these batch sizes are checked in test_baseline_batches_gpu.py)."""
     text1 = synth.CFGS[name](batch=1, w=side, h=side)
     textb = synth.CFGS[name](batch=batch, w=side, h=side)
     (tmp_path / "b1.cfg").write_text(text1)
@@ -328,14 +329,15 @@ def test_networks_at_serving_batches(tmp_path, name, side, batch):
     dn.set_gpu_index(0)
     net1 = dn.parse_network_cfg(tmp_path / "b1.cfg")
     dn.load_weights(net1, tmp_path / "n.weights")
-    row = dn.network_predict(net1, np.ascontiguousarray(x[:1]))[0]
+    rows = np.stack([dn.network_predict(net1, np.ascontiguousarray(x[b:b + 1]))[0] for b in range(batch)])
     dn.free_network(net1)
     net = dn.parse_network_cfg(tmp_path / "bn.cfg")
     dn.load_weights(net, tmp_path / "n.weights")
     out = dn.network_predict(net, x)
     assert np.isfinite(out).all()
-    err = float(np.abs(out[0] - row).max() / np.abs(row).max())
-    assert err <= 5e-3, f"image 0 at batch {batch} differs from batch 1 by {err:.2e} of the row maximum"
+    err = np.abs(out - rows).max(axis=1) / np.abs(rows).max(axis=1)
+    assert err.max() <= 5e-3, \
+        f"image {int(err.argmax())} at batch {batch} differs from its batch-1 run by {err.max():.2e} of the row maximum"
     again = dn.network_predict(net, x)
     assert np.array_equal(again, out), "two runs of the same batch must be bit-identical"
     if net.layers[net.n - 1].type == dn.REGION:

@@ -75,9 +75,23 @@ def test_decode_and_nms_match_reference_golden(tmp_path, name):
     out.mkdir()
     R.run_raw([R.ORACLE_BIN, "region", "net.cfg", "in.f32", "out", float(d["thresh"]), float(d["nms"])], cwd=tmp_path,
               env={"Y2_USE_MAP": str(int(d["use_map"]))})
-    assert _compare(d, out) == 5
+    assert _compare(d, out) == 6  # region_out, boxes, probs_pre, probs_post, region_after_boxes, dets
     # the fixtures are not vacuous: NMS removed something
     assert (d["probs_pre"] != 0).sum() > (d["probs_post"] != 0).sum() > 0
+
+
+def test_do_nms_unsorted_matches_reference_golden(tmp_path):
+    """do_nms (box.c:279-297), the variant demo.c and validate_detector_recall call"""
+    d = np.load(GOLDEN / "do_nms.npz")
+    d["boxes"].tofile(tmp_path / "b.f32")
+    d["probs"].tofile(tmp_path / "p.f32")
+    total, classes = d["probs"].shape
+    for tag in ("a", "b"):
+        subprocess.run([str(R.ORACLE_BIN), "donms", "b.f32", "p.f32", str(total), str(classes),
+                        repr(float(d[f"thresh_{tag}"])), "o.f32"], cwd=tmp_path, check=True)
+        got = np.fromfile(tmp_path / "o.f32", np.float32).reshape(total, classes)
+        assert np.array_equal(_bits(got), _bits(d[f"out_{tag}"]))
+        assert 0 < (got != 0).sum() < (d["probs"] != 0).sum()
 
 
 def test_resize_matches_reference_golden(tmp_path):
