@@ -142,6 +142,48 @@ def mini_dense_cfg(batch=2, w=64, h=64, classes=4, num=3):
     return s + _region(anchors, classes, num)
 
 
+EXACT_ANCHORS = "1.0,1.5, 2.5,2.0, 4.0,5.0"
+
+
+def exact_detector_cfg(batch=1, w=32, h=24, classes=4, num=3):
+    """A detector whose head output is EXACTLY representable: one 3x3 linear convolution (no batchnorm) straight
+    into the region layer.  With write_exact_weights and exact_frames every product k/64 * m/32 and every partial
+    sum is a dyadic rational of at most 17 bits, so fp32 accumulation on the CPU (any order) and bf16 x bf16 ->
+    fp32 on the tensor cores give the same bits: everything behind the head can be compared with the
+    reference bit for bit through whole-pipeline entry points (Detector::detect)."""
+    return _net(batch, w, h) + _conv(num * (classes + 5), 3, bn=0, act="linear") + _region(EXACT_ANCHORS, classes, num)
+
+
+def write_exact_weights(path, cfg_text, seed=5, classes=4, num=3):
+    """weights m/32 (m/256 for the tw/th filters, so that boxes stay a few cells wide), biases m/64, |m| <= 32"""
+    (sp,) = conv_specs_from_cfg(cfg_text)
+    rng = np.random.default_rng(seed)
+    n, k, c = sp.filters, sp.size, sp.channels
+    biases = (rng.integers(-32, 33, n) / 64.0).astype(np.float32)
+    w = (rng.integers(-32, 33, (n, c * k * k)) / 32.0).astype(np.float32)
+    for a in range(num):
+        for j in (2, 3):
+            w[a * (classes + 5) + j] /= 8.0
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiii", 0, 1, 0, 0))
+        f.write(biases.tobytes())
+        f.write(w.tobytes())
+
+
+def exact_frames(n, h, w, seed=9):
+    """n frames [3][h][w] with values k/64 (exact in bf16); consecutive frames differ in a moving block only,
+    so detections persist from frame to frame (tracking has something to follow)."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 65, (3, h, w))
+    out = np.empty((n, 3, h, w), np.float32)
+    for i in range(n):
+        fr = base.copy()
+        x0 = (3 * i) % max(w - 8, 1)
+        fr[:, 4:12, x0:x0 + 8] = rng.integers(0, 65, (3, 8, 8))
+        out[i] = fr / 64.0
+    return out
+
+
 def region_only_cfg(batch, cells_w, cells_h, anchors, classes, num, extra=""):
     """A network that is ONLY the region layer over a [num*(5+classes)][cells_h][cells_w] input: lets the CPU
     checkers decode a given head output without allocating the whole detector (parse_region asserts

@@ -199,10 +199,43 @@ def main():
                             out_b=f32(t / "ob.f32").reshape(probs.shape))
         print("do_nms: nonzero before/after", int((probs != 0).sum()), int((f32(t / "oa.f32") != 0).sum()),
               int((f32(t / "ob.f32") != 0).sum()))
+    # 3c. the reference's C++ Detector (yolo_v2_class.cpp compiled without GPU / OPENCV over the same CPU objects)
+    detector_golden()
     # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
     classifier_front()
     # 5. parser tables, incl. the reference's own cfg files
     parser_tables()
+
+
+def detector_golden():
+    """tests/cpp/detector_scenario.cpp compiled against the REFERENCE's yolo_v2_class.{hpp,cpp} (oracle/Makefile
+    refdet) on the exactly representable detector of synth.exact_detector_cfg: detect, tracking, use_mean,
+    detect(filename), nms = 0, the load_image exception.  The GPU test compiles the same caller against our
+    header and library and must print the same lines."""
+    det = ROOT / "oracle" / "_ref" / "detector_ref"
+    if not det.exists():
+        raise SystemExit("oracle/_ref/detector_ref missing: run `make -C oracle refdet` first")
+    w, h, n = 32, 24, 6
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        cfg_text = synth.exact_detector_cfg(batch=1, w=w, h=h)
+        (t / "net.cfg").write_text(cfg_text)
+        synth.write_exact_weights(t / "net.weights", cfg_text)
+        frames = synth.exact_frames(n, h, w)
+        frames.tofile(t / "frames.f32")
+        ppm = np.random.default_rng(21).integers(0, 2, (h, w, 3)).astype(np.uint8) * 255  # byte/255. in {0, 1}: exact
+        (t / "image.ppm").write_bytes(b"P6\n%d %d\n255\n" % (w, h) + ppm.tobytes())
+        params = {"thresh": 0.5, "nms": 0.4, "story": 3}
+        r = subprocess.run([str(det), "net.cfg", "net.weights", "frames.f32", str(n), str(w), str(h), str(params["thresh"]),
+                            str(params["nms"]), str(params["story"]), "image.ppm", "0"], cwd=t, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SystemExit("detector_ref failed:\n" + r.stderr[-2000:])
+        lines = [l for l in r.stdout.splitlines() if l.split()[0] in
+                 ("size", "detect", "track", "mean", "file", "loaded", "nonms", "load", "script")]
+        out = {"cfg": cfg_text, "w": w, "h": h, "n": n, **params, "ppm_seed": 21, "lines": lines}
+        (OUT / "detector_ref.json").write_text(json.dumps(out, indent=0))
+        counts = {k: [int(l.split()[2]) for l in lines if l.startswith(k + " ")] for k in ("detect", "mean", "file", "nonms")}
+        print("detector_ref:", counts)
 
 
 def classifier_front():
