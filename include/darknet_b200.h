@@ -262,6 +262,13 @@ float box_iou(box a, box b);                                       /* box.c:94-9
 float box_intersection(box a, box b);
 float box_union(box a, box b);
 
+/* ---- detector.c:202-369: validation result writers (VOC per-class files, COCO json, ImageNet-detection) --- */
+void validate_detector(char *datacfg, char *cfgfile, char *weightfile);            /* detector.c:244-369 */
+void print_detector_detections(FILE **fps, char *id, box *boxes, float **probs, int total, int classes, int w,
+                               int h);                                             /* detector.c:202-221 */
+void print_imagenet_detections(FILE *fp, int id, box *boxes, float **probs, int total, int classes, int w,
+                               int h);                                             /* detector.c:223-242 */
+
 /* ---- option_list.h:12-21, list.h, utils.h --------------------------------------------- */
 typedef struct node { void *val; struct node *next; struct node *prev; } node;
 typedef struct list { int size; node *front; node *back; } list;
@@ -271,6 +278,7 @@ void free_list(list *l);
 void free_list_contents(list *l);
 void **list_to_array(list *l);
 
+list *get_paths(char *filename);                                   /* data.c:12-23 */
 list *read_data_cfg(char *filename);                               /* option_list.c:7-33 */
 int read_option(char *s, list *options);                           /* option_list.c:35-51 */
 void option_insert(list *l, char *key, char *val);
@@ -301,6 +309,10 @@ typedef struct { int h, w, c; float *data; } image;
 image make_image(int w, int h, int c);                             /* image.c:1436-1441 */
 void free_image(image m);
 image resize_image(image im, int w, int h);                        /* image.c:1950-1993 */
+/* binary PPM / PGM reader in place of the reference's stb_image decoder: `c` planes of byte / 255., then the
+ * optional resize (image.c:2069-2095) */
+image load_image(char *filename, int w, int h, int c);
+image load_image_color(char *filename, int w, int h);
 /* classifier front end (classifier.c:676-730 predict_classifier) */
 void fill_image(image m, float s);                                 /* image.c:1601-1605 */
 void embed_image(image source, image dest, int dx, int dy);        /* image.c:1087-1098 */

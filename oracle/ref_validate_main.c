@@ -1,0 +1,15 @@
+/* TEST INFRASTRUCTURE: runs the reference's own validate_detector (detector.c:244-369, compiled from the reference
+ * sources by oracle/Makefile, target refval) on its CPU path.  tests/golden/make_golden.py stores the result files
+ * it writes; the GPU tests compare ours byte for byte.   ref_validate <data.cfg> <net.cfg> <net.weights> */
+#include <stdio.h>
+void validate_detector(char *datacfg, char *cfgfile, char *weightfile);
+extern int gpu_index;
+void *GlobleObjBoxes; /* darknet.c:358-359, not part of the CPU objects */
+int GlobleObjBoxesNum;
+int main(int argc, char **argv)
+{
+    if (argc < 4) { fprintf(stderr, "usage: ref_validate data.cfg net.cfg net.weights\n"); return 1; }
+    gpu_index = -1;
+    validate_detector(argv[1], argv[2], argv[3]);
+    return 0;
+}

@@ -91,7 +91,9 @@ void get_region_boxes(layer l, int w, int h, float thresh, float **probs, box *b
     y2_layer_rt *r = y2_lrt(l);
     if (!r || l.type != REGION) error("get_region_boxes: not a planned region layer");
     const int total = l.w * l.h * l.n;
-    const int out_classes = map ? 200 : l.classes;
+    /* the 200-entry map is only read inside the softmax-tree branch (region_layer.c:349-356) */
+    const int use_map = map && l.softmax_tree;
+    const int out_classes = use_map ? 200 : l.classes;
     const size_t pred_bytes = (size_t)l.outputs * sizeof(float);
     scratch_reserve(&g_pred, pred_bytes);
     scratch_reserve(&g_boxes, (size_t)total * 4 * sizeof(float));
@@ -99,7 +101,7 @@ void get_region_boxes(layer l, int w, int h, float thresh, float **probs, box *b
     memcpy(g_pred.host, l.output, pred_bytes);
     Y2_CHECK(y2_memcpy_h2d(g_pred.dev, g_pred.host, pred_bytes, 0));
     int *map_dev = 0;
-    if (map) {
+    if (use_map) {
         if (map == l.map && r->map_dev) map_dev = r->map_dev;
         else {
             Y2_CHECK(y2_malloc((void **)&map_dev, 200 * sizeof(int)));
@@ -108,7 +110,7 @@ void get_region_boxes(layer l, int w, int h, float thresh, float **probs, box *b
     }
     Y2_CHECK(y2_region_boxes((float *)g_pred.dev, r->biases_dev, (float *)g_boxes.dev, (float *)g_probs.dev, 1,
                              l.w, l.h, l.n, l.classes, (float)w, (float)h, thresh, only_objectness, l.classfix,
-                             l.softmax_tree ? l.softmax_tree->n : 0, r->tree_parent_dev, map_dev, map ? 200 : 0,
+                             l.softmax_tree ? l.softmax_tree->n : 0, r->tree_parent_dev, map_dev, use_map ? 200 : 0,
                              0));
     Y2_CHECK(y2_memcpy_d2h(g_boxes.host, g_boxes.dev, (size_t)total * 4 * sizeof(float), 0));
     Y2_CHECK(y2_memcpy_d2h(g_probs.host, g_probs.dev, (size_t)total * out_classes * sizeof(float), 0));

@@ -145,13 +145,56 @@ def mini_dense_cfg(batch=2, w=64, h=64, classes=4, num=3):
 EXACT_ANCHORS = "1.0,1.5, 2.5,2.0, 4.0,5.0"
 
 
-def exact_detector_cfg(batch=1, w=32, h=24, classes=4, num=3):
+def exact_detector_cfg(batch=1, w=32, h=24, classes=4, num=3, extra=""):
     """A detector whose head output is EXACTLY representable: one 3x3 linear convolution (no batchnorm) straight
     into the region layer.  With write_exact_weights and exact_frames every product k/64 * m/32 and every partial
     sum is a dyadic rational of at most 17 bits, so fp32 accumulation on the CPU (any order) and bf16 x bf16 ->
     fp32 on the tensor cores give the same bits: everything behind the head can be compared with the
     reference bit for bit through whole-pipeline entry points (Detector::detect)."""
-    return _net(batch, w, h) + _conv(num * (classes + 5), 3, bn=0, act="linear") + _region(EXACT_ANCHORS, classes, num)
+    return (_net(batch, w, h) + _conv(num * (classes + 5), 3, bn=0, act="linear")
+            + _region(EXACT_ANCHORS, classes, num, extra))
+
+
+def binary_ppm(path, w, h, seed):
+    """A P6 file whose bytes are 0 or 255: byte / 255. is exactly 0 or 1, so the loaders' float image is exact in
+    bf16 as well (used with exact_detector_cfg for byte-identical validation files)."""
+    px = np.random.default_rng(seed).integers(0, 2, (h, w, 3)).astype(np.uint8) * 255
+    Path(path).write_bytes(b"P6\n%d %d\n255\n" % (w, h) + px.tobytes())
+    return px
+
+
+VALIDATION_CASES = {
+    # eval type -> (classes, region extras, image file names)
+    "voc": (4, "", ["2008_000001", "2008_000002", "img_c", "img_d", "img_e"]),
+    # (the reference starts four loader threads on paths[0..3] unconditionally: a list needs >= 4 images)
+    "coco": (80, "", ["COCO_val2014_000000000042", "COCO_val2014_000000000073", "COCO_val2014_000000000139",
+                      "COCO_val2014_000000000785", "COCO_val2014_000000000872"]),
+    "imagenet": (220, "tree=t.tree\nmap=t.map\n", [f"ILSVRC2013_val_0000000{i}" for i in range(1, 6)]),
+}
+
+
+def write_validation_set(root, kind, w=16, h=12):
+    """Everything validate_detector reads for one eval type, under `root` (paths inside the files are relative
+    to `root`: run with cwd = root): net.cfg, net.weights, images/*.ppm, valid.list, names.list, data.cfg,
+    results/ (+ t.tree / t.map for the ImageNet-detection case)."""
+    root = Path(root)
+    classes, extra, stems = VALIDATION_CASES[kind]
+    (root / "images").mkdir(parents=True, exist_ok=True)
+    (root / "results").mkdir(exist_ok=True)
+    cfg_text = exact_detector_cfg(batch=1, w=w, h=h, classes=classes, num=3, extra=extra)
+    (root / "net.cfg").write_text(cfg_text)
+    write_exact_weights(root / "net.weights", cfg_text, seed=17, classes=classes, num=3)
+    for i, stem in enumerate(stems):
+        binary_ppm(root / "images" / f"{stem}.ppm", w, h, seed=300 + i)
+    (root / "valid.list").write_text("".join(f"images/{s}.ppm\n" for s in stems))
+    (root / "names.list").write_text("".join(f"class{j}\n" for j in range(classes)))
+    data = f"classes={classes}\nvalid=valid.list\nnames=names.list\nresults=results\neval={kind}\n"
+    if kind == "imagenet":
+        write_tree(root / "t.tree", n=classes, fanout=5, roots=4)
+        write_map(root / "t.map", classes)
+        data += "map=t.map\n"
+    (root / "data.cfg").write_text(data)
+    return stems
 
 
 def write_exact_weights(path, cfg_text, seed=5, classes=4, num=3):

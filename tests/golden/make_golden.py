@@ -201,6 +201,8 @@ def main():
               int((f32(t / "ob.f32") != 0).sum()))
     # 3c. the reference's C++ Detector (yolo_v2_class.cpp compiled without GPU / OPENCV over the same CPU objects)
     detector_golden()
+    # 3d. the reference's validate_detector result files (VOC per-class files, COCO json, ImageNet-detection)
+    validation_golden()
     # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
     classifier_front()
     # 5. parser tables, incl. the reference's own cfg files
@@ -236,6 +238,27 @@ def detector_golden():
         (OUT / "detector_ref.json").write_text(json.dumps(out, indent=0))
         counts = {k: [int(l.split()[2]) for l in lines if l.startswith(k + " ")] for k in ("detect", "mean", "file", "nonms")}
         print("detector_ref:", counts)
+
+
+def validation_golden():
+    """oracle/_ref/ref_validate = the reference's validate_detector (detector.c:244-369) on its CPU path, run on
+    synth.write_validation_set for the three eval types; every file it writes goes into validate_ref.npz."""
+    exe = ROOT / "oracle" / "_ref" / "ref_validate"
+    if not exe.exists():
+        raise SystemExit("oracle/_ref/ref_validate missing: run `make -C oracle refval` first")
+    out = {}
+    for kind in synth.VALIDATION_CASES:
+        with tempfile.TemporaryDirectory() as t:
+            t = Path(t)
+            synth.write_validation_set(t, kind)
+            r = subprocess.run([str(exe), "data.cfg", "net.cfg", "net.weights"], cwd=t, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise SystemExit(f"ref_validate {kind} failed:\n" + r.stderr[-2000:])
+            files = sorted((t / "results").iterdir())
+            for f in files:
+                out[f"{kind}/{f.name}"] = np.frombuffer(f.read_bytes(), np.uint8)
+            print("validate", kind, {f.name: len(f.read_bytes().splitlines()) for f in files})
+    np.savez_compressed(OUT / "validate_ref.npz", **out)
 
 
 def classifier_front():
