@@ -376,6 +376,20 @@ int network_detect_submit_frames(network net, const unsigned char *frames_hwc, i
                                  float thresh, float nms, int max_det);
 void network_detect_batch_frames(network net, const unsigned char *frames_hwc, int frame_w, int frame_h,
                                  float thresh, float nms, y2_detection *dets, int *counts, int max_det);
+/* ---- the same over several GPUs of one box from ONE caller (one replica and one host thread per GPU; idiom of
+ * train_networks, network_kernels.cu:346-376).  Replica i owns the next nets[i].batch images of the global batch;
+ * detections land in the caller's arrays in image order - nothing else crosses GPUs. ------------------------- */
+network *parse_network_cfg_multi(char *cfgfile, char *weightfile, int *gpus, int ngpus, int batch);
+void free_network_multi(network *nets, int n);
+int network_multi_batch(network *nets, int n); /* images per call = sum of the replicas' batches */
+void network_detect_batch_multi(network *nets, int n, const float *images, float thresh, float nms,
+                                y2_detection *dets, int *counts, int max_det);
+void network_detect_batch_u8_multi(network *nets, int n, const unsigned char *images_hwc, float thresh, float nms,
+                                   y2_detection *dets, int *counts, int max_det);
+void network_detect_submit_multi(network *nets, int n, const float *images, float thresh, float nms, int max_det);
+void network_detect_submit_u8_multi(network *nets, int n, const unsigned char *images_hwc, float thresh, float nms,
+                                    int max_det);
+void network_detect_wait_multi(network *nets, int n, y2_detection *dets, int *counts, int max_det);
 /* Block until the network's stream is idle. */
 void network_sync(network net);
 /* Device stream the network runs on (cudaStream_t) — for timing with CUDA events. */

@@ -155,6 +155,14 @@ def lib() -> C.CDLL:
         "network_pipeline_staging_frames": (C.POINTER(C.c_ubyte), [Network, i, i, i]),
         "network_detect_submit_frames": (i, [Network, C.POINTER(C.c_ubyte), i, i, f, f, i]),
         "network_detect_batch_frames": (None, [Network, C.POINTER(C.c_ubyte), i, i, f, f, C.POINTER(Detection), _ip, i]),
+        "parse_network_cfg_multi": (C.POINTER(Network), [C.c_char_p, C.c_char_p, _ip, i, i]),
+        "free_network_multi": (None, [C.POINTER(Network), i]),
+        "network_multi_batch": (i, [C.POINTER(Network), i]),
+        "network_detect_batch_multi": (None, [C.POINTER(Network), i, fp, f, f, C.POINTER(Detection), _ip, i]),
+        "network_detect_batch_u8_multi": (None, [C.POINTER(Network), i, C.POINTER(C.c_ubyte), f, f, C.POINTER(Detection), _ip, i]),
+        "network_detect_submit_multi": (None, [C.POINTER(Network), i, fp, f, f, i]),
+        "network_detect_submit_u8_multi": (None, [C.POINTER(Network), i, C.POINTER(C.c_ubyte), f, f, i]),
+        "network_detect_wait_multi": (None, [C.POINTER(Network), i, C.POINTER(Detection), _ip, i]),
         "network_sync": (None, [Network]),
         "network_stream": (C.c_void_p, [Network]),
         "network_conv_flops": (C.c_double, [Network]),

@@ -344,3 +344,75 @@ def test_networks_at_serving_batches(tmp_path, name, side, batch):
         dets, counts = dn.network_detect_batch(net, x, 0.02, 0.4, 256)
         assert len(dets) == batch
     dn.free_network(net)
+
+
+def _device_count():
+    import ctypes as C
+    from sr_object_detection_b200 import _lib
+    n = C.c_int(0)
+    _lib.check(_lib.load().y2_device_count(C.byref(n)))
+    return n.value
+
+
+@pytest.mark.parametrize("replicas", [2, 3])
+def test_multi_gpu_entry_one_thread_per_replica_equals_single_network(tmp_path, replicas):
+    """network_detect_batch_multi / _u8_multi / submit_multi + wait_multi: one host thread per replica, image order
+    preserved, detections identical to ONE network run over the whole batch.  Replicas go to distinct GPUs when the
+    box has them; on a one-GPU box they share cuda:0, which is the stricter test of the per-network scratch (two
+    networks in flight on one device from two host threads)."""
+    import ctypes as C
+    per, max_det = 3, 845
+    total = per * replicas
+    cfg, weights, _, _ = _setup(tmp_path, "tiny-yolo-voc", total)
+    synth.write_weights(weights, cfg.read_text(), seed=1234, head_gain=30.0)
+    x = synth.images(total, 3, 416, 416, seed=42)
+    thresh, nms = 0.24, 0.4
+    dn.set_gpu_index(0)
+    lib = dn.lib()
+    net = dn.parse_network_cfg(cfg)
+    dn.load_weights(net, weights)
+    want, want_counts = dn.network_detect_batch(net, x, thresh, nms, max_det)
+    dn.free_network(net)
+    assert sum(want_counts) > 20, "the case must produce detections"
+    ndev = _device_count()
+    gpus = (C.c_int * replicas)(*[i % ndev for i in range(replicas)])
+    nets = lib.parse_network_cfg_multi(str(cfg).encode(), str(weights).encode(), gpus, replicas, per)
+    assert lib.network_multi_batch(nets, replicas) == total
+    dets = (dn.Detection * (total * max_det))()
+    counts = (C.c_int * total)()
+
+    def check(tag):
+        arr = np.ctypeslib.as_array(dets)
+        assert list(counts) == want_counts, tag
+        for b in range(total):
+            assert arr[b * max_det:b * max_det + counts[b]].tobytes() == want[b].tobytes(), f"{tag}: image {b}"
+
+    with dn._quiet_stderr():
+        pass
+    lib.network_detect_batch_multi(nets, replicas, x.ctypes.data_as(C.POINTER(C.c_float)), thresh, nms, dets, counts, max_det)
+    check("batch_multi")
+    # pipelined: two global batches in flight, results in submission order
+    x2 = np.ascontiguousarray(x[::-1])
+    lib.network_detect_submit_multi(nets, replicas, x.ctypes.data_as(C.POINTER(C.c_float)), thresh, nms, max_det)
+    lib.network_detect_submit_multi(nets, replicas, x2.ctypes.data_as(C.POINTER(C.c_float)), thresh, nms, max_det)
+    lib.network_detect_wait_multi(nets, replicas, dets, counts, max_det)
+    check("submit/wait first")
+    lib.network_detect_wait_multi(nets, replicas, dets, counts, max_det)
+    arr = np.ctypeslib.as_array(dets)
+    for b in range(total):
+        assert counts[b] == want_counts[total - 1 - b]
+        assert arr[b * max_det:b * max_det + counts[b]].tobytes() == want[total - 1 - b].tobytes()
+    # raw uint8 frames
+    u8 = np.random.default_rng(5).integers(0, 256, size=(total, 416, 416, 3), dtype=np.uint8)
+    planar = (u8.transpose(0, 3, 1, 2).astype(np.float32).astype(np.float64) / 255.0).astype(np.float32)
+    lib.network_detect_batch_multi(nets, replicas, np.ascontiguousarray(planar).ctypes.data_as(C.POINTER(C.c_float)),
+                                   thresh, nms, dets, counts, max_det)
+    ref_bytes = [np.ctypeslib.as_array(dets)[b * max_det:b * max_det + counts[b]].tobytes() for b in range(total)]
+    ref_counts = list(counts)
+    lib.network_detect_batch_u8_multi(nets, replicas, u8.ctypes.data_as(C.POINTER(C.c_ubyte)), thresh, nms, dets, counts,
+                                      max_det)
+    assert list(counts) == ref_counts
+    arr = np.ctypeslib.as_array(dets)
+    for b in range(total):
+        assert arr[b * max_det:b * max_det + counts[b]].tobytes() == ref_bytes[b]
+    lib.free_network_multi(nets, replicas)
