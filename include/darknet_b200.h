@@ -318,6 +318,9 @@ void fill_image(image m, float s);                                 /* image.c:16
 void embed_image(image source, image dest, int dx, int dy);        /* image.c:1087-1098 */
 image letterbox_image(image im, int w, int h);                     /* image.c:1624-1644 */
 void top_k(float *a, int n, int k, int *index);                    /* utils.c:179-193 */
+/* classifier.c:676-730: classify an image file (letterbox, forward, WordTree products, top-k) */
+void predict_classifier(char *datacfg, char *cfgfile, char *weightfile, char *filename, int top);
+void predict_classifier_image(network net, image im, char **names, int top, FILE *out); /* the lines for one image */
 
 /* =========================================================================================
  * B200 extensions (not in the reference): batched, device-resident detection.

@@ -224,6 +224,12 @@ int y2_region_forward(const float *in, float *out, int batch, int hw, int n, int
                       int softmax, int n_groups, const int *d_group_size,
                       const int *d_group_offset, y2_stream_t s);
 
+/* the same with a row stride on the input: position p's n*(5+classes) values start at in + p*in_cs (wide fp32 heads
+ * are stored with rows padded to 16 bytes) */
+int y2_region_forward_strided(const float *in, int in_cs, float *out, int batch, int hw, int n, int classes,
+                              int softmax, int n_groups, const int *d_group_size,
+                              const int *d_group_offset, y2_stream_t s);
+
 /* ---- get_region_boxes (replaces region_layer.c:328-379, flat softmax and
  *      tree-without-map / tree-with-map variants) ------------------------------------- */
 /* pred: [B][hw*n][5+classes] (mutated in the tree case, like the reference);
@@ -273,11 +279,29 @@ int y2_collect_ws(const float *boxes, const float *probs, int batch, int total, 
                   float thresh, y2_det *det, int *count, int max_det, void *ws, int *nz_count,
                   y2_stream_t s);
 
+/* ---- softmax-tree detection without the dense pass (yolo9000).  Replaces, for the detection entry points,
+ *      softmax_tree (softmax_layer.c:35-47) + hierarchy_predictions (tree.c:37-51) + the tree branch of
+ *      get_region_boxes (region_layer.c:349-366) + do_nms_sort + the final pick: only the groups on the path of
+ *      classes above .5 are evaluated (see region.cu), results bit-identical to the dense kernels above.
+ *  head: the RAW conv output, fp32 [B][lw*lh][head_cs] (box a of a cell at a*(5+classes));
+ *  d_child_ptr [classes+2] / d_child_grp: CSR of the groups below every node, node `classes` = the virtual root;
+ *  rec: [B][lw*lh*n] records of y2_tree_rec_bytes() bytes each. */
+size_t y2_tree_rec_bytes(void);
+int y2_region_tree_detect(const float *head, int head_cs, const float *d_biases, int batch, int lw, int lh,
+                          int n, int classes, float thresh, int classfix, const int *d_group_size,
+                          const int *d_group_offset, const int *d_child_ptr, const int *d_child_grp,
+                          void *rec, y2_stream_t s);
+int y2_tree_nms_collect(const void *rec, int batch, int total, float thresh, float nms, y2_det *det,
+                        int *count, int max_det, y2_stream_t s);
+
 /* ---- classifier tail (config 5) ----------------------------------------------------- */
 int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs,
                     y2_stream_t s);
 int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp,
                     y2_stream_t s);
+/* softmax_tree of a [softmax] layer with tree= (softmax_layer.c:35-47): per row, one softmax per WordTree group */
+int y2_softmax_tree_rows(const float *in, float *out, int rows, int n, float temp, int n_groups,
+                         const int *d_group_size, const int *d_group_offset, y2_stream_t s);
 /* shortcut (replaces shortcut_layer.c:54-59 copy_ongpu + shortcut_gpu (blas_kernels.cu:618-651)
  * + activate_array_ongpu): out = act(in + add sampled per blas.c:57-81).  in/out: bf16 padded
  * NHWC of extent out_h x out_w, out_cpad stored channels (out_c real); add: the `from` layer. */

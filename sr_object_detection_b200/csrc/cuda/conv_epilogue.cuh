@@ -58,6 +58,56 @@ __device__ __forceinline__ void slab_epilogue_chunk(const SlabParams &prm, const
     }
 }
 
+// fp32 flat output [B][h*w][out_cs] of a wide head (yolo9000: 28 269 filters) through the warp's 4 KB staging tile.
+// After tcgen05.ld a lane owns one output ROW, so storing from registers means 32 scalar stores per lane that touch
+// 32 different lines each; staged, the warp writes 4 rows x 128 contiguous bytes per instruction (8 instructions per
+// 32 x 32 chunk).  flat_row: this lane's row in the output (b*h*w + y*w + x), -1 for pad positions.  out_cs % 4 == 0.
+template <int ACT>
+__device__ __forceinline__ void slab_store_f32_staged(const SlabParams &prm, uint4 *stage, const uint32_t (&v)[32],
+                                                      const float2 *sab, int c0, int n0, long long flat_row, int lane)
+{
+    const float4 *ab4 = reinterpret_cast<const float4 *>(sab + c0);
+    uint32_t f[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float4 q = ab4[j];  // (alpha, beta) of two filters
+        float t0 = fmaf(__uint_as_float(v[2 * j]), q.x, q.y);
+        float t1 = fmaf(__uint_as_float(v[2 * j + 1]), q.z, q.w);
+        if (ACT == Y2_ACT_LEAKY) {
+            t0 = fmaxf(t0, 0.1f * t0);
+            t1 = fmaxf(t1, 0.1f * t1);
+        } else if (ACT == Y2_ACT_LOGISTIC) {
+            t0 = 1.f / (1.f + __expf(-t0));
+            t1 = 1.f / (1.f + __expf(-t1));
+        }
+        f[2 * j] = __float_as_uint(t0);
+        f[2 * j + 1] = __float_as_uint(t1);
+    }
+    __syncwarp();  // the previous chunk has been read out of the tile
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        stage[lane * 8 + (c ^ (lane & 7))] = make_uint4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+    __syncwarp();
+    const int ch = n0 + c0 + (lane & 7) * 4;
+    float *out = reinterpret_cast<float *>(prm.out);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const long long fr = __shfl_sync(0xffffffffu, flat_row, r);
+        const uint4 q = stage[r * 8 + ((lane & 7) ^ (r & 7))];
+        if (fr >= 0 && ch < prm.cout) {
+            float *o = out + fr * prm.out_cs + ch;
+            if (ch + 4 <= prm.cout) {
+                *reinterpret_cast<uint4 *>(o) = q;
+            } else {  // the last filters of a head whose count is not a multiple of 4
+                o[0] = __uint_as_float(q.x);
+                if (ch + 1 < prm.cout) o[1] = __uint_as_float(q.y);
+                if (ch + 2 < prm.cout) o[2] = __uint_as_float(q.z);
+            }
+        }
+    }
+}
+
 // affine + activation of one 32-column chunk, packed to bf16 (zeros when the row is a pad position)
 template <int ACT>
 __device__ __forceinline__ void slab_affine_pack(const uint32_t (&v)[32], const float2 *sab, int c0, bool valid,

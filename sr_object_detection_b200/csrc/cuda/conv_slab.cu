@@ -284,7 +284,20 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         tc_fence_before();
                         mbar_arrive(&tempty_bar[buf]);
                     }
-                    if (prm.tma_store) {  // bf16 tensor, 64-channel aligned: staged, one TMA store per warp
+                    if (prm.tma_store == 2) {  // fp32 flat head: staged, row-contiguous 16-byte stores
+                        const long long fr = valid ? ((long long)b * prm.h + y) * prm.w + x : -1ll;
+                        uint4 *st = s_stage + (warp - 3) * 256;
+                        if (prm.act == Y2_ACT_LINEAR) {
+                            slab_store_f32_staged<Y2_ACT_LINEAR>(prm, st, v0, sab, col0 + c, n0, fr, lane);
+                            slab_store_f32_staged<Y2_ACT_LINEAR>(prm, st, v1, sab, col0 + c + 32, n0, fr, lane);
+                        } else if (prm.act == Y2_ACT_LEAKY) {
+                            slab_store_f32_staged<Y2_ACT_LEAKY>(prm, st, v0, sab, col0 + c, n0, fr, lane);
+                            slab_store_f32_staged<Y2_ACT_LEAKY>(prm, st, v1, sab, col0 + c + 32, n0, fr, lane);
+                        } else {
+                            slab_store_f32_staged<Y2_ACT_LOGISTIC>(prm, st, v0, sab, col0 + c, n0, fr, lane);
+                            slab_store_f32_staged<Y2_ACT_LOGISTIC>(prm, st, v1, sab, col0 + c + 32, n0, fr, lane);
+                        }
+                    } else if (prm.tma_store) {  // bf16 tensor, 64-channel aligned: staged, one TMA store per warp
                         uint4 w[8];
                         if (prm.act == Y2_ACT_LEAKY) {
                             slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, col0 + c, valid, w);
@@ -323,7 +336,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (prm.tiles_n > 1 && next < total_tiles && ab_lane) s_ab[(buf ^ 1) * BLOCK_N + et] = ab_next;
         }
-        if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
+        if (prm.tma_store == 1 && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -416,6 +429,10 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
         if (rc != Y2_OK) return rc;
         p.tma_store = 1;
     }
+    // wide fp32 heads (>= 1024 filters, 16-byte aligned rows): staged row-contiguous stores (conv_epilogue.cuh)
+    const bool f32_staged = d->out_mode == Y2_OUT_F32_FLAT && bn == 256 && d->cout >= 1024 && d->out_cs % 4 == 0 &&
+                            ((uintptr_t)d->out & 15) == 0 && !getenv("Y2_SLAB_NO_F32_STAGE");
+    if (f32_staged) p.tma_store = 2;
     p.cblocks = d->cin / bk;
     p.wp = wp;
     p.hp = hp;
@@ -458,7 +475,7 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // 1x1 layers: the 256-position tiles pay off only while every SM still gets two or more of them and
     // the output is the bf16 tensor (measured on B200: L5/L9/L13 +5..15%, the 13x13 layers and the fp32
     // head are faster on the per-tap kernel's 128-position tiles)
-    if (taps == 1 && (tiles < 2 * sms || d->out_mode != Y2_OUT_BF16_PADDED) && !getenv("Y2_CONV_VARIANT"))
+    if (taps == 1 && (tiles < 2 * sms || (d->out_mode != Y2_OUT_BF16_PADDED && !f32_staged)) && !getenv("Y2_CONV_VARIANT"))
         return Y2_EINVAL;
     pl->grid = tiles < sms ? tiles : sms;
     pl->taps = taps;

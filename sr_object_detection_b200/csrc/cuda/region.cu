@@ -28,7 +28,7 @@ __device__ __forceinline__ float logistic_ref(float x)
 //   index order by shuffling the terms through lane 0's order, so it is the same sequence
 //   of roundings as the reference's serial loop.
 // ---------------------------------------------------------------------------------
-__global__ void region_forward_kernel(const float *in, float *out,
+__global__ void region_forward_kernel(const float *in, int in_cs, int anchors, float *out,
                                       long long boxes, int classes, int softmax, int n_groups,
                                       const int *__restrict__ group_size,
                                       const int *__restrict__ group_offset)
@@ -42,7 +42,7 @@ __global__ void region_forward_kernel(const float *in, float *out,
     for (long long wi = warp_global; wi < work; wi += nwarps) {
         const long long box = wi / groups;
         const int g = (int)(wi - box * groups);
-        const float *x = in + box * size;
+        const float *x = in + (box / anchors) * in_cs + (box % anchors) * size;
         float *o = out + box * size;
         if (g == 0 && lane < 5) o[lane] = (lane == 4) ? logistic_ref(x[4]) : x[lane];
         int off = 0, n = classes;
@@ -91,7 +91,7 @@ __global__ void region_forward_kernel(const float *in, float *out,
 // group; the few groups wider than a warp are then finished by the whole warp, lanes over classes, the
 // float sum still accumulated in class order.
 // ---------------------------------------------------------------------------------
-__global__ void region_forward_tree_kernel(const float *__restrict__ in, float *__restrict__ out, long long boxes,
+__global__ void region_forward_tree_kernel(const float *__restrict__ in, int in_cs, int anchors, float *__restrict__ out, long long boxes,
                                            int classes, int softmax, int n_groups,
                                            const int *__restrict__ group_size, const int *__restrict__ group_offset)
 {
@@ -107,7 +107,7 @@ __global__ void region_forward_tree_kernel(const float *__restrict__ in, float *
         const int g = active ? (int)(t - box * n_groups) : 0;
         const int off = group_offset[g];
         const int n = active ? group_size[g] : 0;
-        const float *x = in + box * size;
+        const float *x = in + (box / anchors) * in_cs + (box % anchors) * size;
         float *o = out + box * size;
         if (active && g == 0) {
             o[0] = x[0];
@@ -146,7 +146,7 @@ __global__ void region_forward_tree_kernel(const float *__restrict__ in, float *
             const long long wbox = __shfl_sync(0xffffffffu, box, src);
             const int woff = __shfl_sync(0xffffffffu, off, src);
             const int wn = __shfl_sync(0xffffffffu, n, src);
-            const float *wx = in + wbox * size + 5 + woff;
+            const float *wx = in + (wbox / anchors) * in_cs + (wbox % anchors) * size + 5 + woff;
             float *wo = out + wbox * size + 5 + woff;
             if (!softmax) {
                 for (int i = lane; i < wn; i += 32) wo[i] = wx[i];
@@ -188,7 +188,7 @@ __global__ void region_forward_tree_kernel(const float *__restrict__ in, float *
 // classes 4k..4k+3 through quad shuffles and every lane adds them in that order, so the sequence of
 // roundings is the reference's serial loop (blas.c:205-221).
 // ---------------------------------------------------------------------------------
-__global__ void region_forward_flat_kernel(const float *__restrict__ in, float *__restrict__ out, long long boxes,
+__global__ void region_forward_flat_kernel(const float *__restrict__ in, int in_cs, int anchors, float *__restrict__ out, long long boxes,
                                            int classes, int softmax)
 {
     const int lane = threadIdx.x & 31;
@@ -202,8 +202,9 @@ __global__ void region_forward_flat_kernel(const float *__restrict__ in, float *
     for (long long wb = quad0 - (lane >> 2); wb < boxes; wb += nquads) {
         const long long box = wb + (lane >> 2);
         const bool active = box < boxes;
-        const float *x = in + (active ? box : 0) * size;
-        float *o = out + (active ? box : 0) * size;
+        const long long bx = active ? box : 0;
+        const float *x = in + (bx / anchors) * in_cs + (bx % anchors) * size;
+        float *o = out + bx * size;
         if (active) {
             if (q == 0) {
                 o[0] = x[0];
@@ -532,6 +533,264 @@ __global__ void collect_kernel(const float *__restrict__ boxes, const float *__r
         for (int j = threadIdx.x; j < classes; j += blockDim.x) nz_count[(size_t)b * classes + j] = 0;
 }
 
+// ---------------------------------------------------------------------------------
+// Softmax-tree detection without the dense pass (yolo9000: 9418 classes x 867 boxes x batch).
+//
+// What the reference computes per box (region_layer.c:349-366 on top of softmax_tree, softmax_layer.c:35-47, and
+// hierarchy_predictions, tree.c:37-51): the softmax of EVERY group, the product along every root path, then it
+// keeps the highest-index class whose product exceeds .5 and zeroes the rest.  Which class that is, and its value,
+// depend on a handful of groups only:
+//   * p = e / sum <= 1 in float arithmetic and a product RN(p * h) never exceeds h, so a class above .5 has all
+//     its ancestors above .5 and its own softmax value above .5;
+//   * inside one group at most one member is above .5 (the float sum of the group is >= twice the smaller of any
+//     two members - rounding is monotone and 2e is representable);
+//   * children follow their parents in the file (checked at plan time), so the highest index is the deepest one.
+// So the kernel walks down from the root group(s): softmax of the group exactly as the dense kernel does it (double
+// exp rounded to float, float sum in index order), take the member above .5, multiply, descend into its child
+// group(s).  ~30 of the 9418 logits of a box are read; the values are bit-identical to the dense path (tests:
+// golden tree fixtures + yolo9000 against the reference end to end).  A warp per box.
+// ---------------------------------------------------------------------------------
+struct TreeRec {      // one per box
+    float x, y, w, h; // get_region_box
+    float val;        // probs[box][cls] as get_region_boxes leaves it (0: no class above .5, or objectness <= thresh)
+    int cls;          // -1 when val == 0
+    int pad0, pad1;
+};
+
+// softmax value of member `lane + 32 i` of one group, all lanes of the warp cooperating (blas.c:205-221);
+// returns through `visit` every member whose hierarchy value exceeds .5
+template <typename F>
+__device__ __forceinline__ void tree_group_softmax(const float *__restrict__ xi, int n, float hpar, bool is_root, int lane,
+                                                   F visit)
+{
+    float largest = -FLT_MAX;
+    for (int i = lane; i < n; i += 32) {
+        const float v = xi[i];
+        if (v > largest) largest = v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+        if (other > largest) largest = other;
+    }
+    float sum = 0.f;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float e = 0.f;
+        if (i < n) {
+            const float arg = xi[i] / 1.f - largest / 1.f;  // temperature 1, float expression
+            e = (float)exp((double)arg);
+        }
+        const int cnt = (n - base) < 32 ? (n - base) : 32;
+        for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
+    }
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float hv = 0.f;
+        if (i < n) {
+            const float arg = xi[i] / 1.f - largest / 1.f;
+            const float pj = (float)exp((double)arg) / sum;
+            hv = is_root ? pj : pj * hpar;  // tree.c:44-45: predictions[j] *= predictions[parent]
+        }
+        unsigned hot = __ballot_sync(0xffffffffu, hv > .5);
+        while (hot) {
+            const int src = __ffs(hot) - 1;
+            hot &= hot - 1;
+            visit(base + src, __shfl_sync(0xffffffffu, hv, src));
+        }
+    }
+}
+
+__global__ void region_tree_detect_kernel(const float *__restrict__ head, int head_cs, const float *__restrict__ biases,
+                                          long long nboxes, int lw, int lh, int n, int classes, float thresh, int classfix,
+                                          const int *__restrict__ group_size, const int *__restrict__ group_offset,
+                                          const int *__restrict__ child_ptr, const int *__restrict__ child_grp,
+                                          TreeRec *__restrict__ rec)
+{
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int size = classes + 5;
+    const int per_img = lw * lh * n;
+    for (long long bi = w0; bi < nboxes; bi += nw) {
+        const int index = (int)(bi % per_img);
+        const long long pos = bi / n;  // b * hw + cell
+        const int an = index % n;
+        const float *x = head + pos * head_cs + (long long)an * size;
+        // pending groups: (group, hierarchy value of its parent); the walk is warp-uniform
+        int stk_g[24];
+        float stk_h[24];
+        int sp = 0;
+        for (int q = child_ptr[classes]; q < child_ptr[classes + 1] && sp < 24; ++q) {
+            stk_g[sp] = child_grp[q];
+            stk_h[sp] = -1.f;  // marks a root group
+            ++sp;
+        }
+        int best = -1;
+        float best_val = 0.f;
+        while (sp > 0) {
+            --sp;
+            const int g = stk_g[sp];
+            const float hpar = stk_h[sp];
+            const int off = group_offset[g];
+            tree_group_softmax(x + 5 + off, group_size[g], hpar, hpar < 0.f, lane, [&](int member, float hv) {
+                const int j = off + member;
+                if (j > best) {
+                    best = j;
+                    best_val = hv;
+                }
+                for (int q = child_ptr[j]; q < child_ptr[j + 1] && sp < 24; ++q) {
+                    stk_g[sp] = child_grp[q];
+                    stk_h[sp] = hv;
+                    ++sp;
+                }
+            });
+        }
+        if (lane == 0) {
+            float scale = logistic_ref(x[4]);  // forward_region_layer (region_layer.c:160)
+            if (classfix == -1 && scale < .5) scale = 0;
+            const float val = (best >= 0 && scale > thresh) ? best_val : 0.f;
+            const int cell = index / n;
+            const int row = cell / lw;
+            const int col = cell % lw;
+            TreeRec r;
+            r.x = (col + logistic_ref(x[0])) / lw;
+            r.y = (row + logistic_ref(x[1])) / lh;
+            r.w = (float)(exp((double)x[2]) * (double)biases[2 * an] / (double)lw);
+            r.h = (float)(exp((double)x[3]) * (double)biases[2 * an + 1] / (double)lh);
+            r.val = val;
+            r.cls = val != 0.f ? best : -1;
+            r.pad0 = r.pad1 = 0;
+            rec[bi] = r;
+        }
+    }
+}
+
+// do_nms_sort + the final pick on the sparse records of one image (a box carries at most one non-zero class): class
+// k's candidates in the order (value descending, index ascending) - the reference's carried sort order reduces to
+// that when every other column of the two rows is zero (see nms.cu) -, greedy suppression inside the class, then the
+// survivors above thresh in box-index order.
+__device__ __forceinline__ float tree_overlap(float x1, float w1, float x2, float w2)
+{
+    const float l1 = x1 - w1 / 2;
+    const float l2 = x2 - w2 / 2;
+    const float left = l1 > l2 ? l1 : l2;
+    const float r1 = x1 + w1 / 2;
+    const float r2 = x2 + w2 / 2;
+    const float right = r1 < r2 ? r1 : r2;
+    return right - left;
+}
+
+__device__ __forceinline__ float tree_iou(const TreeRec &a, const TreeRec &b)
+{
+    const float w = tree_overlap(a.x, a.w, b.x, b.w);
+    const float h = tree_overlap(a.y, a.h, b.y, b.h);
+    float inter;
+    if (w < 0 || h < 0) inter = 0;
+    else inter = w * h;
+    const float uni = a.w * a.h + b.w * b.h - inter;
+    return inter / uni;
+}
+
+__global__ void tree_nms_collect_kernel(const TreeRec *__restrict__ rec, int total, float thresh, float nms,
+                                        y2_det *__restrict__ det, int *__restrict__ count, int max_det)
+{
+    extern __shared__ int tsm[];
+    int *s_idx = tsm;              // candidates in index order
+    int *s_sorted = tsm + total;   // positions in s_idx, sorted
+    int *s_alive = tsm + 2 * total;
+    __shared__ int s_warp_tot[32];
+    __shared__ int s_base;
+    const int b = blockIdx.x;
+    const TreeRec *r = rec + (size_t)b * total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < total; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const bool is = i < total && r[i].cls >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, is);
+        if (lane == 0) s_warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+        if (is) s_idx[off + __popc(m & ((1u << lane) - 1))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < nw; ++w) t += s_warp_tot[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    const int m = s_base;
+    for (int a = threadIdx.x; a < m; a += blockDim.x) {
+        const int ia = s_idx[a];
+        const int ca = r[ia].cls;
+        const float va = r[ia].val;
+        int rank = 0;
+        for (int o = 0; o < m; ++o) {
+            const int io = s_idx[o];
+            const int co = r[io].cls;
+            const float vo = r[io].val;
+            const bool before = co != ca ? co < ca : (vo != va ? vo > va : io < ia);
+            if (o != a && before) ++rank;
+        }
+        s_sorted[rank] = ia;
+        s_alive[rank] = 1;
+    }
+    __syncthreads();
+    if (nms > 0) {
+        for (int i = 0; i < m - 1; ++i) {
+            if (!s_alive[i]) continue;  // uniform
+            const TreeRec a = r[s_sorted[i]];
+            for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
+                const TreeRec o = r[s_sorted[j]];
+                if (o.cls != a.cls) break;  // sorted by class: the rest of this thread's stride is further away still
+                if (s_alive[j] && tree_iou(a, o) > nms) s_alive[j] = 0;
+            }
+            __syncthreads();
+        }
+    }
+    // survivors above thresh, in box-index order: mark per box, then the same ordered compaction
+    int *s_keep = s_idx;  // reuse: 1 per box index
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_keep[i] = 0;
+    __syncthreads();
+    for (int a = threadIdx.x; a < m; a += blockDim.x)
+        if (s_alive[a] && r[s_sorted[a]].val > thresh) s_keep[s_sorted[a]] = 1;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    y2_det *d = det + (size_t)b * max_det;
+    for (int start = 0; start < total; start += blockDim.x) {
+        const int i = start + threadIdx.x;
+        const bool is = i < total && s_keep[i];
+        const unsigned mk = __ballot_sync(0xffffffffu, is);
+        if (lane == 0) s_warp_tot[warp] = __popc(mk);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp_tot[w];
+        const int pos = off + __popc(mk & ((1u << lane) - 1));
+        if (is && pos < max_det) {
+            const TreeRec q = r[i];
+            y2_det o;
+            o.x = q.x; o.y = q.y; o.w = q.w; o.h = q.h;
+            o.prob = q.val;
+            o.obj_id = q.cls;
+            o.box_index = i;
+            d[pos] = o;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < nw; ++w) t += s_warp_tot[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[b] = s_base;
+}
+
 // classifier tail ------------------------------------------------------------------
 // avgpool_layer.c:40-55: sequential float sum over h*w, then / (h*w).  One thread per
 // (b, c) keeps the reference's summation order; reads are coalesced along c.
@@ -586,6 +845,47 @@ __global__ void softmax_rows_kernel(const float *__restrict__ in, float *__restr
     }
 }
 
+// softmax_tree (softmax_layer.c:35-47) over plain rows: warp per (row, group), blas.c:205-221 per group
+__global__ void softmax_tree_rows_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int n, float temp,
+                                         int n_groups, const int *__restrict__ group_size,
+                                         const int *__restrict__ group_offset)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long work = (long long)rows * n_groups;
+    for (long long wi = warp_global; wi < work; wi += nwarps) {
+        const long long r = wi / n_groups;
+        const int g = (int)(wi - r * n_groups);
+        const int off = group_offset[g], m = group_size[g];
+        const float *xi = in + r * n + off;
+        float *oi = out + r * n + off;
+        float largest = -FLT_MAX;
+        for (int i = lane; i < m; i += 32) {
+            const float v = xi[i];
+            if (v > largest) largest = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+            if (other > largest) largest = other;
+        }
+        float sum = 0.f;
+        for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            float e = 0.f;
+            if (i < m) {
+                const float arg = xi[i] / temp - largest / temp;
+                e = (float)exp((double)arg);
+                oi[i] = e;
+            }
+            const int cnt = (m - base) < 32 ? (m - base) : 32;
+            for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
+        }
+        for (int i = lane; i < m; i += 32) oi[i] = oi[i] / sum;
+    }
+}
+
 static inline int grid_cap(long long blocks, int per_sm)
 {
     long long cap = (long long)sm_count() * per_sm;
@@ -598,33 +898,41 @@ static inline int grid_cap(long long blocks, int per_sm)
 
 using namespace y2;
 
-extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw, int n, int classes,
-                                 int softmax, int n_groups, const int *d_group_size,
-                                 const int *d_group_offset, y2_stream_t s)
+extern "C" int y2_region_forward_strided(const float *in, int in_cs, float *out, int batch, int hw, int n, int classes,
+                                         int softmax, int n_groups, const int *d_group_size,
+                                         const int *d_group_offset, y2_stream_t s)
 {
-    if (!in || !out || batch <= 0 || hw <= 0 || n <= 0 || classes <= 0) return Y2_EINVAL;
+    if (!in || !out || batch <= 0 || hw <= 0 || n <= 0 || classes <= 0 || in_cs < n * (classes + 5)) return Y2_EINVAL;
     if (n_groups > 0 && (!d_group_size || !d_group_offset)) return Y2_EINVAL;
     const long long boxes = (long long)batch * hw * n;
     const int threads = 256;
     if (n_groups <= 0) {  // flat softmax (or none): four lanes per box
         const int grid = grid_cap((boxes * 4 + threads - 1) / threads, 8);
-        region_forward_flat_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax);
+        region_forward_flat_kernel<<<grid, threads, 0, to_stream(s)>>>(in, in_cs, n, out, boxes, classes, softmax);
         Y2_LAUNCH_CHECK();
         return Y2_OK;
     }
     const long long work = boxes * n_groups;
     if (!getenv("Y2_REGION_WARP_PER_GROUP")) {
         const int grid = grid_cap((work + threads - 1) / threads, 8);
-        region_forward_tree_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
+        region_forward_tree_kernel<<<grid, threads, 0, to_stream(s)>>>(in, in_cs, n, out, boxes, classes, softmax, n_groups,
                                                                        d_group_size, d_group_offset);
         Y2_LAUNCH_CHECK();
         return Y2_OK;
     }
     const int grid = grid_cap((work * 32 + threads - 1) / threads, 8);
-    region_forward_kernel<<<grid, threads, 0, to_stream(s)>>>(in, out, boxes, classes, softmax, n_groups,
+    region_forward_kernel<<<grid, threads, 0, to_stream(s)>>>(in, in_cs, n, out, boxes, classes, softmax, n_groups,
                                                               d_group_size, d_group_offset);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
+}
+
+extern "C" int y2_region_forward(const float *in, float *out, int batch, int hw, int n, int classes,
+                                 int softmax, int n_groups, const int *d_group_size,
+                                 const int *d_group_offset, y2_stream_t s)
+{
+    return y2_region_forward_strided(in, n * (classes + 5), out, batch, hw, n, classes, softmax, n_groups, d_group_size,
+                                     d_group_offset, s);
 }
 
 extern "C" int y2_region_boxes_counted(float *pred, const float *d_biases, float *boxes, float *probs, int batch,
@@ -728,6 +1036,39 @@ extern "C" int y2_collect(const float *boxes, const float *probs, int batch, int
     return rc;
 }
 
+extern "C" size_t y2_tree_rec_bytes(void) { return sizeof(TreeRec); }
+
+extern "C" int y2_region_tree_detect(const float *head, int head_cs, const float *d_biases, int batch, int lw, int lh,
+                                     int n, int classes, float thresh, int classfix, const int *d_group_size,
+                                     const int *d_group_offset, const int *d_child_ptr, const int *d_child_grp,
+                                     void *rec, y2_stream_t s)
+{
+    if (!head || !d_biases || !d_group_size || !d_group_offset || !d_child_ptr || !d_child_grp || !rec || batch <= 0 ||
+        head_cs < n * (classes + 5))
+        return Y2_EINVAL;
+    const long long nboxes = (long long)batch * lw * lh * n;
+    region_tree_detect_kernel<<<grid_cap((nboxes * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(
+        head, head_cs, d_biases, nboxes, lw, lh, n, classes, thresh, classfix, d_group_size, d_group_offset, d_child_ptr,
+        d_child_grp, (TreeRec *)rec);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_tree_nms_collect(const void *rec, int batch, int total, float thresh, float nms, y2_det *det,
+                                   int *count, int max_det, y2_stream_t s)
+{
+    if (!rec || !det || !count || batch <= 0 || total <= 0) return Y2_EINVAL;
+    const size_t smem = (size_t)total * 3 * sizeof(int);
+    if (smem > 48 * 1024) {
+        set_error("y2_tree_nms_collect: %d boxes per image exceed the staging buffer", total);
+        return Y2_EINVAL;
+    }
+    tree_nms_collect_kernel<<<batch, 256, smem, to_stream(s)>>>((const TreeRec *)rec, total, thresh, nms, det, count,
+                                                                max_det);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
 extern "C" int y2_avgpool_flat(const float *in, float *out, int batch, int hw, int c, int cs, y2_stream_t s)
 {
     if (!in || !out) return Y2_EINVAL;
@@ -742,6 +1083,17 @@ extern "C" int y2_softmax_rows(const float *in, float *out, int rows, int n, flo
     if (!in || !out) return Y2_EINVAL;
     softmax_rows_kernel<<<grid_cap(((long long)rows * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(in, out, rows,
                                                                                                    n, temp);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_softmax_tree_rows(const float *in, float *out, int rows, int n, float temp, int n_groups,
+                                    const int *d_group_size, const int *d_group_offset, y2_stream_t s)
+{
+    if (!in || !out || rows <= 0 || n <= 0 || n_groups <= 0 || !d_group_size || !d_group_offset) return Y2_EINVAL;
+    const long long work = (long long)rows * n_groups;
+    softmax_tree_rows_kernel<<<grid_cap((work * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(
+        in, out, rows, n, temp, n_groups, d_group_size, d_group_offset);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

@@ -170,11 +170,22 @@ static layer *region_of(network net)
 /* get_region_boxes + do_nms_sort + the final pick for the whole batch on the network's stream: the decode
  * counts the NMS candidates while it writes the probabilities, the suppression pass marks losers negative
  * and the pick reads negative as zero (3 launches; the counters and scratch are the network's own) */
-static void detect_tail(y2_net_rt *rt, layer *l, float thresh, float nms, y2_det *det_dev, int *cnt_dev, int det_cap)
+static void detect_tail(y2_net_rt *rt, layer *l, void *head_rt, float thresh, float nms, y2_det *det_dev, int *cnt_dev,
+                        int det_cap)
 {
     y2_layer_rt *r = (y2_layer_rt *)l->b200;
     const int B = l->batch;
     const int total = l->w * l->h * l->n;
+    if (l->softmax_tree && rt->defer_region) {
+        /* softmax tree: only the groups on the path of classes above .5 are evaluated, straight from the head's
+         * raw output; NMS and the pick work on one (class, value) record per box (2 launches) */
+        y2_layer_rt *hr = (y2_layer_rt *)head_rt;
+        Y2_CHECK(y2_region_tree_detect((const float *)hr->out, hr->out_cs, r->biases_dev, B, l->w, l->h, l->n,
+                                       l->classes, thresh, l->classfix, r->group_size_dev, r->group_offset_dev,
+                                       r->child_ptr_dev, r->child_grp_dev, r->tree_rec_dev, rt->stream));
+        Y2_CHECK(y2_tree_nms_collect(r->tree_rec_dev, B, total, thresh, nms, det_dev, cnt_dev, det_cap, rt->stream));
+        return;
+    }
     Y2_CHECK(y2_region_boxes_counted((float *)r->out, r->biases_dev, r->boxes_dev, r->probs_dev, B, l->w, l->h, l->n,
                                      l->classes, 1.f, 1.f, thresh, 0, l->classfix,
                                      l->softmax_tree ? l->softmax_tree->n : 0, r->tree_parent_dev, 0, 0,
@@ -205,7 +216,7 @@ void network_detect_device(network net, float thresh, float nms, y2_detection *d
         Y2_CHECK(y2_malloc((void **)&rt->cnt_dev, (size_t)rt->det_batch * sizeof(int)));
         Y2_CHECK(y2_host_alloc((void **)&rt->cnt_pinned, (size_t)rt->det_batch * sizeof(int)));
     }
-    detect_tail(rt, l, thresh, nms, rt->det_dev, rt->cnt_dev, rt->det_cap);
+    detect_tail(rt, l, net.layers[net.n - 2].b200, thresh, nms, rt->det_dev, rt->cnt_dev, rt->det_cap);
     Y2_CHECK(y2_memcpy_d2h(rt->cnt_pinned, rt->cnt_dev, (size_t)B * sizeof(int), rt->stream));
     Y2_CHECK(y2_memcpy_d2h(rt->det_pinned, rt->det_dev, (size_t)B * rt->det_cap * sizeof(y2_det), rt->stream));
     Y2_CHECK(y2_stream_sync(rt->stream));
@@ -362,7 +373,7 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
     } else {
         y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
     }
-    detect_tail(rt, l, thresh, nms, ps->det_dev, ps->cnt_dev, ps->det_cap);
+    detect_tail(rt, l, net.layers[net.n - 2].b200, thresh, nms, ps->det_dev, ps->cnt_dev, ps->det_cap);
     Y2_CHECK(y2_memcpy_d2h(ps->cnt_pinned, ps->cnt_dev, (size_t)B * sizeof(int), rt->stream));
     Y2_CHECK(y2_memcpy_d2h(ps->det_pinned, ps->det_dev, (size_t)B * ps->det_cap * sizeof(y2_det), rt->stream));
     Y2_CHECK(y2_event_record(ps->ev_done, rt->stream));

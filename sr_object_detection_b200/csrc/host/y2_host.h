@@ -59,6 +59,10 @@ typedef struct y2_layer_rt {
     int *nms_cnt_dev;   /* [B][classes] NMS candidate counters, zero between batches (owned per network: two
                            networks in flight on one GPU must not share them) */
     void *collect_ws;   /* per-box maxima scratch of the final pick (wide class rows) */
+    /* softmax tree: CSR of the groups below every node (node `classes` = virtual root) and the per-box records
+     * of the sparse detection path; the dense region forward then runs on demand only (region_stale) */
+    int *child_ptr_dev, *child_grp_dev;
+    void *tree_rec_dev;
     /* profiling */
     y2_event_t ev0, ev1;
 } y2_layer_rt;
@@ -107,6 +111,9 @@ typedef struct y2_net_rt {
     y2_stream_t copy_stream;
     int pipe_ready, pipe_head, pipe_inflight;
     int input_u8;        /* the forward pass being issued reads uint8 HWC images (first-layer kernel only) */
+    int defer_region;    /* softmax-tree region layer: its dense forward is not part of the schedule, it runs when
+                            somebody asks for the layer's output (the detection entries never do) */
+    int region_stale;    /* a forward pass ran since the region output was last computed */
 } y2_net_rt;
 
 static inline y2_net_rt *y2_rt(network net) { return (y2_net_rt *)net.b200; }

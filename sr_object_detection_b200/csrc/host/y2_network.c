@@ -457,6 +457,9 @@ static void free_layer_rt(layer *l)
     y2_free(r->biases_dev);
     y2_free(r->nms_cnt_dev);
     y2_free(r->collect_ws);
+    y2_free(r->child_ptr_dev);
+    y2_free(r->child_grp_dev);
+    y2_free(r->tree_rec_dev);
     y2_free(r->tree_parent_dev);
     y2_free(r->group_size_dev);
     y2_free(r->group_offset_dev);
@@ -788,6 +791,12 @@ void y2_plan_network(network *net)
                 r->ktot = kk * cin_pad;
                 r->pool_fused = r->out_kind == Y2_KIND_BF16_PADDED && r->cpad == l->n && pool_fusable(net, i, cin_pad);
             }
+            /* 32-channel K blocks (a first layer, or a layer behind a 32-channel tensor) have no 256-filter tile in
+             * the GEMM kernels that take 1x1 / gathered operands: use two 128-filter tiles */
+            if (r->block_k == 32 && r->block_n == 256 && (l->size == 1 || r->use_patches)) {
+                r->block_n = 128;
+                r->npad = round_up(l->n > r->cpad ? l->n : r->cpad, 128);
+            }
             break;
         }
         case MAXPOOL:
@@ -860,7 +869,8 @@ void y2_plan_network(network *net)
         case SOFTMAX: {
             y2_layer_rt *pr = i ? (y2_layer_rt *)net->layers[i - 1].b200 : 0;
             if (!pr || pr->out_kind != Y2_KIND_F32_VEC) unsupported(i, "softmax without a vector input");
-            if (l->softmax_tree) unsupported(i, "tree softmax layer");
+            if (l->softmax_tree && l->softmax_tree->n != l->inputs / l->groups)
+                unsupported(i, "softmax tree whose size differs from the layer's inputs");
             r->out_kind = Y2_KIND_F32_VEC;
             r->cpad = l->inputs;
             break;
@@ -914,8 +924,9 @@ void y2_plan_network(network *net)
             r->out_cs = r->cpad;
         } else if (r->out_kind == Y2_KIND_F32_FLAT) {
             const int oh = l->type == REGION ? l->h : l->out_h, ow = l->type == REGION ? l->w : l->out_w;
-            r->own_bytes = (size_t)B * oh * ow * r->cpad * sizeof(float);
-            r->out_cs = r->cpad;
+            /* wide conv heads: rows padded to 16 bytes so that the epilogue can store them with 16-byte accesses */
+            r->out_cs = (l->type == CONVOLUTIONAL && r->cpad >= 1024) ? round_up(r->cpad, 4) : r->cpad;
+            r->own_bytes = (size_t)B * oh * ow * r->out_cs * sizeof(float);
         } else {
             r->own_bytes = (size_t)B * r->cpad * sizeof(float);
             r->out_cs = r->cpad;
@@ -962,6 +973,10 @@ void y2_plan_network(network *net)
                 Y2_CHECK(y2_malloc((void **)&r->reorg_table, (size_t)l->out_h * l->out_w * l->out_c * sizeof(int)));
                 Y2_CHECK(y2_reorg_table(r->reorg_table, pr->out_cs, l->c, l->h, l->w, l->stride, 0));
             }
+        } else if (l->type == SOFTMAX && l->softmax_tree) {
+            tree *t = l->softmax_tree;
+            r->group_size_dev = (int *)dev_upload(t->group_size, (size_t)t->groups * sizeof(int));
+            r->group_offset_dev = (int *)dev_upload(t->group_offset, (size_t)t->groups * sizeof(int));
         } else if (l->type == REGION) {
             const size_t total = (size_t)l->w * l->h * l->n;
             r->probs_classes = l->map ? 200 : l->classes;
@@ -979,6 +994,27 @@ void y2_plan_network(network *net)
                 r->tree_parent_dev = (int *)dev_upload(t->parent, (size_t)t->n * sizeof(int));
                 r->group_size_dev = (int *)dev_upload(t->group_size, (size_t)t->groups * sizeof(int));
                 r->group_offset_dev = (int *)dev_upload(t->group_offset, (size_t)t->groups * sizeof(int));
+                /* groups below every node (a group = a run of consecutive nodes with one parent, tree.c:72-82) */
+                int *cptr = (int *)calloc((size_t)t->n + 2, sizeof(int));
+                int *cgrp = (int *)calloc((size_t)t->groups > 0 ? t->groups : 1, sizeof(int));
+                for (int g = 0; g < t->groups; ++g) {
+                    int par = t->parent[t->group_offset[g]];
+                    ++cptr[(par < 0 ? t->n : par) + 1];
+                }
+                for (int j = 0; j <= t->n; ++j) cptr[j + 1] += cptr[j];
+                int *fill = (int *)calloc((size_t)t->n + 1, sizeof(int));
+                for (int g = 0; g < t->groups; ++g) {
+                    int par = t->parent[t->group_offset[g]];
+                    if (par < 0) par = t->n;
+                    cgrp[cptr[par] + fill[par]++] = g;
+                }
+                r->child_ptr_dev = (int *)dev_upload(cptr, ((size_t)t->n + 2) * sizeof(int));
+                r->child_grp_dev = (int *)dev_upload(cgrp, (size_t)(t->groups > 0 ? t->groups : 1) * sizeof(int));
+                free(cptr);
+                free(cgrp);
+                free(fill);
+                Y2_CHECK(y2_malloc(&r->tree_rec_dev, (size_t)B * total * y2_tree_rec_bytes()));
+                rt->defer_region = !getenv("Y2_TREE_DENSE");
             }
             if (l->map) r->map_dev = (int *)dev_upload(l->map, 200 * sizeof(int));
         }
@@ -1087,11 +1123,18 @@ void forward_region_layer_gpu(const layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
+    y2_net_rt *rt = y2_rt(state.net);
+    if (rt && rt->defer_region && !rt->profile) {
+        /* 9418-way softmax tree: the detection entries read the head output directly (y2_region_tree_detect);
+         * the dense softmax runs when the layer's output is asked for (export_layer) */
+        rt->region_stale = 1;
+        return;
+    }
     int groups = 0;
     if (l.softmax_tree) groups = l.softmax_tree->groups;
-    Y2_CHECK(y2_region_forward((const float *)pr->out, (float *)r->out, l.batch, l.w * l.h, l.n, l.classes,
-                               l.softmax || l.softmax_tree, groups, r->group_size_dev, r->group_offset_dev,
-                               net_stream(state.net)));
+    Y2_CHECK(y2_region_forward_strided((const float *)pr->out, pr->out_cs, (float *)r->out, l.batch, l.w * l.h, l.n,
+                                       l.classes, l.softmax || l.softmax_tree, groups, r->group_size_dev,
+                                       r->group_offset_dev, net_stream(state.net)));
     count_launch(state.net, 1);
 }
 
@@ -1109,8 +1152,13 @@ void forward_softmax_layer_gpu(layer l, network_state state)
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
     const int n = l.inputs / l.groups;
-    Y2_CHECK(y2_softmax_rows((const float *)pr->out, (float *)r->out, l.batch * l.groups, n, l.temperature,
-                             net_stream(state.net)));
+    if (l.softmax_tree)
+        Y2_CHECK(y2_softmax_tree_rows((const float *)pr->out, (float *)r->out, l.batch * l.groups, n, l.temperature,
+                                      l.softmax_tree->groups, r->group_size_dev, r->group_offset_dev,
+                                      net_stream(state.net)));
+    else
+        Y2_CHECK(y2_softmax_rows((const float *)pr->out, (float *)r->out, l.batch * l.groups, n, l.temperature,
+                                 net_stream(state.net)));
     count_launch(state.net, 1);
 }
 
@@ -1194,6 +1242,7 @@ void y2_run_forward_from(network net, float *in_dev, y2_graph_t *graph, int *gra
         *graph_valid = 1;
     }
     Y2_CHECK(y2_graph_launch(*graph, rt->stream));
+    if (rt->defer_region) rt->region_stale = 1;
 }
 
 static void run_forward(network net)
@@ -1349,6 +1398,14 @@ static float *export_layer(network net, int i)
         Y2_CHECK(y2_malloc((void **)&rt->export_dev, rt->export_bytes));
     }
     const float *src = rt->export_dev;
+    if (l->type == REGION && rt->defer_region && rt->region_stale) {
+        y2_layer_rt *pr = (y2_layer_rt *)net.layers[i - 1].b200;
+        Y2_CHECK(y2_region_forward_strided((const float *)pr->out, pr->out_cs, (float *)r->out, net.batch, l->w * l->h,
+                                           l->n, l->classes, l->softmax || l->softmax_tree,
+                                           l->softmax_tree ? l->softmax_tree->groups : 0, r->group_size_dev,
+                                           r->group_offset_dev, rt->stream));
+        rt->region_stale = 0;
+    }
     if (r->stem_fused) {
         /* inspection path: the fused kernel never stores this activation, so recompute it with the
          * generic patch-gather + convolution kernels into scratch buffers */

@@ -416,3 +416,59 @@ def decode_region_input(net: Network, region_in: np.ndarray, thresh: float, nms:
     finally:
         for b in bufs:
             b.free()
+
+
+def tree_detect_region_input(net: Network, region_in: np.ndarray, thresh: float, nms: float, max_det: int | None = None):
+    """The sparse softmax-tree detection kernels (y2_region_tree_detect + y2_tree_nms_collect) on a given region-layer
+    INPUT (fp32 [B][n*(5+classes)][h][w], the conv-head layout), with the region layer's own anchors and tree.
+    Returns a list (per image) of detection record arrays, like network_detect_batch."""
+    lib = _lib.load()
+    l = region_layer(net)
+    assert l.type == REGION and l.softmax_tree
+    t = l.softmax_tree.contents
+    B = region_in.shape[0]
+    hw, n, classes = l.w * l.h, l.n, l.classes
+    size, total = classes + 5, hw * n
+    max_det = max_det or total
+    parent = np.ctypeslib.as_array(t.parent, (t.n,)).astype(np.int32)
+    gsize = np.ctypeslib.as_array(t.group_size, (t.groups,)).astype(np.int32)
+    goff = np.ctypeslib.as_array(t.group_offset, (t.groups,)).astype(np.int32)
+    owner = np.where(parent[goff] < 0, t.n, parent[goff])          # node every group hangs under (t.n = virtual root)
+    order = np.argsort(owner, kind="stable").astype(np.int32)
+    child_ptr = np.zeros(t.n + 2, np.int32)
+    np.add.at(child_ptr, owner + 1, 1)
+    child_ptr = np.cumsum(child_ptr).astype(np.int32)
+    lib.y2_tree_rec_bytes.restype = C.c_size_t
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.y2_region_tree_detect.restype = i
+    lib.y2_region_tree_detect.argtypes = [vp, i, vp, i, i, i, i, i, f, i, vp, vp, vp, vp, vp, vp]
+    lib.y2_tree_nms_collect.restype = i
+    lib.y2_tree_nms_collect.argtypes = [vp, i, i, f, f, vp, vp, i, vp]
+    bufs = []
+
+    def dev(nbytes, host=None):
+        b = _DevBuf(nbytes, host)
+        bufs.append(b)
+        return b
+
+    try:
+        xin = dev(region_in.nbytes, region_in.astype(np.float32))
+        flat = dev(region_in.nbytes)
+        _lib.check(lib.y2_nchw_to_flat_f32(xin.ptr, flat.ptr, B, n * size, hw, None), "nchw_to_flat")
+        biases = dev(n * 2 * 4, np.ctypeslib.as_array(l.biases, (n * 2,)).astype(np.float32))
+        rec = dev(B * total * lib.y2_tree_rec_bytes())
+        det = dev(B * max_det * C.sizeof(Detection))
+        cnt = dev(B * 4)
+        _lib.check(lib.y2_region_tree_detect(flat.ptr, n * size, biases.ptr, B, l.w, l.h, n, classes, thresh, l.classfix,
+                                             dev(gsize.nbytes, gsize).ptr, dev(goff.nbytes, goff).ptr,
+                                             dev(child_ptr.nbytes, child_ptr).ptr, dev(order.nbytes, order).ptr, rec.ptr,
+                                             None), "region_tree_detect")
+        _lib.check(lib.y2_tree_nms_collect(rec.ptr, B, total, thresh, nms, det.ptr, cnt.ptr, max_det, None),
+                   "tree_nms_collect")
+        counts = cnt.get(np.int32, (B,))
+        dets = det.get(np.dtype([("x", "f4"), ("y", "f4"), ("w", "f4"), ("h", "f4"), ("prob", "f4"), ("obj_id", "i4"),
+                                 ("box_index", "i4")]), (B, max_det))
+        return [dets[b, :min(counts[b], max_det)].copy() for b in range(B)], counts
+    finally:
+        for b in bufs:
+            b.free()

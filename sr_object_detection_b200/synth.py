@@ -227,6 +227,39 @@ def exact_frames(n, h, w, seed=9):
     return out
 
 
+def exact_classifier_cfg(batch=1, w=16, h=12, classes=10, extra=""):
+    """Classifier counterpart of exact_detector_cfg: one 3x3 linear convolution -> avgpool -> softmax (-> cost), head
+    output exactly representable, so the whole predict_classifier flow can be compared with the reference bit for bit.
+    extra: e.g. "tree=t.tree\n" for a WordTree softmax (net.hierarchy)."""
+    return (_net(batch, w, h) + _conv(classes, 3, bn=0, act="linear") + "[avgpool]\n\n[softmax]\ngroups=1\n" + extra
+            + "\n[cost]\ntype=sse\n\n")
+
+
+def write_classifier_set(root, kind, w=16, h=12):
+    """Everything predict_classifier reads, under `root`: net.cfg, net.weights, image.ppm (network-sized, bytes 0/255),
+    other.ppm (another size: goes through the letterbox resize), names.list, data.cfg (+ t.tree for kind "tree")."""
+    root = Path(root)
+    classes = 30 if kind == "tree" else 10
+    extra = ""
+    if kind == "tree":
+        write_tree(root / "t.tree", n=classes, fanout=3, roots=3)
+        extra = "tree=t.tree\n"
+    cfg_text = exact_classifier_cfg(batch=1, w=w, h=h, classes=classes, extra=extra)
+    (root / "net.cfg").write_text(cfg_text)
+    (sp,) = conv_specs_from_cfg(cfg_text)
+    rng = np.random.default_rng(23)
+    biases = (rng.integers(-32, 33, sp.filters) / 64.0).astype(np.float32)
+    wts = (rng.integers(-32, 33, (sp.filters, sp.channels * 9)) / 256.0).astype(np.float32)
+    with open(root / "net.weights", "wb") as f:
+        f.write(struct.pack("<iiii", 0, 1, 0, 0))
+        f.write(biases.tobytes())
+        f.write(wts.tobytes())
+    binary_ppm(root / "image.ppm", w, h, seed=400)
+    binary_ppm(root / "other.ppm", w + 9, h + 4, seed=401)
+    (root / "names.list").write_text("".join(f"label{j}\n" for j in range(classes)))
+    (root / "data.cfg").write_text(f"classes={classes}\nnames=names.list\ntop=3\n")
+
+
 def region_only_cfg(batch, cells_w, cells_h, anchors, classes, num, extra=""):
     """A network that is ONLY the region layer over a [num*(5+classes)][cells_h][cells_w] input: lets the CPU
     checkers decode a given head output without allocating the whole detector (parse_region asserts

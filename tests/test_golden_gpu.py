@@ -94,3 +94,37 @@ def test_do_nms_unsorted_bit_exact_vs_reference_golden():
         lib.do_nms(boxes.ctypes.data_as(C.POINTER(dn.Box)), rows, total, classes, float(d[f"thresh_{tag}"]))
         assert np.array_equal(_bits(probs), _bits(d[f"out_{tag}"])), \
             f"do_nms {tag}: {(probs != d[f'out_{tag}']).sum()} values differ"
+
+
+@pytest.mark.parametrize("name", ["region_tree_220", "region_tree_wide"])
+def test_sparse_tree_detection_equals_reference_golden(tmp_path, monkeypatch, name):
+    """The detection entries of a softmax-tree network do not run the dense 9418-way pass: y2_region_tree_detect walks
+    only the groups on the path of classes above .5 and y2_tree_nms_collect works on one (class, value) record per
+    box.  Must give exactly the reference's final detections (softmax_tree + hierarchy_predictions +
+    get_region_boxes + do_nms_sort + the max_index pick, golden `dets`), incl. groups wider than a warp."""
+    d = np.load(GOLDEN / f"{name}.npz")
+    _materialise(d, tmp_path)
+    monkeypatch.chdir(tmp_path)
+    dn.set_gpu_index(-1)
+    net = dn.parse_network_cfg("net.cfg")  # host description only (a region layer alone is not a plannable network)
+    dn.set_gpu_index(0)
+    dn.lib().cuda_set_device(0)
+    B = d["region_in"].shape[0]
+    dets, counts = dn.tree_detect_region_input(net, d["region_in"], float(d["thresh"]), float(d["nms"]))
+    want = d["dets"].reshape(-1, 8)
+    assert len(want) > 0
+    got = np.array([(b, r["box_index"], r["obj_id"], r["prob"], r["x"], r["y"], r["w"], r["h"])
+                    for b in range(B) for r in dets[b]], np.float32).reshape(-1, 8)
+    assert got.shape == want.shape, f"{len(got)} detections, the reference has {len(want)}"
+    assert np.array_equal(_bits(got), _bits(want))
+    # and without NMS: every box whose hierarchy walk ends above .5 with objectness above thresh
+    dets0, _ = dn.tree_detect_region_input(net, d["region_in"], float(d["thresh"]), 0.0)
+    pre = d["probs_pre"].reshape(B, -1, net.layers[net.n - 1].classes)
+    for b in range(B):
+        obj = pre[b].argmax(1)
+        p = pre[b][np.arange(len(obj)), obj]
+        keep = np.nonzero(p > float(d["thresh"]))[0]
+        assert [int(r["box_index"]) for r in dets0[b]] == keep.tolist()
+        assert [int(r["obj_id"]) for r in dets0[b]] == obj[keep].tolist()
+        assert np.array_equal(_bits(np.array([r["prob"] for r in dets0[b]], np.float32)), _bits(p[keep]))
+    dn.free_network(net)

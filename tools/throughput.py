@@ -26,7 +26,8 @@ if name == "yolo9000":
     kw["tree"] = str(tmp / "9k.tree")
 cfg_text = synth.CFGS[name](batch=batch, w=side, h=side, **kw)
 (tmp / "n.cfg").write_text(cfg_text)
-synth.write_weights(tmp / "n.weights", cfg_text, seed=1234)
+import os  # noqa: E402
+synth.write_weights(tmp / "n.weights", cfg_text, seed=1234, head_gain=float(os.environ.get("Y2_HEAD_GAIN", "1")))
 dn.set_gpu_index(0)
 lib = dn.lib()
 net = dn.parse_network_cfg(tmp / "n.cfg")
