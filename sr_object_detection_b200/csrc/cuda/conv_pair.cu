@@ -172,8 +172,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_launch_dependents();
     if (warp == 0) {
         // ===================== slab producer (both CTAs, own 128 positions) =====================
+        pdl_wait();  // the activations are the previous layer's output; weights (warp 2) are prefetched meanwhile
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * kPairRowBytes;
@@ -501,9 +503,11 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
     if (pl->taps == 9)
-        conv_pair_kernel<9><<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
+        Y2_CUDA_CHECK(launch_pdl(conv_pair_kernel<9>, dim3(pl->grid), dim3(kPairThreads), pl->smem_bytes, st, pl->tm_a,
+                                 pl->tm_b, pl->tm_out, pl->slab));
     else
-        conv_pair_kernel<1><<<pl->grid, kPairThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->tm_out, pl->slab);
+        Y2_CUDA_CHECK(launch_pdl(conv_pair_kernel<1>, dim3(pl->grid), dim3(kPairThreads), pl->smem_bytes, st, pl->tm_a,
+                                 pl->tm_b, pl->tm_out, pl->slab));
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

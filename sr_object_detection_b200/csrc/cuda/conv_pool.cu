@@ -118,8 +118,10 @@ conv_pool_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_launch_dependents();
     if (warp == 0) {
         // ===================== patch producer: one 3-D TMA box per tile =====================
+        pdl_wait();  // activations = the previous layer's output (weights are prefetched by warp 2 meanwhile)
         int it = 0;
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
@@ -443,7 +445,8 @@ int pool_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
 #define Y2_CASE(BN, BK, TPS)                                                                                     \
     if (pl->block_n == BN && pl->block_k == BK) {                                                                \
-        conv_pool_kernel<BN, BK, TPS><<<pl->grid, kPoolThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->pool); \
+        Y2_CUDA_CHECK(launch_pdl(conv_pool_kernel<BN, BK, TPS>, dim3(pl->grid), dim3(kPoolThreads), pl->smem_bytes, st, \
+                                 pl->tm_a, pl->tm_b, pl->pool));                                                        \
         Y2_LAUNCH_CHECK();                                                                                       \
         return Y2_OK;                                                                                            \
     }

@@ -124,8 +124,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_launch_dependents();
     if (warp == 0) {
         // ===================== slab producer =====================
+        pdl_wait();  // activations = the previous layer's output (weights are prefetched by warp 2 meanwhile)
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * Cfg::kRowBytes;
@@ -490,8 +492,8 @@ int slab_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
 #define Y2_CASE(BN, BK, ACCS, TPS, TAPS)                                                                       \
     if (pl->block_n == BN && pl->block_k == BK && pl->taps == TAPS) {                                            \
-        conv_slab_kernel<BN, BK, ACCS, TPS, TAPS><<<pl->grid, kSlabThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, \
-                                                                                                  pl->tm_out, pl->slab); \
+        Y2_CUDA_CHECK(launch_pdl(conv_slab_kernel<BN, BK, ACCS, TPS, TAPS>, dim3(pl->grid), dim3(kSlabThreads),         \
+                                 pl->smem_bytes, st, pl->tm_a, pl->tm_b, pl->tm_out, pl->slab));                         \
         Y2_LAUNCH_CHECK();                                                                                       \
         return Y2_OK;                                                                                            \
     }

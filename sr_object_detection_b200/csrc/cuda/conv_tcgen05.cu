@@ -96,8 +96,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    pdl_launch_dependents();
     if (warp == 0) {
         // ===================== TMA producer (whole warp waits, one elected lane issues) ==========
+        pdl_wait();  // activations = the previous layer's output
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -316,7 +318,8 @@ static int prepare_cfg()
 template <int BN, int BK>
 static int launch_cfg(const y2_conv_plan *pl, cudaStream_t st)
 {
-    conv_tcgen05_kernel<BN, BK><<<pl->grid, kThreads, pl->smem_bytes, st>>>(pl->tm_a, pl->tm_b, pl->prm);
+    Y2_CUDA_CHECK(launch_pdl(conv_tcgen05_kernel<BN, BK>, dim3(pl->grid), dim3(kThreads), pl->smem_bytes, st, pl->tm_a,
+                             pl->tm_b, pl->prm));
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

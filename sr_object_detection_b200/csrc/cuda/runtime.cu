@@ -23,6 +23,13 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+bool pdl_enabled()
+{
+    static int cached = -1;
+    if (cached < 0) cached = getenv("Y2_NO_PDL") ? 0 : 1;
+    return cached != 0;
+}
+
 int sm_count()
 {
     static int cached[64] = {0};

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "yolo2_b200_kernels.h"
 
@@ -35,6 +36,43 @@ void set_error(const char *fmt, ...);
 static inline cudaStream_t to_stream(y2_stream_t s) { return (cudaStream_t)s; }
 
 int sm_count();
+
+// ---- programmatic dependent launch ---------------------------------------------------
+// The layer schedule is a chain of persistent kernels; launched with the programmatic-serialisation attribute, the
+// CTAs of layer i+1 are scheduled on an SM as soon as layer i's CTA there has finished: they set up their barriers,
+// allocate TMEM and prefetch WEIGHT tiles (which do not depend on layer i) while layer i's last wave drains, and
+// only the warp that loads ACTIVATIONS blocks in pdl_wait() until layer i has completed and its stores are visible.
+// Without the attribute both instructions are no-ops.  Y2_NO_PDL=1 launches everything the plain way.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// let the next kernel of the stream start its prologue once every CTA of this grid has got this far
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// block until the kernels this one depends on have completed and their memory operations are visible
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---- PTX wrappers -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
