@@ -269,6 +269,15 @@ void print_detector_detections(FILE **fps, char *id, box *boxes, float **probs, 
 void print_imagenet_detections(FILE *fp, int id, box *boxes, float **probs, int total, int classes, int w,
                                int h);                                             /* detector.c:223-242 */
 
+/* ---- demo.c:57-230: the fetch / detect video pipeline, fed and drained by callbacks (the reference is wired to an
+ * OpenCV capture and window).  source fills one uint8 interleaved RGB frame at the network's size and returns 0 at the
+ * end of the stream; sink receives, per frame and in stream order, what detect_in_thread hands to the drawing code:
+ * boxes[total], probs[total][classes] after the 3-frame mean, get_region_boxes and do_nms(.4). ---------------------- */
+typedef int (*y2_frame_source)(void *ctx, unsigned char *rgb_hwc, int w, int h);
+typedef void (*y2_detection_sink)(void *ctx, int frame, box *boxes, float **probs, int total, int classes);
+int demo_frames(char *cfgfile, char *weightfile, float thresh, y2_frame_source source, void *source_ctx,
+                y2_detection_sink sink, void *sink_ctx);
+
 /* ---- option_list.h:12-21, list.h, utils.h --------------------------------------------- */
 typedef struct node { void *val; struct node *next; struct node *prev; } node;
 typedef struct list { int size; node *front; node *back; } list;

@@ -163,6 +163,19 @@ def binary_ppm(path, w, h, seed):
     return px
 
 
+def binary_frames(n, h, w, seed):
+    """n uint8 RGB frames [n][h][w][3] of 0 / 255 bytes; consecutive frames share most pixels (a block moves)"""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 2, (h, w, 3)).astype(np.uint8) * 255
+    out = np.empty((n, h, w, 3), np.uint8)
+    for i in range(n):
+        fr = base.copy()
+        x0 = (5 * i) % max(w - 8, 1)
+        fr[4:12, x0:x0 + 8] = rng.integers(0, 2, (8, 8, 3)).astype(np.uint8) * 255
+        out[i] = fr
+    return out
+
+
 VALIDATION_CASES = {
     # eval type -> (classes, region extras, image file names)
     "voc": (4, "", ["2008_000001", "2008_000002", "img_c", "img_d", "img_e"]),

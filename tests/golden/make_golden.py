@@ -205,6 +205,8 @@ def main():
     validation_golden()
     # 3e. the reference's predict_classifier lines (flat softmax and WordTree softmax + hierarchy_predictions)
     classifier_golden()
+    # 3f. the per-frame chain of demo.c's detect_in_thread over the reference's functions
+    demo_golden()
     # 4. classifier front end: letterbox_image and top_k (classifier.c:676-730)
     classifier_front()
     # 5. parser tables, incl. the reference's own cfg files
@@ -261,6 +263,33 @@ def validation_golden():
                 out[f"{kind}/{f.name}"] = np.frombuffer(f.read_bytes(), np.uint8)
             print("validate", kind, {f.name: len(f.read_bytes().splitlines()) for f in files})
     np.savez_compressed(OUT / "validate_ref.npz", **out)
+
+
+def demo_golden():
+    """oracle/_ref/ref_demo: network_predict -> 3-frame mean -> get_region_boxes -> do_nms(.4) per frame (demo.c:71-107)
+    on the exactly representable detector and frames of 0 / 255 bytes."""
+    exe = ROOT / "oracle" / "_ref" / "ref_demo"
+    if not exe.exists():
+        raise SystemExit("oracle/_ref/ref_demo missing: run `make -C oracle refdemo` first")
+    w, h, n, thresh = 32, 24, 5, 0.3
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        cfg_text = synth.exact_detector_cfg(batch=1, w=w, h=h)
+        (t / "net.cfg").write_text(cfg_text)
+        synth.write_exact_weights(t / "net.weights", cfg_text)
+        frames = synth.binary_frames(n, h, w, seed=31)
+        frames.tofile(t / "frames.u8")
+        (t / "out").mkdir()
+        r = subprocess.run([str(exe), "net.cfg", "net.weights", "frames.u8", str(n), str(thresh), "out"], cwd=t,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SystemExit("ref_demo failed:\n" + r.stderr[-2000:])
+        out = {"w": np.int32(w), "h": np.int32(h), "n": np.int32(n), "thresh": np.float32(thresh), "seed": np.int32(31)}
+        for f in range(n):
+            out[f"frame_{f}"] = f32(t / "out" / f"frame_{f:03d}.f32")
+        np.savez_compressed(OUT / "demo_ref.npz", **out)
+        total = w * h * 3
+        print("demo_ref: nonzero probs per frame", [int((out[f"frame_{f}"][total * 4:] != 0).sum()) for f in range(n)])
 
 
 def classifier_golden():
