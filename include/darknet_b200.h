@@ -220,6 +220,11 @@ layer make_shortcut_layer(int batch, int index, int w, int h, int c, int w2, int
 layer make_avgpool_layer(int batch, int w, int h, int c);                          /* avgpool_layer.c:5-30 */
 layer make_softmax_layer(int batch, int inputs, int groups);                       /* softmax_layer.c:11-33 */
 layer make_cost_layer(int batch, int inputs, COST_TYPE type, float scale);         /* cost_layer.c:36-60 */
+layer make_connected_layer(int batch, int inputs, int outputs, ACTIVATION activation,
+                           int batch_normalize);                                   /* connected_layer.c:13-100 */
+layer make_dropout_layer(int batch, int inputs, float probability);                /* dropout_layer.c:7-26 */
+void forward_connected_layer_gpu(layer l, network_state state);      /* connected_layer.c:271-293 */
+void forward_dropout_layer_gpu(layer l, network_state state);        /* dropout_layer_kernels.cu: identity at inference */
 void forward_convolutional_layer_gpu(layer l, network_state state);  /* convolutional_kernels.cu:77-131 */
 void forward_maxpool_layer_gpu(layer l, network_state state);        /* maxpool_layer_kernels.cu:86-100 */
 void forward_reorg_layer_gpu(layer l, network_state state);          /* reorg_layer.c:97-104 */

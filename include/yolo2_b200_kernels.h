@@ -312,6 +312,15 @@ int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_
  * add_f32_cs / out_cpad floats per position.  A chain of shortcuts then accumulates in fp32 (as the
  * reference does) while the convolutions keep reading the bf16 tensors. */
 
+/* ---- connected layer (replaces connected_layer.c:271-293: fill + gemm_ongpu + batchnorm + axpy bias + activate):
+ *      the input (a bf16 padded-NHWC tensor, or an fp32 vector with row stride in_stride) becomes one padded-NHWC
+ *      position per image, bf16 [B][2][2][kpad] (zero-initialised by the caller), and the layer runs as a 1x1
+ *      convolution plan over it.  Tensor sources are packed position-major: k = (y*w + x)*c + ch. */
+int y2_fc_pack_tensor(const void *in, int in_cs, int c, int h, int w, void *dst, int kpad, int batch, y2_stream_t s);
+int y2_fc_pack_vec(const float *in, int in_stride, int n, void *dst, int kpad, int batch, y2_stream_t s);
+/* any activation of activations.h:6-8 in place on a bf16 padded-NHWC tensor (valid positions, real channels) */
+int y2_activate_bf16(void *x, int cs, int c, int batch, int h, int w, int activation, y2_stream_t s);
+
 /* ---- fp32 vector helpers behind fill/copy/axpy/scal_ongpu and activate_array_ongpu
  * (blas_kernels.cu:402-470,560-616; activation_kernels.cu:143-159).  inc* in elements.  Not on the
  * detection hot path. */

@@ -579,9 +579,113 @@ __global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// connected layer input (connected_layer.c:122-155 reads state.input as a flat vector): the tensor of the layer
+// before it, or a vector, as ONE padded-NHWC position per image ([B][2][2][kpad], h = w = 1), so that the layer is a
+// 1x1 convolution on the tensor cores.  A tensor source is laid out position-major ((y*w + x)*c + ch); the weights
+// are permuted to that order when they are uploaded (the reference's flat index is ch*h*w + y*w + x).
+// ---------------------------------------------------------------------------------
+__global__ void fc_pack_tensor_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int c, int h, int w,
+                                      __nv_bfloat16 *__restrict__ dst, int kpad, int batch)
+{
+    const long long per = (long long)h * w * c;
+    const long long total = (long long)batch * per;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / per);
+        const long long k = t - (long long)b * per;
+        const int ch = (int)(k % c);
+        const int pos = (int)(k / c);
+        const int y = pos / w, x = pos - y * w;
+        dst[(size_t)b * 4 * kpad + k] = in[(((size_t)b * (h + 1) + y) * (w + 1) + x) * in_cs + ch];
+    }
+}
+
+__global__ void fc_pack_vec_kernel(const float *__restrict__ in, int in_stride, int n, __nv_bfloat16 *__restrict__ dst,
+                                   int kpad, int batch)
+{
+    const long long total = (long long)batch * n;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / n);
+        const int k = (int)(t - (long long)b * n);
+        dst[(size_t)b * 4 * kpad + k] = __float2bfloat16_rn(in[(size_t)b * in_stride + k]);
+    }
+}
+
+// ACTIVATION numbering of activations.h:6-8 (same table as vec_f32.cu)
+__device__ __forceinline__ float activate_any(float x, int a)
+{
+    switch (a) {
+    case 0: return 1.f / (1.f + expf(-x));
+    case 1: return x > 0.f ? x : 0.f;
+    case 2: return x > 0.f ? x : .01f * x;
+    case 3: return x;
+    case 4: return (x > 0.f ? x : 0.f) + .1f * x;
+    case 5: return (2.f / (1.f + expf(-2.f * x)) - 1.f);
+    case 6: return x < -4.f ? .01f * (x + 4.f) : x > 4.f ? .01f * (x - 4.f) + 1.f : .125f * x + .5f;
+    case 7: return x > 0.f ? x : .1f * x;
+    case 8: return x >= 0.f ? x : expf(x) - 1.f;
+    case 9: return 2.f / (1.f + expf(-x)) - 1.f;
+    case 10: {
+        const int n = (int)floorf(x);
+        return (n % 2 == 0) ? floorf(x / 2.f) : (x - n) + floorf(x / 2.f);
+    }
+    case 11: return x < -1.f ? -1.f : x > 1.f ? 1.f : x;
+    case 12: return x < 0.f ? .001f * x : x > 1.f ? .001f * (x - 1.f) + 1.f : x;
+    }
+    return x;
+}
+
+// any of the 13 activations on a bf16 padded-NHWC tensor in place: valid positions and real channels only (pads and
+// padding channels stay zero whatever f(0) is).  Used behind a convolution whose activation the tensor-core epilogue
+// does not implement (it then runs LINEAR): relu, elu, tanh, ... of classifier cfgs.
+__global__ void activate_bf16_kernel(__nv_bfloat16 *__restrict__ x, int cs, int c, int batch, int h, int w, int act)
+{
+    const long long total = (long long)batch * h * w * c;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const long long p = t / c;
+        const int xx = (int)(p % w);
+        const int yy = (int)((p / w) % h);
+        const int b = (int)(p / ((long long)w * h));
+        __nv_bfloat16 *q = x + (((size_t)b * (h + 1) + yy) * (w + 1) + xx) * cs + ch;
+        *q = __float2bfloat16_rn(activate_any(__bfloat162float(*q), act));
+    }
+}
+
 } // namespace y2
 
 using namespace y2;
+
+extern "C" int y2_fc_pack_tensor(const void *in, int in_cs, int c, int h, int w, void *dst, int kpad, int batch,
+                                 y2_stream_t s)
+{
+    if (!in || !dst || batch <= 0 || (long long)h * w * c > kpad) return Y2_EINVAL;
+    fc_pack_tensor_kernel<<<grid_for((long long)batch * h * w * c, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, in_cs, c, h, w, (__nv_bfloat16 *)dst, kpad, batch);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_fc_pack_vec(const float *in, int in_stride, int n, void *dst, int kpad, int batch, y2_stream_t s)
+{
+    if (!in || !dst || batch <= 0 || n > kpad) return Y2_EINVAL;
+    fc_pack_vec_kernel<<<grid_for((long long)batch * n, 256), 256, 0, to_stream(s)>>>(in, in_stride, n,
+                                                                                    (__nv_bfloat16 *)dst, kpad, batch);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_activate_bf16(void *x, int cs, int c, int batch, int h, int w, int activation, y2_stream_t s)
+{
+    if (!x || activation < 0 || activation > 12) return Y2_EINVAL;
+    activate_bf16_kernel<<<grid_for((long long)batch * h * w * c, 256), 256, 0, to_stream(s)>>>(
+        (__nv_bfloat16 *)x, cs, c, batch, h, w, activation);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
 
 extern "C" int y2_shortcut(const void *in, int in_cs, const void *add, int add_cs, int add_c, int add_h,
                            int add_w, void *out, int out_cs, int out_c, int out_cpad, int out_h, int out_w,

@@ -45,6 +45,12 @@ typedef struct y2_layer_rt {
     int fused_into_prev; /* the maxpool of such a pair: its forward is a no-op */
     void *patches;      /* bf16 [B][H+1][W+1][kpad] */
     int wt_dirty;
+    int post_act;       /* ACTIVATION applied by a separate pass behind a LINEAR epilogue (the tensor-core epilogue
+                           implements leaky / linear / logistic only), -1: none */
+    /* connected layer: runs as a 1x1 convolution over one position per image */
+    void *fc_in;        /* bf16 [B][2][2][kpad] */
+    int fc_src;         /* layer whose output is flattened into fc_in */
+    int fc_h, fc_w, fc_c; /* extent of that tensor (h = w = 0: an fp32 vector of fc_c values) */
     /* input packing for a non-patch first layer */
     void *packed_in;
     /* reorg */

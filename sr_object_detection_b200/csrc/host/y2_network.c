@@ -369,6 +369,58 @@ layer make_cost_layer(int batch, int inputs, COST_TYPE type, float scale)
     return l;
 }
 
+/* connected_layer.c:13-100 (host description; the device side is a 1x1 convolution plan over the flattened input) */
+layer make_connected_layer(int batch, int inputs, int outputs, ACTIVATION activation, int batch_normalize)
+{
+    layer l;
+    memset(&l, 0, sizeof(l));
+    l.type = CONNECTED;
+    l.inputs = inputs;
+    l.outputs = outputs;
+    l.batch = batch;
+    l.batch_normalize = batch_normalize;
+    l.h = 1;
+    l.w = 1;
+    l.c = inputs;
+    l.out_h = 1;
+    l.out_w = 1;
+    l.out_c = outputs;
+    l.n = outputs;
+    l.size = 1;
+    l.stride = 1;
+    l.activation = activation;
+    l.weights = (float *)calloc((size_t)outputs * inputs, sizeof(float));
+    l.biases = (float *)calloc(outputs, sizeof(float));
+    float scale = sqrtf(2.f / inputs);
+    uint32_t st = 0x85EBCA6Bu ^ (uint32_t)(outputs * 131 + inputs);
+    for (size_t i = 0; i < (size_t)outputs * inputs; ++i) l.weights[i] = scale * rand_uniform_pm1(&st);
+    if (batch_normalize) {
+        l.scales = (float *)calloc(outputs, sizeof(float));
+        for (int i = 0; i < outputs; ++i) l.scales[i] = 1;
+        l.rolling_mean = (float *)calloc(outputs, sizeof(float));
+        l.rolling_variance = (float *)calloc(outputs, sizeof(float));
+    }
+    l.forward = forward_no_cpu_path;
+    l.forward_gpu = forward_connected_layer_gpu;
+    fprintf(stderr, "connected                            %4d  ->  %4d\n", inputs, outputs);
+    return l;
+}
+
+/* dropout_layer.c:7-26: identity at inference (forward_dropout_layer returns at once when !state.train) */
+layer make_dropout_layer(int batch, int inputs, float probability)
+{
+    layer l;
+    memset(&l, 0, sizeof(l));
+    l.type = DROPOUT;
+    l.inputs = inputs;
+    l.outputs = inputs;
+    l.batch = batch;
+    l.forward = forward_no_cpu_path;
+    l.forward_gpu = forward_dropout_layer_gpu;
+    fprintf(stderr, "dropout       p = %.2f               %4d  ->  %4d\n", probability, inputs, inputs);
+    return l;
+}
+
 /* ---- network queries ----------------------------------------------------------------------- */
 int y2_output_layer_index(network net)
 {
@@ -399,6 +451,7 @@ double network_conv_flops(network net)
     for (int i = 0; i < net.n; ++i) {
         layer l = net.layers[i];
         if (l.type == CONVOLUTIONAL) ops += 2.0 * l.n * l.size * l.size * l.c * l.out_h * l.out_w;
+        else if (l.type == CONNECTED) ops += 2.0 * l.inputs * l.outputs; /* darknet.c:126-128 */
     }
     return ops;
 }
@@ -449,6 +502,7 @@ static void free_layer_rt(layer *l)
     y2_free(r->alpha_dev);
     y2_free(r->beta_dev);
     y2_free(r->patches);
+    y2_free(r->fc_in);
     y2_free(r->packed_in);
     y2_free(r->reorg_table);
     y2_free(r->stream_f32);
@@ -511,7 +565,15 @@ void y2_push_convolutional_layer(layer *l)
     const int kk = l->size * l->size;
     const size_t elems = (size_t)r->npad * r->ktot;
     uint16_t *w = (uint16_t *)calloc(elems, sizeof(uint16_t));
-    if (r->use_patches == 3) {
+    if (l->type == CONNECTED) {
+        /* reference flat index ch*h*w + pos (NCHW) -> position-major (pos*c + ch) of y2_fc_pack_tensor */
+        const int hw = r->fc_h > 0 ? r->fc_h * r->fc_w : 1, c = r->fc_c;
+        for (int f = 0; f < l->outputs; ++f)
+            for (int ch = 0; ch < c; ++ch)
+                for (int pos = 0; pos < hw; ++pos)
+                    w[(size_t)f * r->ktot + (size_t)pos * c + ch] =
+                        y2_f32_to_bf16(l->weights[(size_t)f * l->inputs + (size_t)ch * hw + pos]);
+    } else if (r->use_patches == 3) {
         /* K index = (c*k + r)*8 + s (y2_gather_rows_f32) */
         for (int f = 0; f < l->n; ++f)
             for (int c = 0; c < l->c; ++c)
@@ -635,6 +697,12 @@ static y2_view input_view(network *net, int i)
     return v;
 }
 
+/* the epilogue's activation code; anything else runs LINEAR and gets a separate activation pass (post_act) */
+static int epilogue_act(ACTIVATION a)
+{
+    return a == LEAKY ? Y2_ACT_LEAKY : a == LOGISTIC ? Y2_ACT_LOGISTIC : Y2_ACT_LINEAR;
+}
+
 static void build_conv_plan(network *net, int i, int batch)
 {
     layer *l = &net->layers[i];
@@ -678,7 +746,7 @@ static void build_conv_plan(network *net, int i, int batch)
     d.block_k = r->block_k;
     d.alpha = r->alpha_dev;
     d.beta = r->beta_dev;
-    d.act = (l->activation == LEAKY) ? Y2_ACT_LEAKY : (l->activation == LOGISTIC) ? Y2_ACT_LOGISTIC : Y2_ACT_LINEAR;
+    d.act = r->post_act >= 0 ? Y2_ACT_LINEAR : epilogue_act(l->activation);
     d.out = r->out;
     d.out_cs = r->out_cs;
     if (r->pool_fused) {
@@ -698,12 +766,45 @@ static void build_conv_plan(network *net, int i, int batch)
     r->write_order = y2_conv_plan_order(r->plan);
 }
 
+static void build_fc_plan(network *net, int i, int batch)
+{
+    layer *l = &net->layers[i];
+    y2_layer_rt *r = (y2_layer_rt *)l->b200;
+    if (r->plan) {
+        y2_conv_plan_destroy(r->plan);
+        r->plan = 0;
+    }
+    y2_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.in = r->fc_in;
+    d.in_cs = r->kpad;
+    d.cin = r->kpad;
+    d.batch = batch;
+    d.h = 1;
+    d.w = 1;
+    d.ksize = 1;
+    d.wt = r->wt_dev;
+    d.cout = l->outputs;
+    d.npad = r->npad;
+    d.block_n = r->block_n;
+    d.block_k = r->block_k;
+    d.alpha = r->alpha_dev;
+    d.beta = r->beta_dev;
+    d.act = r->post_act >= 0 ? Y2_ACT_LINEAR : epilogue_act(l->activation);
+    d.out = r->out;
+    d.out_cs = r->out_cs;
+    d.out_mode = Y2_OUT_F32_FLAT;
+    Y2_CHECK(y2_conv_plan_create(&d, &r->plan));
+}
+
 static void build_plans(network *net, int batch)
 {
     y2_net_rt *rt = (y2_net_rt *)net->b200;
-    for (int i = 0; i < net->n; ++i)
+    for (int i = 0; i < net->n; ++i) {
         if (net->layers[i].type == CONVOLUTIONAL && !((y2_layer_rt *)net->layers[i].b200)->stem_fused)
             build_conv_plan(net, i, batch);
+        else if (net->layers[i].type == CONNECTED) build_fc_plan(net, i, batch);
+    }
     rt->plan_batch = batch;
     if (rt->graph) {
         y2_graph_destroy(rt->graph);
@@ -735,14 +836,15 @@ void y2_plan_network(network *net)
         y2_layer_rt *r = (y2_layer_rt *)calloc(1, sizeof(y2_layer_rt));
         l->b200 = r;
         r->placed_in = -1;
+        r->post_act = -1;
         switch (l->type) {
         case CONVOLUTIONAL: {
             /* 1x1 and 3x3 stride-1 'same' layers run on the shifted-descriptor kernels; every other
              * size / stride / padding goes through a patch gather + 1x1 GEMM (use_patches) */
             const int native = l->stride == 1 && (l->size == 1 || l->size == 3) && l->pad == l->size / 2;
             if (l->stride < 1 || l->size < 1 || l->out_h < 1 || l->out_w < 1) unsupported(i, "degenerate convolution");
-            if (l->activation != LEAKY && l->activation != LINEAR && l->activation != LOGISTIC)
-                unsupported(i, "activation other than leaky/linear/logistic");
+            r->post_act = (l->activation != LEAKY && l->activation != LINEAR && l->activation != LOGISTIC)
+                              ? (int)l->activation : -1;
             if (l->binary || l->xnor) unsupported(i, "binary/xnor convolution");
             r->out_kind = consumer_wants_f32(net, i) ? Y2_KIND_F32_FLAT : Y2_KIND_BF16_PADDED;
             r->cpad = (r->out_kind == Y2_KIND_F32_FLAT) ? l->n : storage_channels(l->n);
@@ -875,6 +977,44 @@ void y2_plan_network(network *net)
             r->cpad = l->inputs;
             break;
         }
+        case CONNECTED: {
+            /* the tensor (or vector) this layer flattens: the previous layer, looking through dropout layers */
+            int src = i - 1;
+            while (src >= 0 && net->layers[src].type == DROPOUT) --src;
+            if (src < 0) unsupported(i, "connected layer without an input layer");
+            y2_layer_rt *sr = (y2_layer_rt *)net->layers[src].b200;
+            layer *sl = &net->layers[src];
+            r->fc_src = src;
+            if (sr->out_kind == Y2_KIND_BF16_PADDED) {
+                r->fc_h = sl->out_h;
+                r->fc_w = sl->out_w;
+                r->fc_c = sl->out_c;
+                if (l->inputs != sl->out_h * sl->out_w * sl->out_c) unsupported(i, "connected layer input size");
+            } else if (sr->out_kind == Y2_KIND_F32_VEC) {
+                r->fc_c = l->inputs;
+                if (l->inputs != sr->cpad) unsupported(i, "connected layer input size");
+            } else {
+                unsupported(i, "connected layer behind a flat head");
+            }
+            r->post_act = (l->activation != LEAKY && l->activation != LINEAR && l->activation != LOGISTIC)
+                              ? (int)l->activation : -1;
+            r->out_kind = Y2_KIND_F32_VEC;
+            r->cpad = l->outputs;
+            r->block_n = pick_block_n(l->outputs);
+            r->npad = round_up(l->outputs, r->block_n);
+            r->kpad = round_up(l->inputs, 64);
+            r->cin_pad = r->kpad;
+            r->ktot = r->kpad;
+            r->block_k = 64;
+            break;
+        }
+        case DROPOUT: {
+            y2_layer_rt *pr = i ? (y2_layer_rt *)net->layers[i - 1].b200 : 0;
+            if (!pr) unsupported(i, "dropout without an input layer");
+            r->out_kind = pr->out_kind; /* identity at inference: aliases its input (resolved in pass 3) */
+            r->cpad = pr->cpad;
+            break;
+        }
         case COST:
             r->out_kind = Y2_KIND_NONE;
             break;
@@ -903,7 +1043,7 @@ void y2_plan_network(network *net)
     for (int i = 0; i < net->n; ++i) {
         layer *l = &net->layers[i];
         y2_layer_rt *r = (y2_layer_rt *)l->b200;
-        if (l->type == ROUTE || r->out_kind == Y2_KIND_NONE) continue;
+        if (l->type == ROUTE || l->type == DROPOUT || r->out_kind == Y2_KIND_NONE) continue;
         if (r->stem_fused || r->pool_fused) { /* the full-resolution activation is never materialised */
             r->out = 0;
             r->out_cs = r->cpad;
@@ -943,6 +1083,11 @@ void y2_plan_network(network *net)
             r->out = ir->out;
             r->out_cs = ir->out_cs;
         }
+        if (l->type == DROPOUT) { /* layers are visited in order: the input's view is final */
+            y2_layer_rt *pr = (y2_layer_rt *)net->layers[i - 1].b200;
+            r->out = pr->out;
+            r->out_cs = pr->out_cs;
+        }
         l->output_gpu = (float *)r->out;
     }
 
@@ -960,6 +1105,15 @@ void y2_plan_network(network *net)
             if (r->stem_fused) Y2_CHECK(y2_stem_prepare());
             else if (r->use_patches) r->patches = dev_alloc_zero(padded_bytes(B, l->out_h, l->out_w, r->kpad));
             else if (i == 0) r->packed_in = dev_alloc_zero(padded_bytes(B, l->h, l->w, r->cin_pad));
+            y2_push_convolutional_layer(l);
+        } else if (l->type == CONNECTED) {
+            Y2_CHECK(y2_malloc(&r->wt_dev, (size_t)r->npad * r->ktot * 2));
+            Y2_CHECK(y2_malloc((void **)&r->alpha_dev, (size_t)r->npad * 4));
+            Y2_CHECK(y2_malloc((void **)&r->beta_dev, (size_t)r->npad * 4));
+            l->weights_gpu = (float *)r->wt_dev;
+            l->biases_gpu = r->beta_dev;
+            l->scales_gpu = r->alpha_dev;
+            r->fc_in = dev_alloc_zero(padded_bytes(B, 1, 1, r->kpad));
             y2_push_convolutional_layer(l);
         } else if (l->type == SHORTCUT) {
             /* a later shortcut that adds this one's output reads it in fp32, so the residual stream is
@@ -1077,6 +1231,37 @@ void forward_convolutional_layer_gpu(layer l, network_state state)
     }
     Y2_CHECK(y2_conv_plan_launch(r->plan, s));
     count_launch(state.net, 1);
+    if (r->post_act >= 0) { /* an activation the epilogue does not implement: the plan ran LINEAR */
+        if (r->out_kind == Y2_KIND_F32_FLAT)
+            Y2_CHECK(y2_vec_activate((float *)r->out, (long long)l.batch * l.out_h * l.out_w * r->out_cs, r->post_act, s));
+        else
+            Y2_CHECK(y2_activate_bf16(r->out, r->out_cs, l.out_c, l.batch, l.out_h, l.out_w, r->post_act, s));
+        count_launch(state.net, 1);
+    }
+}
+
+/* connected_layer.c:271-293 as a 1x1 convolution: flatten the input into one position per image, run the plan */
+void forward_connected_layer_gpu(layer l, network_state state)
+{
+    y2_layer_rt *r = y2_lrt(l);
+    y2_stream_t s = net_stream(state.net);
+    y2_layer_rt *sr = y2_lrt(state.net.layers[r->fc_src]);
+    if (r->fc_h > 0)
+        Y2_CHECK(y2_fc_pack_tensor(sr->out, sr->out_cs, r->fc_c, r->fc_h, r->fc_w, r->fc_in, r->kpad, l.batch, s));
+    else
+        Y2_CHECK(y2_fc_pack_vec((const float *)sr->out, sr->out_cs, r->fc_c, r->fc_in, r->kpad, l.batch, s));
+    Y2_CHECK(y2_conv_plan_launch(r->plan, s));
+    count_launch(state.net, 2);
+    if (r->post_act >= 0) {
+        Y2_CHECK(y2_vec_activate((float *)r->out, (long long)l.batch * r->out_cs, r->post_act, s));
+        count_launch(state.net, 1);
+    }
+}
+
+void forward_dropout_layer_gpu(layer l, network_state state)
+{
+    (void)l;
+    (void)state; /* dropout_layer.c:40: if (!state.train) return; */
 }
 
 void forward_maxpool_layer_gpu(layer l, network_state state)

@@ -305,6 +305,27 @@ static layer parse_softmax(list *options, size_params params)
     return l;
 }
 
+/* parser.c:214-224 */
+static layer parse_connected(list *options, size_params params)
+{
+    int output = option_find_int(options, "output", 1);
+    char *activation_s = option_find_str(options, "activation", "logistic");
+    ACTIVATION activation = get_activation(activation_s);
+    int batch_normalize = option_find_int_quiet(options, "batch_normalize", 0);
+    return make_connected_layer(params.batch, params.inputs, output, activation, batch_normalize);
+}
+
+/* parser.c:389-399: the layer keeps the extent of its input */
+static layer parse_dropout(list *options, size_params params)
+{
+    float probability = option_find_float(options, "probability", .5);
+    layer l = make_dropout_layer(params.batch, params.inputs, probability);
+    l.out_w = params.w;
+    l.out_h = params.h;
+    l.out_c = params.c;
+    return l;
+}
+
 static layer parse_cost(list *options, size_params params)
 {
     char *type_s = option_find_str(options, "type", "sse");
@@ -378,6 +399,8 @@ network parse_network_cfg(char *filename)
             net.hierarchy = l.softmax_tree;
             break;
         case COST: l = parse_cost(options, params); break;
+        case CONNECTED: l = parse_connected(options, params); break;
+        case DROPOUT: l = parse_dropout(options, params); break;
         case BLANK: fprintf(stderr, "Type not recognized: %s\n", s->type); break;
         default:
             /* layer types outside the detection forward path */
@@ -440,6 +463,20 @@ static void load_convolutional_weights(layer *l, FILE *fp)
     if (gpu_index >= 0 && l->b200) y2_push_convolutional_layer(l);
 }
 
+/* parser.c:897-919: biases, weights[outputs][inputs] (transposed in very old files), then the batchnorm vectors */
+static void load_connected_weights(layer *l, FILE *fp, int transpose)
+{
+    read_floats(l->biases, l->outputs, fp);
+    read_floats(l->weights, (size_t)l->outputs * l->inputs, fp);
+    if (transpose) transpose_matrix(l->weights, l->inputs, l->outputs);
+    if (l->batch_normalize && !l->dontloadscales) {
+        read_floats(l->scales, l->outputs, fp);
+        read_floats(l->rolling_mean, l->outputs, fp);
+        read_floats(l->rolling_variance, l->outputs, fp);
+    }
+    if (gpu_index >= 0 && l->b200) y2_push_convolutional_layer(l);
+}
+
 void load_weights_upto(network *net, char *filename, int cutoff)
 {
     if (net->gpu_index >= 0) cuda_set_device(net->gpu_index);
@@ -460,10 +497,12 @@ void load_weights_upto(network *net, char *filename, int cutoff)
         if (fread(&iseen, sizeof(int), 1, fp) != 1) error("weights file: truncated header");
         *net->seen = iseen;
     }
+    const int transpose = (major > 1000) || (minor > 1000); /* parser.c:1035 */
     for (int i = 0; i < net->n && i < cutoff; ++i) {
         layer *l = &net->layers[i];
         if (l->dontload) continue;
         if (l->type == CONVOLUTIONAL) load_convolutional_weights(l, fp);
+        if (l->type == CONNECTED) load_connected_weights(l, fp, transpose);
     }
     fprintf(stderr, "Done!\n");
     fclose(fp);
@@ -486,6 +525,15 @@ void save_weights_upto(network net, char *filename, int cutoff)
     fwrite(net.seen, sizeof(int), 1, fp);
     for (int i = 0; i < net.n && i < cutoff; ++i) {
         layer l = net.layers[i];
+        if (l.type == CONNECTED) { /* parser.c:806-820 */
+            fwrite(l.biases, sizeof(float), l.outputs, fp);
+            fwrite(l.weights, sizeof(float), (size_t)l.outputs * l.inputs, fp);
+            if (l.batch_normalize) {
+                fwrite(l.scales, sizeof(float), l.outputs, fp);
+                fwrite(l.rolling_mean, sizeof(float), l.outputs, fp);
+                fwrite(l.rolling_variance, sizeof(float), l.outputs, fp);
+            }
+        }
         if (l.type != CONVOLUTIONAL) continue;
         size_t num = (size_t)l.n * l.c * l.size * l.size;
         fwrite(l.biases, sizeof(float), l.n, fp);

@@ -288,7 +288,19 @@ REGION_PARAMS = {  # anchors, classes, num of the detector cfgs above
 }
 
 
+def mini_alexnet_cfg(batch=2, w=32, h=32, classes=10):
+    """Toy classifier in the style of cfg/alexnet.cfg: relu convolutions (an activation the tensor-core epilogue does
+    not implement), maxpools, connected layers (one with batchnorm and a non-epilogue activation), dropout, softmax."""
+    s = _net(batch, w, h) + _conv(16, 3, act="relu") + _maxpool() + _conv(32, 3, bn=0, act="relu") + _maxpool()
+    s += _conv(24, 3, act="elu")
+    s += "[connected]\noutput=96\nactivation=relu\n\n[dropout]\nprobability=.5\n\n"
+    s += "[connected]\nbatch_normalize=1\noutput=64\nactivation=tanh\n\n[dropout]\nprobability=.5\n\n"
+    s += f"[connected]\noutput={classes}\nactivation=linear\n\n"
+    return s + "[softmax]\ngroups=1\n\n[cost]\ntype=sse\n\n"
+
+
 CFGS = {
+    "mini-alexnet": mini_alexnet_cfg,
     "mini-dense": mini_dense_cfg,
     "mini-yolo": mini_yolo_cfg,
     "mini-resnet": mini_resnet_cfg,
@@ -307,11 +319,12 @@ class ConvSpec:
     size: int
     channels: int
     batch_normalize: bool
+    kind: str = "conv"   # "conv": weights[n][c][k][k]; "fc": a connected layer, weights[filters][channels]
 
 
 def conv_specs_from_cfg(cfg_text: str) -> list[ConvSpec]:
-    """Walk a cfg the way parse_network_cfg does (parser.c:585-700), tracking channels only,
-    to know what a .weights file for it must contain."""
+    """Walk a cfg the way parse_network_cfg does (parser.c:585-700), tracking the extent, to know what a
+    .weights file for it must contain: one entry per convolutional / connected layer, in order."""
     sections: list[tuple[str, dict]] = []
     for raw in cfg_text.splitlines():
         line = "".join(raw.split())
@@ -323,21 +336,35 @@ def conv_specs_from_cfg(cfg_text: str) -> list[ConvSpec]:
             k, _, v = line.partition("=")
             sections[-1][1][k] = v
     assert sections[0][0] == "[net]"
-    c = int(sections[0][1].get("channels", 3))
+    net = sections[0][1]
+    c, h, w = int(net.get("channels", 3)), int(net.get("height", 0)), int(net.get("width", 0))
     out_c: list[int] = []
     specs: list[ConvSpec] = []
     for idx, (name, opt) in enumerate(sections[1:]):
         if name == "[convolutional]":
-            n = int(opt.get("filters", 1))
-            specs.append(ConvSpec(n, int(opt.get("size", 1)), c, bool(int(opt.get("batch_normalize", 0)))))
-            c = n
+            n, k, st = int(opt.get("filters", 1)), int(opt.get("size", 1)), int(opt.get("stride", 1))
+            pad = k // 2 if int(opt.get("pad", 0)) else int(opt.get("padding", 0))
+            specs.append(ConvSpec(n, k, c, bool(int(opt.get("batch_normalize", 0)))))
+            c, h, w = n, (h + 2 * pad - k) // st + 1, (w + 2 * pad - k) // st + 1
+        elif name == "[connected]":
+            n = int(opt.get("output", 1))
+            specs.append(ConvSpec(n, 1, c * max(h, 1) * max(w, 1), bool(int(opt.get("batch_normalize", 0))), "fc"))
+            c, h, w = n, 1, 1
+        elif name == "[maxpool]":
+            st = int(opt.get("stride", 1))
+            size = int(opt.get("size", st))
+            pad = int(opt.get("padding", (size - 1) // 2))
+            h, w = (h + 2 * pad) // st, (w + 2 * pad) // st
+        elif name == "[avgpool]":
+            h, w = 1, 1
         elif name == "[route]":
             layers = [int(v) for v in opt["layers"].split(",")]
             c = sum(out_c[(idx + l) if l < 0 else l] for l in layers)
         elif name == "[reorg]":
             st = int(opt.get("stride", 1))
-            c = c * st * st
-        # maxpool / shortcut / avgpool / softmax / cost / region keep or ignore c
+            c, h, w = c * st * st, h // st, w // st
+        # shortcut / dropout / softmax / cost / region keep the extent (spatial sizes behind a route are not tracked:
+        # no cfg here puts a connected layer there)
         out_c.append(c)
     return specs
 
@@ -371,7 +398,14 @@ def write_weights(path: str | Path, cfg_text: str, seed: int = 1234, head_gain: 
             w = rng.uniform(-s, s, n * c * k * k).astype(np.float32)
             if head_gain != 1.0 and li == len(specs) - 1:
                 w = (w * np.float32(head_gain)).astype(np.float32)
-            f.write(w.tobytes())
+            if sp.kind == "fc":
+                # load_connected_weights (parser.c:897-913): biases, weights, THEN the batchnorm vectors
+                f.seek(-(3 * n * 4 if sp.batch_normalize else 0), 1)
+                f.write(w.tobytes())
+                if sp.batch_normalize:
+                    f.write(scales.tobytes() + mean.tobytes() + var.tobytes())
+            else:
+                f.write(w.tobytes())
             total += n + w.size
     return total
 

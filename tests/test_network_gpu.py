@@ -37,7 +37,9 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
                                              # non-square and odd extents: 15x11 and 13x9 cells, 2/1 pool on an odd row count
                                              ("tiny-yolo-voc", 2, (480, 352)), ("yolo-voc", 1, (416, 288)),
                                              # nested routes (a route that concatenates another route's output)
-                                             ("mini-dense", 3, 64)])
+                                             ("mini-dense", 3, 64),
+                                             # classifier cfgs: connected / dropout layers, relu / elu / tanh
+                                             ("mini-alexnet", 3, 32)])
 def test_layer_activations_match_reference(tmp_path, name, batch, side):
     """BASELINE.json configs 1-5 (at a batch the CPU reference finishes in seconds): every layer of
     the B200 forward pass against the reference's CPU forward on the same weights and images."""
