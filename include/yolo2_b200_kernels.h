@@ -211,6 +211,11 @@ int y2_reorg_table(int *table, int in_cs, int c, int h, int w, int stride, y2_st
 int y2_reorg_gather(const void *in, int in_cs, void *out, int out_cs, const int *table, int batch,
                     int c, int h, int w, int stride, y2_stream_t s);
 
+/* reverse = 1 layers (reorg_layer.c:80-81, reorg_cpu with forward = 1): in (c, h, w) -> out (c/s^2, h*s, w*s) */
+int y2_reorg_table_reverse(int *table, int in_cs, int c, int h, int w, int stride, y2_stream_t s);
+int y2_reorg_gather_reverse(const void *in, int in_cs, void *out, int out_cs, const int *table, int batch,
+                            int c, int h, int w, int stride, y2_stream_t s);
+
 /* ---- route fallback copy (replaces route_layer.c:104-117 copy_ongpu loop); the
  *      planner normally aliases producers into the concat buffer instead ------------- */
 int y2_copy_channels(const void *in, int in_cs, void *out, int out_cs, int batch, int c,

@@ -462,6 +462,25 @@ __global__ void reorg_table_kernel(int *__restrict__ table, int in_cs, int c, in
     }
 }
 
+// reverse = 1 (reorg_layer.c:80-81 -> reorg_cpu(..., forward = 1): out[out_index] = x[in_index]): a true
+// depth-to-space.  Input (c, h, w), output (c/s^2, h*s, w*s); output element (c2, h2, w2) comes from input channel
+// (h2 % s * s + w2 % s) * out_c + c2 at (h2 / s, w2 / s).  Same table layout as above, over the OUTPUT extent.
+__global__ void reorg_table_reverse_kernel(int *__restrict__ table, int in_cs, int c, int h, int w, int stride)
+{
+    const int oc = c / (stride * stride), oh = h * stride, ow = w * stride;
+    const int wp = w + 1;
+    const int total = oh * ow * oc;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int c2 = t % oc;
+        const int pos = t / oc;
+        const int w2 = pos % ow, h2 = pos / ow;
+        const int i = w2 / stride, j = h2 / stride;
+        const int offset = (h2 % stride) * stride + (w2 % stride);
+        const int k = offset * oc + c2;
+        table[t] = (j * wp + i) * in_cs + k;
+    }
+}
+
 // one thread per 8 output channels: 8 table entries, 8 two-byte gathers, one 16-byte store
 __global__ void reorg_gather_kernel(const __nv_bfloat16 *__restrict__ in, size_t in_img_elems,
                                     __nv_bfloat16 *__restrict__ out, int out_cs, const int *__restrict__ table,
@@ -893,6 +912,37 @@ extern "C" int y2_reorg_gather(const void *in, int in_cs, void *out, int out_cs,
         return Y2_EINVAL;
     }
     const int oh = h / stride, ow = w / stride;
+    const long long total = (long long)batch * (oh + 1) * (ow + 1) * (oc / 8);
+    reorg_gather_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
+        (const __nv_bfloat16 *)in, (size_t)(h + 1) * (w + 1) * in_cs, (__nv_bfloat16 *)out, out_cs, table, batch, oc,
+        oh, ow);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_reorg_table_reverse(int *table, int in_cs, int c, int h, int w, int stride, y2_stream_t s)
+{
+    if (!table || stride <= 0 || c % (stride * stride)) {
+        set_error("y2_reorg_table_reverse: c=%d not divisible by stride^2=%d", c, stride * stride);
+        return Y2_EINVAL;
+    }
+    const long long total = (long long)h * w * c;
+    reorg_table_reverse_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(table, in_cs, c, h, w, stride);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+// gather through a table built by y2_reorg_table_reverse: in (c, h, w) -> out (c/s^2, h*s, w*s)
+extern "C" int y2_reorg_gather_reverse(const void *in, int in_cs, void *out, int out_cs, const int *table, int batch,
+                                       int c, int h, int w, int stride, y2_stream_t s)
+{
+    if (!in || !out || !table || stride <= 0 || c % (stride * stride)) return Y2_EINVAL;
+    const int oc = c / (stride * stride), oh = h * stride, ow = w * stride;
+    if (oc % 8 || out_cs % 8 || ((uintptr_t)out & 15) || ((uintptr_t)table & 15)) {
+        set_error("y2_reorg_gather_reverse: needs a multiple of 8 output channels (c=%d stride=%d out_cs=%d)", c, stride,
+                  out_cs);
+        return Y2_EINVAL;
+    }
     const long long total = (long long)batch * (oh + 1) * (ow + 1) * (oc / 8);
     reorg_gather_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
         (const __nv_bfloat16 *)in, (size_t)(h + 1) * (w + 1) * in_cs, (__nv_bfloat16 *)out, out_cs, table, batch, oc,

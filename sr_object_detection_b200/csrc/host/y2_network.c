@@ -905,7 +905,8 @@ void y2_plan_network(network *net)
         case REORG: {
             y2_layer_rt *pr = i ? (y2_layer_rt *)net->layers[i - 1].b200 : 0;
             if (!pr || pr->out_kind != Y2_KIND_BF16_PADDED) unsupported(i, "maxpool/reorg without a tensor input");
-            if (l->type == REORG && l->reverse) unsupported(i, "reverse reorg");
+            if (l->type == REORG && l->reverse && (l->out_c % 8 || l->c % (l->stride * l->stride)))
+                unsupported(i, "reverse reorg to a channel count that is not a multiple of 8");
             r->out_kind = Y2_KIND_BF16_PADDED;
             if (l->type == MAXPOOL && (pr->stem_fused || pr->pool_fused)) r->fused_into_prev = 1;
             if (l->type == MAXPOOL) r->cpad = pr->cpad;
@@ -1125,7 +1126,10 @@ void y2_plan_network(network *net)
             y2_layer_rt *pr = (y2_layer_rt *)net->layers[i - 1].b200;
             if (l->out_c % 8 == 0 && r->out_cs % 8 == 0) {
                 Y2_CHECK(y2_malloc((void **)&r->reorg_table, (size_t)l->out_h * l->out_w * l->out_c * sizeof(int)));
-                Y2_CHECK(y2_reorg_table(r->reorg_table, pr->out_cs, l->c, l->h, l->w, l->stride, 0));
+                if (l->reverse) Y2_CHECK(y2_reorg_table_reverse(r->reorg_table, pr->out_cs, l->c, l->h, l->w, l->stride, 0));
+                else Y2_CHECK(y2_reorg_table(r->reorg_table, pr->out_cs, l->c, l->h, l->w, l->stride, 0));
+            } else if (l->reverse) {
+                unsupported(i, "reverse reorg into an unaligned channel slice");
             }
         } else if (l->type == SOFTMAX && l->softmax_tree) {
             tree *t = l->softmax_tree;
@@ -1278,7 +1282,10 @@ void forward_reorg_layer_gpu(layer l, network_state state)
 {
     y2_layer_rt *r = y2_lrt(l);
     y2_layer_rt *pr = y2_lrt(state.net.layers[state.index - 1]);
-    if (r->reorg_table)
+    if (r->reorg_table && l.reverse)
+        Y2_CHECK(y2_reorg_gather_reverse(pr->out, pr->out_cs, r->out, r->out_cs, r->reorg_table, l.batch, l.c, l.h, l.w,
+                                         l.stride, net_stream(state.net)));
+    else if (r->reorg_table)
         Y2_CHECK(y2_reorg_gather(pr->out, pr->out_cs, r->out, r->out_cs, r->reorg_table, l.batch, l.c, l.h, l.w,
                                  l.stride, net_stream(state.net)));
     else

@@ -288,6 +288,14 @@ REGION_PARAMS = {  # anchors, classes, num of the detector cfgs above
 }
 
 
+def mini_reorg_reverse_cfg(batch=2, w=32, h=32, classes=4, num=3):
+    """Toy detector with a reverse reorg layer (depth-to-space, reorg_layer.c:80-81): 8x8x64 -> 16x16x16."""
+    s = _net(batch, w, h) + _conv(16, 3) + _maxpool() + _conv(32, 3) + _maxpool() + _conv(64, 1)
+    s += "[reorg]\nstride=2\nreverse=1\n\n" + _conv(32, 3) + _conv(num * (classes + 5), 1, bn=0, act="linear")
+    anchors = ",".join(f"{0.6 + 0.7 * i:.2f},{0.8 + 0.5 * i:.2f}" for i in range(num))
+    return s + _region(anchors, classes, num)
+
+
 def mini_alexnet_cfg(batch=2, w=32, h=32, classes=10):
     """Toy classifier in the style of cfg/alexnet.cfg: relu convolutions (an activation the tensor-core epilogue does
     not implement), maxpools, connected layers (one with batchnorm and a non-epilogue activation), dropout, softmax."""
@@ -301,6 +309,7 @@ def mini_alexnet_cfg(batch=2, w=32, h=32, classes=10):
 
 CFGS = {
     "mini-alexnet": mini_alexnet_cfg,
+    "mini-reorg-reverse": mini_reorg_reverse_cfg,
     "mini-dense": mini_dense_cfg,
     "mini-yolo": mini_yolo_cfg,
     "mini-resnet": mini_resnet_cfg,
@@ -362,7 +371,10 @@ def conv_specs_from_cfg(cfg_text: str) -> list[ConvSpec]:
             c = sum(out_c[(idx + l) if l < 0 else l] for l in layers)
         elif name == "[reorg]":
             st = int(opt.get("stride", 1))
-            c, h, w = c * st * st, h // st, w // st
+            if int(opt.get("reverse", 0)):
+                c, h, w = c // (st * st), h * st, w * st
+            else:
+                c, h, w = c * st * st, h // st, w // st
         # shortcut / dropout / softmax / cost / region keep the extent (spatial sizes behind a route are not tracked:
         # no cfg here puts a connected layer there)
         out_c.append(c)

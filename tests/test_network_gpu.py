@@ -39,7 +39,9 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
                                              # nested routes (a route that concatenates another route's output)
                                              ("mini-dense", 3, 64),
                                              # classifier cfgs: connected / dropout layers, relu / elu / tanh
-                                             ("mini-alexnet", 3, 32)])
+                                             ("mini-alexnet", 3, 32),
+                                             # depth-to-space: a reorg layer with reverse=1
+                                             ("mini-reorg-reverse", 2, 32)])
 def test_layer_activations_match_reference(tmp_path, name, batch, side):
     """BASELINE.json configs 1-5 (at a batch the CPU reference finishes in seconds): every layer of
     the B200 forward pass against the reference's CPU forward on the same weights and images."""
