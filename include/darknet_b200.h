@@ -241,7 +241,8 @@ void resize_region_layer(layer *l, int w, int h);                    /* region_l
 void resize_avgpool_layer(avgpool_layer *l, int w, int h);           /* avgpool_layer.c:32-37 */
 
 /* ---- blas.h:16-19,43-53, activations.h:16-18: vector helpers on host arrays and on
- * cuda_make_array buffers (fp32).  gemm*, im2col* and blas_handle are NOT provided: the convolution
+ * cuda_make_array buffers (fp32).  gemm_ongpu / gemm_gpu / im2col_ongpu are plain fp32 device kernels for callers of
+ * the helper surface; gemm, gemm_cpu, im2col_cpu and blas_handle are NOT provided: the convolution
  * is an implicit GEMM inside the tcgen05 kernels. ----------------------------------- */
 void fill_cpu(int N, float ALPHA, float *X, int INCX);
 void copy_cpu(int N, float *X, int INCX, float *Y, int INCY);
@@ -256,6 +257,12 @@ void scal_ongpu(int N, float ALPHA, float *X, int INCX);
 float activate(float x, ACTIVATION a);                              /* activations.c:64-93 */
 void activate_array(float *x, const int n, const ACTIVATION a);     /* activations.c:95-101 */
 void activate_array_ongpu(float *x, int n, ACTIVATION a);           /* activation_kernels.cu:143-159 */
+void gemm_ongpu(int TA, int TB, int M, int N, int K, float ALPHA, float *A_gpu, int lda, float *B_gpu, int ldb,
+                float BETA, float *C_gpu, int ldc);                 /* gemm.c:173-183 */
+void gemm_gpu(int TA, int TB, int M, int N, int K, float ALPHA, float *A, int lda, float *B, int ldb, float BETA,
+              float *C, int ldc);                                   /* gemm.c:185-213 */
+void im2col_ongpu(float *im, int channels, int height, int width, int ksize, int stride, int pad,
+                  float *data_col);                                 /* im2col_kernels.cu:48-61 */
 
 /* ---- region_layer.h:9-18, box.h:12-20 -------------------------------------------------- */
 void forward_region_layer_gpu(const layer l, network_state state); /* region_layer.c:383-422 */

@@ -336,6 +336,13 @@ int y2_vec_axpy(long long n, float alpha, const float *x, long long incx, float 
 int y2_vec_scal(long long n, float alpha, float *x, long long incx, y2_stream_t s);
 /* activation = the ACTIVATION enum value of activations.h:6-8 (0 LOGISTIC ... 12 LHTAN) */
 int y2_vec_activate(float *x, long long n, int activation, y2_stream_t s);
+/* fp32 helpers behind gemm_ongpu (gemm.c:173-183: C = ALPHA op(A) op(B) + BETA C, row-major) and im2col_ongpu
+ * (im2col_kernels.cu:48-61).  CUDA-core kernels for callers of the helper surface; the network's convolutions are
+ * implicit GEMMs on the tensor cores and never use them. */
+int y2_sgemm(int TA, int TB, int M, int N, int K, float alpha, const float *A, int lda, const float *B, int ldb,
+             float beta, float *C, int ldc, y2_stream_t s);
+int y2_im2col_f32(const float *im, int channels, int height, int width, int ksize, int stride, int pad,
+                  float *col, y2_stream_t s);
 /* for check_error(cudaError_t) (cuda.c:27-49) */
 const char *y2_cuda_error_string(int cuda_status);
 int y2_cuda_last_status(void);

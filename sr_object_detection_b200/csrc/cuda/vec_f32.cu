@@ -90,6 +90,60 @@ __global__ void vec_activate_kernel(float *__restrict__ x, long long n, int a)
         x[i] = activate(x[i], a);
 }
 
+// ---- gemm_ongpu / im2col_ongpu of the helper surface (gemm.c:173-183, im2col_kernels.cu:48-61) -----------------
+// Plain fp32 CUDA-core kernels for callers that still link these names (the reference's layer code around the hot
+// path: connected / rnn training utilities, test_gpu_blas).  The network's own convolutions never come here: they are
+// implicit GEMMs on the tensor cores.  C (row-major M x N) = ALPHA * op(A) * op(B) + BETA * C.
+template <int TA, int TB>
+__global__ void sgemm_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int lda,
+                             const float *__restrict__ B, int ldb, float beta, float *__restrict__ C, int ldc)
+{
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    const int row0 = blockIdx.y * 32, col0 = blockIdx.x * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int r = ty; r < 32; r += 8) {
+            const int i = row0 + r, k = k0 + tx;  // sa[r][tx] = op(A)[i][k]
+            sa[r][tx] = (i < M && k < K) ? (TA ? A[(size_t)k * lda + i] : A[(size_t)i * lda + k]) : 0.f;
+            const int kb = k0 + r, j = col0 + tx;  // sb[r][tx] = op(B)[kb][j]
+            sb[r][tx] = (kb < K && j < N) ? (TB ? B[(size_t)j * ldb + kb] : B[(size_t)kb * ldb + j]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float b = sb[k][tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(sa[ty + 8 * q][k], b, acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = row0 + ty + 8 * q, j = col0 + tx;
+        if (i < M && j < N) {
+            float *c = C + (size_t)i * ldc + j;
+            *c = alpha * acc[q] + (beta == 0.f ? 0.f : beta * *c);
+        }
+    }
+}
+
+// col[(c*k*k + i*k + j)][h_out][w_out] = im[c][h_out*stride - pad + i][w_out*stride - pad + j], 0 outside
+__global__ void im2col_kernel(const float *__restrict__ im, int channels, int height, int width, int ksize, int stride,
+                              int pad, int height_col, int width_col, float *__restrict__ col)
+{
+    const long long total = (long long)channels * ksize * ksize * height_col * width_col;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int w_out = (int)(t % width_col);
+        const int h_out = (int)((t / width_col) % height_col);
+        const int row = (int)(t / ((long long)width_col * height_col));
+        const int j = row % ksize, i = (row / ksize) % ksize, c = row / (ksize * ksize);
+        const int h = h_out * stride - pad + i, w = w_out * stride - pad + j;
+        col[t] = (h >= 0 && w >= 0 && h < height && w < width) ? im[((size_t)c * height + h) * width + w] : 0.f;
+    }
+}
+
 template <int OP>
 static int vec_launch(long long n, float alpha, const float *x, long long incx, float *y, long long incy,
                       y2_stream_t s)
@@ -144,6 +198,34 @@ extern "C" int y2_vec_activate(float *x, long long n, int activation, y2_stream_
         return Y2_EINVAL;
     }
     vec_activate_kernel<<<vec_grid(n, 256), 256, 0, to_stream(s)>>>(x, n, activation);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_sgemm(int TA, int TB, int M, int N, int K, float alpha, const float *A, int lda, const float *B,
+                        int ldb, float beta, float *C, int ldc, y2_stream_t s)
+{
+    if (M <= 0 || N <= 0) return Y2_OK;
+    if (!A || !B || !C || K < 0) return Y2_EINVAL;
+    const dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32)), block(32, 8);
+    if (!TA && !TB) sgemm_kernel<0, 0><<<grid, block, 0, to_stream(s)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (TA && !TB) sgemm_kernel<1, 0><<<grid, block, 0, to_stream(s)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (!TA && TB) sgemm_kernel<0, 1><<<grid, block, 0, to_stream(s)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else sgemm_kernel<1, 1><<<grid, block, 0, to_stream(s)>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    Y2_LAUNCH_CHECK();
+    return Y2_OK;
+}
+
+extern "C" int y2_im2col_f32(const float *im, int channels, int height, int width, int ksize, int stride, int pad,
+                             float *col, y2_stream_t s)
+{
+    if (!im || !col || channels <= 0 || ksize <= 0 || stride <= 0) return Y2_EINVAL;
+    const int height_col = (height + 2 * pad - ksize) / stride + 1;
+    const int width_col = (width + 2 * pad - ksize) / stride + 1;
+    if (height_col <= 0 || width_col <= 0) return Y2_EINVAL;
+    const long long total = (long long)channels * ksize * ksize * height_col * width_col;
+    im2col_kernel<<<vec_grid(total, 256), 256, 0, to_stream(s)>>>(im, channels, height, width, ksize, stride, pad,
+                                                                  height_col, width_col, col);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }

@@ -4,10 +4,13 @@
  * functions (convolutional_layer.h:29, maxpool_layer.h:13, reorg_layer.h:10, route_layer.h:11,
  * region_layer.h:13, avgpool_layer.h:13).
  *
- * Not provided on purpose: the CPU forward_*_layer functions (there is no CPU execution path; a caller
- * that links them fails at link time rather than silently computing on the host), gemm / gemm_cpu / gemm_ongpu / gemm_gpu, im2col_cpu / im2col_ongpu and
- * blas_handle (gemm.h, im2col.h, cuda.h:23): the convolution is an implicit GEMM inside the tcgen05
- * kernels, there is no im2col buffer, no cuBLAS handle and no host GEMM in this library. */
+ * gemm_ongpu / gemm_gpu (gemm.c:173-213) and im2col_ongpu (im2col_kernels.cu:48-61) are provided as plain fp32 device
+ * kernels for callers of the helper surface; the network's own convolutions never use them (implicit GEMM inside the
+ * tcgen05 kernels, no im2col buffer).
+ *
+ * Not provided on purpose: the CPU forward_*_layer functions, gemm / gemm_cpu and im2col_cpu (there is no CPU
+ * execution path; a caller that links them fails at link time rather than silently computing on the host) and
+ * blas_handle (cuda.h:23): there is no cuBLAS handle in this library. */
 #include "y2_host.h"
 
 #include <assert.h>
@@ -210,4 +213,30 @@ void resize_avgpool_layer(avgpool_layer *l, int w, int h)
     l->w = w;
     l->h = h;
     l->inputs = h * w * l->c;
+}
+
+/* ---- gemm.c:173-213, im2col_kernels.cu:48-61 on cuda_make_array buffers ------------------------------------------- */
+void gemm_ongpu(int TA, int TB, int M, int N, int K, float ALPHA, float *A_gpu, int lda, float *B_gpu, int ldb,
+                float BETA, float *C_gpu, int ldc)
+{
+    Y2_CHECK(y2_sgemm(TA, TB, M, N, K, ALPHA, A_gpu, lda, B_gpu, ldb, BETA, C_gpu, ldc, 0));
+}
+
+/* host arrays in, host array out (gemm.c:185-213) */
+void gemm_gpu(int TA, int TB, int M, int N, int K, float ALPHA, float *A, int lda, float *B, int ldb, float BETA,
+              float *C, int ldc)
+{
+    float *A_gpu = cuda_make_array(A, (size_t)(TA ? lda * K : lda * M));
+    float *B_gpu = cuda_make_array(B, (size_t)(TB ? ldb * N : ldb * K));
+    float *C_gpu = cuda_make_array(C, (size_t)ldc * M);
+    gemm_ongpu(TA, TB, M, N, K, ALPHA, A_gpu, lda, B_gpu, ldb, BETA, C_gpu, ldc);
+    cuda_pull_array(C_gpu, C, (size_t)ldc * M);
+    cuda_free(A_gpu);
+    cuda_free(B_gpu);
+    cuda_free(C_gpu);
+}
+
+void im2col_ongpu(float *im, int channels, int height, int width, int ksize, int stride, int pad, float *data_col)
+{
+    Y2_CHECK(y2_im2col_f32(im, channels, height, width, ksize, stride, pad, data_col, 0));
 }

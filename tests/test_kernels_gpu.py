@@ -571,3 +571,44 @@ def test_collect_final_pick_matches_max_index(classes):
         assert np.array_equal(got[:, 5], arg[keep[:n]])                 # obj_id
         assert np.array_equal(got[:, 4].view(np.float32), best[keep[:n]])
         assert np.array_equal(got[:, :4].view(np.float32), boxes[b, keep[:n]])
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_gemm_ongpu_helper_matches_fp32_reference(ta, tb):
+    """gemm_ongpu of the helper surface (gemm.c:173-183): C = ALPHA op(A) op(B) + BETA C, row-major, fp32."""
+    import ctypes as C
+    from sr_object_detection_b200 import darknet as dn
+    lib = dn.lib()
+    M, N, K = 70, 45, 133
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    Cm = torch.randn(M, N, generator=g)
+    want = 0.5 * ((A.t() if ta else A).double() @ (B.t() if tb else B).double()) + 2.0 * Cm.double()
+    dA, dB, dC = A.cuda().contiguous(), B.cuda().contiguous(), Cm.cuda().contiguous()
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.gemm_ongpu.restype = None
+    lib.gemm_ongpu.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i]
+    torch.cuda.synchronize()
+    lib.gemm_ongpu(ta, tb, M, N, K, 0.5, dA.data_ptr(), A.shape[1], dB.data_ptr(), B.shape[1], 2.0, dC.data_ptr(), N)
+    torch.cuda.synchronize()
+    assert torch.allclose(dC.cpu().double(), want, rtol=1e-5, atol=1e-4)
+
+
+def test_im2col_ongpu_helper_matches_unfold():
+    """im2col_ongpu (im2col_kernels.cu:48-61): rows ordered c*k*k + i*k + j, zero outside the image."""
+    import ctypes as C
+    from sr_object_detection_b200 import darknet as dn
+    lib = dn.lib()
+    c, h, w, k, stride, pad = 5, 13, 17, 3, 2, 1
+    x = torch.randn(c, h, w)
+    want = torch.nn.functional.unfold(x[None], k, padding=pad, stride=stride)[0]
+    dx = x.cuda().contiguous()
+    col = torch.empty_like(want, device="cuda")
+    vp, i = C.c_void_p, C.c_int
+    lib.im2col_ongpu.restype = None
+    lib.im2col_ongpu.argtypes = [vp, i, i, i, i, i, i, vp]
+    torch.cuda.synchronize()
+    lib.im2col_ongpu(dx.data_ptr(), c, h, w, k, stride, pad, col.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(col.cpu(), want)
