@@ -398,7 +398,9 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int slab_rows = tile_m + 2 * halo;
     const int loads = (slab_rows + 255) / 256;
     int box_rows = (slab_rows + loads - 1) / loads;
-    box_rows = (box_rows + 15) / 16 * 16;
+    // a load must cover whole swizzle atoms (1024 bytes: 8 rows of 128 bytes, 16 rows of 64 bytes)
+    const int gran = 1024 / row_bytes;
+    box_rows = (box_rows + gran - 1) / gran * gran;
     if (box_rows > 256) return Y2_EINVAL;
     const int slab_bytes = loads * box_rows * row_bytes;  // multiple of 1024
     const int b_stage = tps * bn * bk * 2;
@@ -413,7 +415,9 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     }
     int stages_b = (budget - stages_a * slab_bytes) / b_stage;
     if (stages_b > kSlabMaxStagesB) stages_b = kSlabMaxStagesB;
-    if (stages_b < 2 || (tps == 1 && stages_b < 3)) return Y2_EINVAL;
+    // wide images (yolo.cfg at 608: 152-position rows) leave room for two weight stages only: still well ahead
+    // of the per-tap kernel, which reloads the activations for every tap
+    if (stages_b < 2 || (tps == 1 && stages_b < 3 && wp <= 128)) return Y2_EINVAL;
     const int ktot = taps * d->cin;
     int rc = encode_2d_bf16(&pl->tm_a, d->in, (uint64_t)d->cin, (uint64_t)total, (uint64_t)d->in_cs * 2,
                             (uint32_t)bk, (uint32_t)box_rows, bk);

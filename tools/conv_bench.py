@@ -32,6 +32,10 @@ YOLO_VOC = [
 ]
 
 
+# wide-image shapes: yolo.cfg at 608 (152-position rows) and yolo9000 at 544 (136), batch 32
+WIDE = [("W4_608", 64, 152, 128, 3), ("W4_544", 64, 136, 128, 3), ("W8_608", 128, 76, 256, 3), ("W2_608", 32, 304, 64, 3)]
+
+
 def storage_channels(c):
     return (c + 31) // 32 * 32 if c < 64 else (c + 63) // 64 * 64
 
@@ -52,8 +56,8 @@ def main():
     dev = torch.device("cuda:0")
     only = set(args.only.split(",")) if args.only else None
     rows = []
-    for name, cin, hw, cout, k in YOLO_VOC:
-        if only and name not in only:
+    for name, cin, hw, cout, k in YOLO_VOC + WIDE:
+        if (only and name not in only) or (not only and name.startswith("W")):
             continue
         B = args.batch
         cin_pad = storage_channels(cin)
@@ -94,7 +98,7 @@ def main():
         ms = e0.elapsed_time(e1) / args.reps
         flops = 2.0 * cout * k * k * cin * hw * hw * B
         row = {"layer": name, "cin": cin, "hw": hw, "cout": cout, "k": k, "ms": round(ms, 4),
-               "tflops": round(flops / ms / 1e9, 1)}
+               "tflops": round(flops / ms / 1e9, 1), "variant": lib.y2_conv_plan_variant(plan)}
         rows.append(row)
         print(json.dumps(row), flush=True)
         lib.y2_conv_plan_destroy(plan)
