@@ -912,7 +912,8 @@ void y2_plan_network(network *net)
             if (l->type == MAXPOOL) r->cpad = pr->cpad;
             else {
                 if (pr->cpad != l->c) unsupported(i, "reorg of a channel-padded tensor");
-                r->cpad = l->out_c;
+                /* depth-to-space shrinks the channel count: store it like any tensor (padding channels stay zero) */
+                r->cpad = l->reverse ? storage_channels(l->out_c) : l->out_c;
             }
             break;
         }
