@@ -173,6 +173,54 @@ __global__ void gather_rows_f32_kernel(const float *__restrict__ src, __nv_bfloa
     }
 }
 
+// The same gather with the c*ksize input rows an output row needs staged in shared memory: the image is read with
+// coalesced loads once per output row (the direct form issues seven scalar loads per thread whose 32 lanes touch ~24
+// different sectors - the L1 tag path, not the 409 MB patch write, bounded resnet50's first layer), the groups are
+// assembled from shared memory and written back 16 bytes per thread, consecutive threads to consecutive addresses.
+__global__ void gather_rows_f32_smem_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int batch,
+                                            int c, int h, int w, int ksize, int stride, int pad, int oh, int ow, int kpad)
+{
+    extern __shared__ float srow[];  // [c*ksize][ws], ws odd: the lanes of a warp read different rows at one column
+    const int ws = w | 1;
+    const int ohp = oh + 1, owp = ow + 1, k8 = kpad / 8, groups = c * ksize;
+    const int rows = batch * ohp, per_row = owp * k8;
+    for (int rowi = blockIdx.x; rowi < rows; rowi += gridDim.x) {
+        const int b = rowi / ohp, oy = rowi - b * ohp;
+        __nv_bfloat16 *drow = dst + (size_t)rowi * owp * kpad;
+        __syncthreads();  // the previous row's groups have been read
+        if (oy < oh) {
+            for (int t = threadIdx.x; t < groups * w; t += blockDim.x) {
+                const int g = t / w, x = t - g * w;
+                const int ci = g / ksize, r = g - ci * ksize;
+                const int yy = oy * stride + r - pad;
+                srow[g * ws + x] = (yy >= 0 && yy < h) ? __ldg(src + (((size_t)b * c + ci) * h + yy) * w + x) : 0.f;
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < per_row; t += blockDim.x) {
+            const int ox = t / k8, g = t - ox * k8;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            if (ox < ow && oy < oh && g < groups) {
+                const float *row = srow + g * ws;
+                const int x0 = ox * stride - pad;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int xx = x0 + q;
+                    if (q < ksize && xx >= 0 && xx < w) v[q] = row[xx];
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]);
+            o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]);
+            o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4 *>(drow + (size_t)t * 8) = o;
+        }
+    }
+}
+
 __global__ void gather_patches_bf16_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs, int cin_pad, int h,
                                            int w, __nv_bfloat16 *__restrict__ dst, int batch, int ksize,
                                            int stride, int pad, int oh, int ow)
@@ -783,8 +831,13 @@ extern "C" int y2_gather_rows_f32(const float *src, void *dst, int batch, int c,
     }
     const int rows = batch * (oh + 1);
     const int cap = sm_count() * 8;
-    gather_rows_f32_kernel<<<rows < cap ? rows : cap, 256, 0, to_stream(s)>>>(
-        src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize, stride, pad, oh, ow, kpad);
+    const size_t smem = (size_t)c * ksize * (w | 1) * sizeof(float);
+    if (smem <= 48 * 1024 && !getenv("Y2_GATHER_DIRECT"))
+        gather_rows_f32_smem_kernel<<<rows < cap ? rows : cap, 512, smem, to_stream(s)>>>(
+            src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize, stride, pad, oh, ow, kpad);
+    else
+        gather_rows_f32_kernel<<<rows < cap ? rows : cap, 256, 0, to_stream(s)>>>(
+            src, (__nv_bfloat16 *)dst, batch, c, h, w, ksize, stride, pad, oh, ow, kpad);
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }
