@@ -200,6 +200,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===================== weight producer (both CTAs, own 128 filters) =====================
         int stage = 0;
         uint32_t phase = 0;
+        int issued = 0;
         while (sched.next(seg)) {
             const int m_tile = seg.tile / prm.tiles_n;
             const int n0 = (seg.tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
@@ -207,10 +208,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll 1
                 for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(&b_empty[stage], phase ^ 1, 2);
+                    const bool skip = (prm.dbg & 1) && (tap & 1) && issued >= 2 * stages_b;
+                    ++issued;
                     if (elect_one_sync()) {
-                        if (leader) mbar_expect_tx(&b_full[stage], 2u * kPairBHalfBytes);
-                        tma_load_2d_pair(&tm_b, &b_full[stage], smem_b + (size_t)stage * kPairBHalfBytes,
-                                         (tap * cblocks + cb) * kPairBK, n0);
+                        if (skip) {  // timing experiment: the stage "completes" with stale bytes
+                            if (leader) mbar_arrive(&b_full[stage]);
+                        } else {
+                            if (leader) mbar_expect_tx(&b_full[stage], 2u * kPairBHalfBytes);
+                            tma_load_2d_pair(&tm_b, &b_full[stage], smem_b + (size_t)stage * kPairBHalfBytes,
+                                             (tap * cblocks + cb) * kPairBK, n0);
+                        }
                     }
                     __syncwarp();
                     if (++stage == stages_b) { stage = 0; phase ^= 1; }
@@ -452,6 +459,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.out_cs = d->out_cs;
     p.couple = 0;
     p.tma_store = 0;
+    p.dbg = getenv("Y2_PAIR_DBG") ? atoi(getenv("Y2_PAIR_DBG")) : 0;
     memset(&pl->tm_out, 0, sizeof(pl->tm_out));
     if (d->out_mode == Y2_OUT_BF16_PADDED && d->cout % 64 == 0 && !getenv("Y2_SLAB_NO_TMA_STORE")) {
         rc = encode_2d_bf16(&pl->tm_out, d->out, (uint64_t)d->cout, (uint64_t)total, (uint64_t)d->out_cs * 2, 64u, 32u, 64);

@@ -43,6 +43,7 @@ struct SlabParams {
     int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
     int reverse;           // slab kernel: walk the position tiles last-to-first (see slab_plan_init)
     int streamk;           // pair kernel: K-split work distribution (conv_pair.cu), else whole tiles round-robin
+    int dbg;               // pair kernel, timing experiments only (Y2_PAIR_DBG): bit 0 = skip the weight loads of odd taps (WRONG results)
     float *sk_partial;     // [pairs][256 filters][256 positions] fp32 partial accumulators of split tiles
     int *sk_flags;         // [pairs][16 epilogue warps] "partial written" flags, zero between launches
     const float *alpha;
