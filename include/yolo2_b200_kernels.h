@@ -128,6 +128,12 @@ int y2_conv_plan_tiles(const y2_conv_plan *plan);
 /* which kernel the plan launches: 0 per-tap (conv_tcgen05_kernel), 1 halo slab (conv_slab_kernel),
  * 2 CTA pair (conv_pair_kernel, tcgen05.mma.cta_group::2), 3 conv + maxpool (conv_pool_kernel) */
 int y2_conv_plan_variant(const y2_conv_plan *plan);
+/* Host logic of the CTA-pair kernel, exported for the CPU tests: the work lists it hands to `pairs` CTA pairs for
+ * `rows` position tiles of `units` 64-filter units each (units % 4 == 0).  balanced = 0: whole 256-filter tiles
+ * round-robin; 1: contiguous unit ranges of minimal largest cost, split into pieces of 64..256 filters.
+ * out: 4 ints per entry (position tile, first filter, filters, 0), *stride entries per pair, filters == 0 ends a
+ * pair's list.  Returns the number of entries written (pairs * *stride) or Y2_EINVAL when cap is too small. */
+int y2_pair_schedule(int rows, int units, int pairs, int balanced, int *out, int cap_entries, int *stride);
 
 /* ---- first layer (replaces, for a 3x3/1 'same' convolution over <= 3 input channels followed by a
  *      2x2/2 maxpool: cuda_make_array of the input (network_kernels.cu:399) +

@@ -21,19 +21,22 @@
 // Everything else (halo slab, row-shifted descriptors, double-buffered accumulators, 8 epilogue
 // warps) is conv_slab.cu's design.
 //
-// Work distribution.  Whole tiles round-robin leave the last wave partly empty when the tile count is
-// a small non-multiple of the 74 pairs (13x13 layers at batch 64: 196 tiles = 2.65 waves, run as 3).
-// With prm.streamk the K loops of all tiles are laid end to end in units of one channel block
-// (64 input channels x 9 taps) and every pair takes an equal contiguous share: a pair's share starts
-// with the tail of a tile, continues with whole tiles and ends with the head of a tile.  The pair that
-// computes a tile's TAIL does so first thing and parks its raw fp32 accumulator in global scratch;
-// the pair that computes the HEAD does so last, adds the parked partial in its epilogue and finishes
-// the tile.  The dependency always points from a pair's first segment to another pair's last one, so
-// with all pairs resident (grid = SM count) nothing can wait on work that has not been scheduled.
+// Work distribution.  Whole 256 x 256 tiles round-robin leave the last wave partly empty when the tile count is
+// a small non-multiple of the 74 pairs (13x13 layers at batch 64: 196 tiles = 2.65 waves, run as 3).  The host
+// therefore hands every pair an explicit list of PIECES (position tile, first filter, 64..256 filters): the
+// (position tile, 64-filter unit) sequence is cut into one contiguous range per pair such that the largest range
+// cost is minimal under a measured cost model of narrow pieces, and every range is split into pieces of at most
+// 256 filters.  A piece is a full K loop over N = 64..256 filters (tcgen05.mma N is a runtime field of the
+// instruction descriptor), so every output element is still accumulated by ONE pair in the same order: results
+// are bit-identical to whole tiles, nothing is parked or joined (the stream-K schedule this replaces needed fp32
+// partial sums in global scratch and lost at the power cap).  Y2_PAIR_BALANCE=0 restores whole
+// tiles round-robin (same kernel, different list).
 #include "conv_epilogue.cuh"
 
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 namespace y2 {
 
@@ -46,73 +49,41 @@ constexpr int kPairN = 256;                          // filters per pair tile
 constexpr int kPairRowBytes = kPairBK * 2;           // 128
 constexpr int kPairBHalfBytes = 128 * kPairBK * 2;   // this CTA's half of a weight tile
 constexpr uint32_t kPairDescHi = ((8u * kPairRowBytes) >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, v1, SWIZZLE_128B
-// c = F32, a = b = BF16, K-major, N = 256, M = 256 (both CTAs)
-constexpr uint32_t kPairIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPairN >> 3) << 17) |
-                                ((uint32_t)(256 >> 4) << 24);
+// c = F32, a = b = BF16, K-major, M = 256 (both CTAs); N (64 ... 256) is or-ed in per piece at bit 17
+constexpr uint32_t kPairIdescM = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
 
-// one stretch of K iterations of one tile: channel blocks [cb0, cb1)
+// one piece of work: a full K loop over `ncols` filters (64, 128, 192 or 256) of one position tile
 struct PairSeg {
-    int tile, cb0, cb1;
+    int m_tile, n0, ncols;
 };
 
+// this pair's list: int4 (m_tile, n0, ncols, -) entries, ncols == 0 terminates
 struct PairSched {
-    int streamk, n_pairs, cblocks, cur, end;
-    __device__ PairSched(const SlabParams &prm, int pair, int n_pairs_)
-        : streamk(prm.streamk), n_pairs(n_pairs_), cblocks(prm.cblocks)
-    {
-        const int total_tiles = prm.tiles_m * prm.tiles_n;
-        if (streamk) {
-            const long long units = (long long)total_tiles * cblocks;
-            cur = (int)(units * pair / n_pairs);
-            end = (int)(units * (pair + 1) / n_pairs);
-        } else {
-            cur = pair;
-            end = total_tiles;
-        }
-    }
+    const int4 *w;
+    __device__ PairSched(const SlabParams &prm, int pair) : w(prm.work + (size_t)pair * prm.work_stride) {}
     __device__ bool next(PairSeg &s)
     {
-        if (cur >= end) return false;
-        if (streamk) {
-            s.tile = cur / cblocks;
-            s.cb0 = cur - s.tile * cblocks;
-            const int left = end - cur, room = cblocks - s.cb0;
-            const int n = left < room ? left : room;
-            s.cb1 = s.cb0 + n;
-            cur += n;
-        } else {
-            s.tile = cur;
-            s.cb0 = 0;
-            s.cb1 = cblocks;
-            cur += n_pairs;
-        }
+        if (!peek(s)) return false;
+        ++w;
         return true;
     }
     __device__ bool peek(PairSeg &s) const
     {
-        PairSched copy = *this;
-        return copy.next(s);
+        const int4 q = __ldg(w);
+        s.m_tile = q.x;
+        s.n0 = q.y;
+        s.ncols = q.z;
+        return q.z != 0;
     }
 };
-
-__device__ __forceinline__ int ld_acquire_gpu(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release_gpu(int *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // TAPS = 9: 3x3 layer (halo slab, nine row-shifted descriptors per channel block);
 // TAPS = 1: 1x1 layer (the "slab" is the plain 128-position tile, one descriptor per channel block)
 template <int TAPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_out, const SlabParams prm)
+                 const __grid_constant__ CUtensorMap tm_b32, const __grid_constant__ CUtensorMap tm_out,
+                 const SlabParams prm)
 {
     extern __shared__ uint8_t smem_raw[];
     // identical carve-up in both CTAs: descriptors and barrier offsets name the peer's memory too
@@ -139,14 +110,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
-    const int n_pairs = gridDim.x >> 1;
     const int cblocks = prm.cblocks;
-    PairSched sched(prm, pair, n_pairs);
+    PairSched sched(prm, pair);
     PairSeg seg;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_b);
+        tma_prefetch_desc(&tm_b32);
         for (int i = 0; i < stages_a; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
@@ -181,9 +152,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t slab_tx = (uint32_t)prm.slab_loads * prm.box_rows * kPairRowBytes;
         const uint32_t load_bytes = (uint32_t)prm.box_rows * kPairRowBytes;
         while (sched.next(seg)) {
-            const int m_tile = seg.tile / prm.tiles_n;
-            const int row0 = m_tile * 256 + (int)rank * 128 - prm.halo;
-            for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
+            const int row0 = seg.m_tile * 256 + (int)rank * 128 - prm.halo;
+            for (int cb = 0; cb < cblocks; ++cb) {
                 mbar_wait(&a_empty[stage], phase ^ 1, 1);
                 if (elect_one_sync()) {
                     uint8_t *sa = smem_a + (size_t)stage * prm.slab_bytes;
@@ -197,26 +167,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
     } else if (warp == 2) {
-        // ===================== weight producer (both CTAs, own 128 filters) =====================
+        // ===================== weight producer (both CTAs, own half of the piece's filters) =====
         int stage = 0;
         uint32_t phase = 0;
         int issued = 0;
         while (sched.next(seg)) {
-            const int m_tile = seg.tile / prm.tiles_n;
-            const int n0 = (seg.tile - m_tile * prm.tiles_n) * kPairN + (int)rank * 128;
-            for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
+            const int half_rows = seg.ncols >> 1;  // 32, 64, 96 or 128 filters per CTA
+            const int n0 = seg.n0 + (int)rank * half_rows;
+            const uint32_t tx = (uint32_t)seg.ncols * kPairRowBytes;  // both halves
+            for (int cb = 0; cb < cblocks; ++cb) {
 #pragma unroll 1
                 for (int tap = 0; tap < TAPS; ++tap) {
                     mbar_wait(&b_empty[stage], phase ^ 1, 2);
                     const bool skip = (prm.dbg & 1) && (tap & 1) && issued >= 2 * stages_b;
                     ++issued;
                     if (elect_one_sync()) {
+                        uint8_t *sb = smem_b + (size_t)stage * kPairBHalfBytes;
+                        const int k0 = (tap * cblocks + cb) * kPairBK;
                         if (skip) {  // timing experiment: the stage "completes" with stale bytes
                             if (leader) mbar_arrive(&b_full[stage]);
                         } else {
-                            if (leader) mbar_expect_tx(&b_full[stage], 2u * kPairBHalfBytes);
-                            tma_load_2d_pair(&tm_b, &b_full[stage], smem_b + (size_t)stage * kPairBHalfBytes,
-                                             (tap * cblocks + cb) * kPairBK, n0);
+                            if (leader) mbar_expect_tx(&b_full[stage], tx);
+                            if (half_rows == 128) {
+                                tma_load_2d_pair(&tm_b, &b_full[stage], sb, k0, n0);
+                            } else {  // narrow piece: 32-filter boxes, only the rows the MMA reads
+                                for (int r = 0; r < half_rows; r += 32)
+                                    tma_load_2d_pair(&tm_b32, &b_full[stage], sb + r * kPairRowBytes, k0, n0 + r);
+                            }
                         }
                     }
                     __syncwarp();
@@ -241,10 +218,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 mbar_wait(&tempty_bar[buf], buf_phase ^ 1, 3);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(buf * kPairN);
-                for (int cb = seg.cb0; cb < seg.cb1; ++cb) {
+                const uint32_t idesc = kPairIdescM | ((uint32_t)(seg.ncols >> 3) << 17);
+                for (int cb = 0; cb < cblocks; ++cb) {
                     mbar_wait(&a_full[sa_i], pa, 4);
                     const uint32_t a_lo = a_lo0 + (uint32_t)sa_i * slab16;
-                    const uint32_t acc_first = cb != seg.cb0;
+                    const uint32_t acc_first = cb != 0;
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(&b_full[sb_i], pb, 5);
@@ -256,11 +234,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             for (int k = 0; k < kPairBK / 16; ++k)
                                 umma_bf16_pair(d0, ((uint64_t)kPairDescHi << 32) | (uint64_t)(a_tap + (uint32_t)(k * 2)),
                                                ((uint64_t)kPairDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(k * 2)),
-                                               kPairIdesc, (tap == 0 && k == 0) ? acc_first : 1u);
+                                               idesc, (tap == 0 && k == 0) ? acc_first : 1u);
                             umma_commit_pair(&b_empty[sb_i]);
                             if (tap == TAPS - 1) {
                                 umma_commit_pair(&a_empty[sa_i]);
-                                if (cb == seg.cb1 - 1) umma_commit_pair(&tfull_bar[buf]);
+                                if (cb == cblocks - 1) umma_commit_pair(&tfull_bar[buf]);
                             }
                         }
                         __syncwarp();
@@ -272,118 +250,78 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else {
         // ===================== epilogue (warps 3..10 of both CTAs, own 128 TMEM lanes) ==========
+        // 64-column chunks of the piece alternate between the two warp groups (warps 3-6: chunks 0, 2; warps
+        // 7-10: chunks 1, 3)
         const int quarter = warp & 3;
         const int half = (warp - 3) >> 2;
         const int et = threadIdx.x - 96;  // 0..255
-        const int col0 = half * 128;
         const int img_pos = prm.hp * prm.wp;
         int it = 0;
-        const int ewarp = (int)rank * 8 + (warp - 3);  // 0..15 within the pair
-        if (sched.peek(seg)) {
-            const int n0 = (seg.tile % prm.tiles_n) * kPairN;
-            s_ab[et] = make_float2(__ldg(prm.alpha + n0 + et), __ldg(prm.beta + n0 + et));
-        }
+        if (sched.peek(seg) && et < seg.ncols)
+            s_ab[et] = make_float2(__ldg(prm.alpha + seg.n0 + et), __ldg(prm.beta + seg.n0 + et));
         for (; sched.next(seg); ++it) {
-            const int tile = seg.tile;
             const int buf = it & 1;
             const uint32_t buf_phase = (it >> 1) & 1;
-            const int m_tile = tile / prm.tiles_n;
-            const int n0 = (tile - m_tile * prm.tiles_n) * kPairN;
-            // stream-K roles of this segment: the tail of a tile is parked, the head adds it and finishes
-            const bool park = seg.cb0 > 0;
-            const bool join = seg.cb0 == 0 && seg.cb1 < cblocks;
-            const float2 *sab = s_ab + (prm.tiles_n > 1 ? buf * kPairN : 0);
-            const bool reload = prm.tiles_n > 1 || it == 0;
-            if (reload) asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int n0 = seg.n0;
+            const int nchunks = seg.ncols >> 6;
+            const float2 *sab = s_ab + buf * kPairN;
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // sab[buf] written, sab[buf ^ 1] free
             PairSeg nseg;
             const bool has_next = sched.peek(nseg);
             float2 ab_next = make_float2(1.f, 0.f);
-            if (prm.tiles_n > 1 && has_next) {
-                const int nn = (nseg.tile % prm.tiles_n) * kPairN;
-                ab_next = make_float2(__ldg(prm.alpha + nn + et), __ldg(prm.beta + nn + et));
-            }
-            // scratch of a split tile belongs to the pair that parks it: this pair, or the next one
-            float *part = prm.sk_partial + (size_t)(park ? pair : pair + 1) * (kPairN * 256) + (int)rank * 128 +
-                          quarter * 32 + lane;
-            int *flag = prm.sk_flags + (park ? pair : pair + 1) * 16 + ewarp;
-            const int p = m_tile * 256 + (int)rank * 128 + quarter * 32 + lane;
+            if (has_next && et < nseg.ncols)
+                ab_next = make_float2(__ldg(prm.alpha + nseg.n0 + et), __ldg(prm.beta + nseg.n0 + et));
+            const int p = seg.m_tile * 256 + (int)rank * 128 + quarter * 32 + lane;
             const bool in_range = p < prm.total_pos;
             const int b = p / img_pos;
             const int rem = p - b * img_pos;
             const int y = rem / prm.wp;
             const int x = rem - y * prm.wp;
             const bool valid = in_range && (y < prm.h) && (x < prm.w);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kPairN + col0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * kPairN);
 
             mbar_wait(&tfull_bar[buf], buf_phase, 6);
             tc_fence_after();
+            if (half >= nchunks) {  // a 64-filter piece: nothing for the second group to drain
+                tc_fence_before();
+                mbar_arrive_cluster(&tempty_bar[buf], 0);
+            }
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 64) {
+            for (int ch = half; ch < nchunks; ch += 2) {
+                const int c = ch * 64;
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr + (uint32_t)c, v0);
                 tmem_ld32(taddr + (uint32_t)(c + 32), v1);
                 tmem_ld_wait();
-                if (c == 64) {  // accumulator drained into registers: hand it back to the leader's MMA warp
+                if (ch + 2 >= nchunks) {  // this group's part is in registers: hand it back to the leader's MMA warp
                     tc_fence_before();
                     mbar_arrive_cluster(&tempty_bar[buf], 0);
-                }
-                if (park) {  // raw partial sums, [filter][position]: a warp stores 128 contiguous bytes per filter
-                    float *dst = part + (size_t)(col0 + c) * 256;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        dst[j * 256] = __uint_as_float(v0[j]);
-                        dst[(32 + j) * 256] = __uint_as_float(v1[j]);
-                    }
-                    continue;
-                }
-                if (join) {
-                    if (c == 0) {
-                        if (lane == 0)
-                            while (ld_acquire_gpu(flag) == 0) __nanosleep(64);
-                        __syncwarp();
-                    }
-                    const float *src = part + (size_t)(col0 + c) * 256;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __ldcg(src + j * 256));
-                        v1[j] = __float_as_uint(__uint_as_float(v1[j]) + __ldcg(src + (32 + j) * 256));
-                    }
                 }
                 if (prm.tma_store) {  // bf16 tensor: staged, one TMA store per warp and 64 channels
                     uint4 w[8];
                     if (prm.act == Y2_ACT_LEAKY) {
-                        slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, col0 + c, valid, w);
-                        slab_affine_pack<Y2_ACT_LEAKY>(v1, sab, col0 + c + 32, valid, w + 4);
+                        slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, c, valid, w);
+                        slab_affine_pack<Y2_ACT_LEAKY>(v1, sab, c + 32, valid, w + 4);
                     } else if (prm.act == Y2_ACT_LINEAR) {
-                        slab_affine_pack<Y2_ACT_LINEAR>(v0, sab, col0 + c, valid, w);
-                        slab_affine_pack<Y2_ACT_LINEAR>(v1, sab, col0 + c + 32, valid, w + 4);
+                        slab_affine_pack<Y2_ACT_LINEAR>(v0, sab, c, valid, w);
+                        slab_affine_pack<Y2_ACT_LINEAR>(v1, sab, c + 32, valid, w + 4);
                     } else {
-                        slab_affine_pack<Y2_ACT_LOGISTIC>(v0, sab, col0 + c, valid, w);
-                        slab_affine_pack<Y2_ACT_LOGISTIC>(v1, sab, col0 + c + 32, valid, w + 4);
+                        slab_affine_pack<Y2_ACT_LOGISTIC>(v0, sab, c, valid, w);
+                        slab_affine_pack<Y2_ACT_LOGISTIC>(v1, sab, c + 32, valid, w + 4);
                     }
-                    slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + col0 + c);
+                    slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + c);
                 } else if (prm.act == Y2_ACT_LEAKY) {
-                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
-                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, c + 32, n0, p, b, y, x, in_range, valid);
                 } else if (prm.act == Y2_ACT_LINEAR) {
-                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
-                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v0, sab, c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LINEAR>(prm, v1, sab, c + 32, n0, p, b, y, x, in_range, valid);
                 } else {
-                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
-                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v0, sab, c, n0, p, b, y, x, in_range, valid);
+                    slab_epilogue_chunk<Y2_ACT_LOGISTIC>(prm, v1, sab, c + 32, n0, p, b, y, x, in_range, valid);
                 }
             }
-            if (park) {  // publish: every lane's stores, then the warp's flag
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    st_release_gpu(flag, 1);
-                }
-            } else if (join) {  // consumed: leave the flag clear for the next launch
-                __syncwarp();
-                if (lane == 0) *reinterpret_cast<volatile int *>(flag) = 0;
-            }
-            if (prm.tiles_n > 1 && has_next) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
+            if (has_next) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
         }
         if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
@@ -398,6 +336,114 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // -------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------
+// ---- work lists ------------------------------------------------------------------------
+// Cost of one piece of n 64-filter units, in units of a quarter of a full 256-filter piece.  Measured on B200
+// (yolo-voc L23 at batch 64 with every piece forced to one width, Y2_PAIR_FORCE_UNITS, profiles/r2k_pair_balance.txt):
+// a tcgen05.mma.cta_group::2 of M = 256, K = 16 takes ~95 / 105 / 115 / 128 clk at N = 64 / 128 / 192 / 256, i.e. it
+// has a floor of ~90 clk whatever N is - each SM fetches its 4 KB A operand (and N/2 rows of B) from shared memory at
+// ~64 B/clk, which at N = 256 (8 KB) is exactly the 128 clk the tensor pipe needs.  Narrow pieces are therefore
+// expensive and the balanced cut only uses them where they shorten the longest list (the 13x13 layers: -1.3 %).
+// Y2_PAIR_COST=c1,c2,c3 overrides the table.
+static void pair_piece_costs(double c[5])
+{
+    c[0] = 0.0; c[1] = 2.97; c[2] = 3.28; c[3] = 3.6; c[4] = 4.0;
+    if (const char *e = getenv("Y2_PAIR_COST")) {
+        double a, b, cc;
+        if (sscanf(e, "%lf,%lf,%lf", &a, &b, &cc) == 3) { c[1] = a; c[2] = b; c[3] = cc; }
+    }
+}
+
+// rows = position tiles, U = 64-filter units per row (a multiple of 4), P pairs.
+// balanced: the row-major unit sequence is cut into P contiguous ranges of minimal largest cost (binary search on
+// the bound, greedy longest-range check - exact for contiguous partitions with a monotone range cost); the units a
+// range owns in one row are split into the cheapest pieces of <= 4 units.  Otherwise whole 4-unit pieces round-robin.
+static void pair_schedule(int rows, int U, int P, bool balanced, std::vector<int4> &work, int &stride)
+{
+    std::vector<std::vector<int4>> lists(P);
+    const long long T = (long long)rows * U;
+    if (balanced && rows * (U / 4) > P) {
+        double c[5];
+        pair_piece_costs(c);
+        std::vector<double> g(U + 1, 0.0);   // cheapest split of r units of one row
+        std::vector<int> first(U + 1, 0);    // size of the first piece of that split
+        for (int r = 1; r <= U; ++r) {
+            g[r] = 1e30;
+            for (int n = 1; n <= 4 && n <= r; ++n)
+                if (c[n] + g[r - n] < g[r] - 1e-9) { g[r] = c[n] + g[r - n]; first[r] = n; }
+        }
+        std::vector<double> gm(g);  // monotone envelope: owning fewer units of a row never counts as more
+        for (int r = U - 1; r >= 1; --r)
+            if (gm[r] > gm[r + 1]) gm[r] = gm[r + 1];
+        auto range_cost = [&](long long s, long long e) {
+            if (e <= s) return 0.0;
+            const long long r0 = s / U, r1 = (e - 1) / U;
+            if (r0 == r1) return gm[(int)(e - s)];
+            return gm[(int)(U - s % U)] + (double)(r1 - r0 - 1) * gm[U] + gm[(int)(e - r1 * U)];
+        };
+        auto cuts_for = [&](double bound, std::vector<long long> *cuts) {
+            long long pos = 0;
+            for (int q = 0; q < P; ++q) {
+                // longest range from pos whose cost stays within the bound
+                long long lo = pos, hi = T;
+                while (lo < hi) {
+                    const long long mid = (lo + hi + 1) / 2;
+                    if (range_cost(pos, mid) <= bound + 1e-9) lo = mid; else hi = mid - 1;
+                }
+                pos = lo;
+                if (cuts) cuts->push_back(pos);
+                if (pos >= T) break;
+            }
+            return pos >= T;
+        };
+        double lo = 0.0, hi = range_cost(0, T);
+        for (int it = 0; it < 50; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (cuts_for(mid, nullptr)) hi = mid; else lo = mid;
+        }
+        std::vector<long long> cuts;
+        cuts_for(hi, &cuts);
+        // whole tiles round-robin cost 4 per tile: keep them unless the balanced cut is really shorter
+        const long long rr_tiles = ((long long)rows * (U / 4) + P - 1) / P;
+        if (hi > 0.99 * 4.0 * (double)rr_tiles) cuts.clear();
+        long long s = 0;
+        for (size_t q = 0; q < cuts.size(); ++q) {
+            const long long e = cuts[q];
+            while (s < e) {
+                const int row = (int)(s / U);
+                long long seg_end = (long long)(row + 1) * U;
+                if (seg_end > e) seg_end = e;
+                int r = (int)(seg_end - s), jj = (int)(s % U);
+                while (r > 0) {  // cheapest split of the r units this range owns in this row
+                    const int n = first[r];
+                    lists[q].push_back(make_int4(row, jj * 64, n * 64, 0));
+                    jj += n;
+                    r -= n;
+                }
+                s = seg_end;
+            }
+        }
+    }
+    bool any = false;
+    for (const auto &l : lists) any = any || !l.empty();
+    if (!any) {
+        // Y2_PAIR_FORCE_UNITS=1..3: pieces of that many units round-robin (measures the cost table above)
+        int wu = 4;
+        if (const char *e = getenv("Y2_PAIR_FORCE_UNITS")) wu = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 4;
+        long long t = 0;
+        for (int row = 0; row < rows; ++row)
+            for (int j = 0; j < U; j += wu, ++t) {
+                const int n = U - j < wu ? U - j : wu;
+                lists[(size_t)(t % P)].push_back(make_int4(row, j * 64, n * 64, 0));
+            }
+    }
+    size_t longest = 0;
+    for (const auto &l : lists) longest = l.size() > longest ? l.size() : longest;
+    stride = (int)longest + 1;
+    work.assign((size_t)P * stride, make_int4(0, 0, 0, 0));
+    for (int q = 0; q < P; ++q)
+        for (size_t i = 0; i < lists[q].size(); ++i) work[(size_t)q * stride + i] = lists[q][i];
+}
+
 int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
 {
     if ((d->ksize != 3 && d->ksize != 1) || d->block_k != kPairBK || d->block_n != 256 || d->npad % kPairN ||
@@ -477,26 +523,17 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int tiles = p.tiles_m * p.tiles_n;
     const int pairs = tiles < sms / 2 ? tiles : sms / 2;
     pl->grid = 2 * pairs;
-    // stream-K when whole tiles would leave the last wave badly filled (and there is a K loop to split)
-    p.streamk = 0;
-    p.sk_partial = nullptr;
-    p.sk_flags = nullptr;
-    // Opt-in (Y2_PAIR_STREAMK=1).  Measured on yolo-voc b64: it removes 5 % of the L23 kernel's cycles and gains
-    // 1 % on the step during the first ~70 ms after idle, but under sustained load the chip sits at its 1 kW cap,
-    // where only energy per step counts: the parked partial sums cost more than the idle SMs did and the
-    // sustained step is 0.8 % SLOWER with it (1.912 / 1.932 vs 1.901 / 1.913 ms, tools/ab_sustained.sh).
-    if (tiles > pairs && p.cblocks >= 2 && taps == 9) {  // short K loops: the parked partials would cost even more
-        const char *e = getenv("Y2_PAIR_STREAMK");
-        p.streamk = e && atoi(e) != 0;
-    }
-    if (p.streamk) {
-        const size_t partial_bytes = (size_t)(pairs + 1) * kPairN * 256 * sizeof(float);
-        const size_t flag_bytes = (size_t)(pairs + 1) * 16 * sizeof(int);
-        Y2_CUDA_CHECK(cudaMalloc(&pl->sk_buf, partial_bytes + flag_bytes));
-        Y2_CUDA_CHECK(cudaMemset(pl->sk_buf, 0, partial_bytes + flag_bytes));
-        p.sk_partial = (float *)pl->sk_buf;
-        p.sk_flags = (int *)((char *)pl->sk_buf + partial_bytes);
-    }
+    rc = encode_2d_bf16(&pl->tm_b32, d->wt, (uint64_t)ktot, (uint64_t)d->npad, (uint64_t)ktot * 2, (uint32_t)kPairBK,
+                        32u, kPairBK);
+    if (rc != Y2_OK) return rc;
+    std::vector<int4> work;
+    int stride = 0;
+    const char *bal = getenv("Y2_PAIR_BALANCE");
+    pair_schedule(p.tiles_m, d->npad / 64, pairs, !(bal && atoi(bal) == 0), work, stride);
+    Y2_CUDA_CHECK(cudaMalloc(&pl->work_buf, work.size() * sizeof(int4)));
+    Y2_CUDA_CHECK(cudaMemcpy(pl->work_buf, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    p.work = (const int4 *)pl->work_buf;
+    p.work_stride = stride;
     static bool attr_done[64] = {false};
     int dev = 0;
     Y2_CUDA_CHECK(cudaGetDevice(&dev));
@@ -512,12 +549,22 @@ int pair_plan_launch(const y2_conv_plan *pl, cudaStream_t st)
 {
     if (pl->taps == 9)
         Y2_CUDA_CHECK(launch_pdl(conv_pair_kernel<9>, dim3(pl->grid), dim3(kPairThreads), pl->smem_bytes, st, pl->tm_a,
-                                 pl->tm_b, pl->tm_out, pl->slab));
+                                 pl->tm_b, pl->tm_b32, pl->tm_out, pl->slab));
     else
         Y2_CUDA_CHECK(launch_pdl(conv_pair_kernel<1>, dim3(pl->grid), dim3(kPairThreads), pl->smem_bytes, st, pl->tm_a,
-                                 pl->tm_b, pl->tm_out, pl->slab));
+                                 pl->tm_b, pl->tm_b32, pl->tm_out, pl->slab));
     Y2_LAUNCH_CHECK();
     return Y2_OK;
 }
 
 } // namespace y2
+
+extern "C" int y2_pair_schedule(int rows, int units, int pairs, int balanced, int *out, int cap_entries, int *stride)
+{
+    if (rows <= 0 || units <= 0 || units % 4 || pairs <= 0 || !out || !stride) return Y2_EINVAL;
+    std::vector<int4> work;
+    y2::pair_schedule(rows, units, pairs, balanced != 0, work, *stride);
+    if ((long long)work.size() > cap_entries) return Y2_EINVAL;
+    memcpy(out, work.data(), work.size() * sizeof(int4));
+    return (int)work.size();
+}

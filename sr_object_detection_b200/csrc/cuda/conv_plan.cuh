@@ -42,10 +42,9 @@ struct SlabParams {
     int tma_store;         // bf16 output leaves through per-warp TMA stores (else direct 16-byte stores)
     int couple;            // epilogue warps re-synchronise every tile even when (alpha, beta) do not change
     int reverse;           // slab kernel: walk the position tiles last-to-first (see slab_plan_init)
-    int streamk;           // pair kernel: K-split work distribution (conv_pair.cu), else whole tiles round-robin
+    const int4 *work;      // pair kernel: per-pair lists of pieces (m_tile, n0, ncols, -), ncols == 0 terminates
+    int work_stride;       // entries per pair in `work`
     int dbg;               // pair kernel, timing experiments only (Y2_PAIR_DBG): bit 0 = skip the weight loads of odd taps (WRONG results)
-    float *sk_partial;     // [pairs][256 filters][256 positions] fp32 partial accumulators of split tiles
-    int *sk_flags;         // [pairs][16 epilogue warps] "partial written" flags, zero between launches
     const float *alpha;
     const float *beta;
     void *out;
@@ -85,6 +84,7 @@ struct y2_conv_plan {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
     CUtensorMap tm_out;  // slab kernel: the output tensor (TMA stores)
+    CUtensorMap tm_b32;  // pair kernel: the weights in 32-filter boxes (narrow pieces)
     int variant;
     y2::ConvParams prm;
     y2::SlabParams slab;
@@ -92,7 +92,7 @@ struct y2_conv_plan {
     int block_n, block_k, taps;
     int grid;
     size_t smem_bytes;
-    void *sk_buf = nullptr;  // device scratch of the stream-K pair kernel (partials + flags), owned by the plan
+    void *work_buf = nullptr;  // device copy of the pair kernel's work lists, owned by the plan
 };
 
 namespace y2 {

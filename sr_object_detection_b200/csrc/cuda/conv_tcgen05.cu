@@ -467,7 +467,7 @@ extern "C" int y2_conv_plan_launch(const y2_conv_plan *pl, y2_stream_t s)
 extern "C" void y2_conv_plan_destroy(y2_conv_plan *pl)
 {
     if (!pl) return;
-    if (pl->sk_buf) cudaFree(pl->sk_buf);
+    if (pl->work_buf) cudaFree(pl->work_buf);
     delete pl;
 }
 

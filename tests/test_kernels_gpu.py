@@ -55,8 +55,8 @@ CONV_CASES = [
     (1, 32, 208, 208, 64, 3, 64, 32, ACT_LEAKY),
     (3, 128, 52, 52, 256, 3, 256, 64, ACT_LEAKY),
     (5, 128, 17, 23, 64, 1, 64, 64, ACT_LINEAR),
-    # more tiles than CTA pairs with a badly filled last wave: under the "streamk" variant the pair kernel runs
-    # its stream-K schedule (tiles split between pairs along K, partial sums joined through global scratch)
+    # more tiles than CTA pairs with a badly filled last wave: the pair kernel cuts the work into pieces of 64..256
+    # filters and balances them over the pairs; the "roundrobin" variant runs whole 256-filter tiles instead
     (64, 256, 13, 13, 512, 3, 256, 64, ACT_LEAKY),
     (64, 128, 13, 13, 1024, 3, 256, 64, ACT_LINEAR),
     (48, 192, 13, 13, 768, 3, 256, 64, ACT_LEAKY),
@@ -66,17 +66,17 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=["auto", "slab", "pertap", "pair", "streamk"])
+@pytest.fixture(params=["auto", "slab", "pertap", "pair", "roundrobin"])
 def conv_variant(request, monkeypatch):
     """All three implicit-GEMM kernels stay under test: the default choice (CTA-pair kernel for wide
     layers), the halo-slab kernel alone, the per-tap fallback, and the pair kernel wherever its shape
     constraints allow it, however small the layer (Y2_CONV_VARIANT is read at plan creation)."""
-    monkeypatch.delenv("Y2_PAIR_STREAMK", raising=False)
+    monkeypatch.delenv("Y2_PAIR_BALANCE", raising=False)
     if request.param == "auto":  # CTA-pair kernel where it fits, then slab, then per-tap
         monkeypatch.delenv("Y2_CONV_VARIANT", raising=False)
-    elif request.param == "streamk":  # default choice with the pair kernel's opt-in stream-K schedule
+    elif request.param == "roundrobin":  # default choice, pair kernel on whole tiles round-robin
         monkeypatch.delenv("Y2_CONV_VARIANT", raising=False)
-        monkeypatch.setenv("Y2_PAIR_STREAMK", "1")
+        monkeypatch.setenv("Y2_PAIR_BALANCE", "0")
     else:
         monkeypatch.setenv("Y2_CONV_VARIANT", request.param)
     return request.param
