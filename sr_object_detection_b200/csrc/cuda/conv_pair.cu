@@ -171,6 +171,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int stage = 0;
         uint32_t phase = 0;
         int issued = 0;
+        if (TAPS == 1 && prm.b_resident) {
+            // 1x1 layer whose whole weight half fits: stage nt * cblocks + cb holds channel block cb of filter tile nt
+            // for the lifetime of the CTA (loaded under the previous layer's tail, never released)
+            if (elect_one_sync()) {
+                for (int nt = 0; nt < prm.tiles_n; ++nt)
+                    for (int cb = 0; cb < cblocks; ++cb) {
+                        const int st = nt * cblocks + cb;
+                        if (leader) mbar_expect_tx(&b_full[st], 2u * kPairBHalfBytes);
+                        tma_load_2d_pair(&tm_b, &b_full[st], smem_b + (size_t)st * kPairBHalfBytes, cb * kPairBK,
+                                         nt * kPairN + (int)rank * 128);
+                    }
+            }
+            __syncwarp();
+        } else
         while (sched.next(seg)) {
             const int half_rows = seg.ncols >> 1;  // 32, 64, 96 or 128 filters per CTA
             const int n0 = seg.n0 + (int)rank * half_rows;
@@ -205,7 +219,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
             int sa_i = 0, sb_i = 0;
-            uint32_t pa = 0, pb = 0;
+            uint32_t pa = 0, pb = 0, b_seen = 0;
             int it = 0;
             const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -225,7 +239,16 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     const uint32_t acc_first = cb != 0;
 #pragma unroll
                     for (int tap = 0; tap < TAPS; ++tap) {
-                        mbar_wait(&b_full[sb_i], pb, 5);
+                        const bool resident = TAPS == 1 && prm.b_resident;
+                        if (resident) {  // the stage never changes: wait for its one and only fill, once
+                            sb_i = (seg.n0 >> 8) * cblocks + cb;
+                            if (!((b_seen >> sb_i) & 1u)) {
+                                mbar_wait(&b_full[sb_i], 0, 5);
+                                b_seen |= 1u << sb_i;
+                            }
+                        } else {
+                            mbar_wait(&b_full[sb_i], pb, 5);
+                        }
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const uint32_t b_lo = b_lo0 + (uint32_t)sb_i * (kPairBHalfBytes >> 4);
@@ -235,14 +258,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 umma_bf16_pair(d0, ((uint64_t)kPairDescHi << 32) | (uint64_t)(a_tap + (uint32_t)(k * 2)),
                                                ((uint64_t)kPairDescHi << 32) | (uint64_t)(b_lo + (uint32_t)(k * 2)),
                                                idesc, (tap == 0 && k == 0) ? acc_first : 1u);
-                            umma_commit_pair(&b_empty[sb_i]);
+                            if (!resident) umma_commit_pair(&b_empty[sb_i]);
                             if (tap == TAPS - 1) {
                                 umma_commit_pair(&a_empty[sa_i]);
                                 if (cb == cblocks - 1) umma_commit_pair(&tfull_bar[buf]);
                             }
                         }
                         __syncwarp();
-                        if (++sb_i == stages_b) { sb_i = 0; pb ^= 1; }
+                        if (!resident && ++sb_i == stages_b) { sb_i = 0; pb ^= 1; }
                     }
                     if (++sa_i == stages_a) { sa_i = 0; pa ^= 1; }
                 }
@@ -455,13 +478,18 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // 1x1 layers: only bf16 tensors through the TMA-store epilogue, and only when there is enough work to
     // fill the pairs (small layers stay on the single-CTA kernels, which have more CTAs to spread over)
     if (taps == 1 && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;
-    // Measured (yolo-voc L13 / L19, batch 64): the one-tap pair kernel runs 20.9 / 21.0 us against 18.8 / 20.1
-    // of the slab kernel - these layers are bound by L2 -> shared-memory operand traffic and by their few
-    // tiles, not by the tensor pipe - so it is only used when asked for (Y2_CONV_VARIANT=pair; tests).
-    if (taps == 1) {
-        const char *forced = getenv("Y2_CONV_VARIANT");
-        if (!forced || strcmp(forced, "pair")) return Y2_EINVAL;
-    }
+    // 1x1 layers are bound by L2 -> shared-memory operand traffic (no tap reuse).  When the CTA's half of the WHOLE
+    // weight matrix fits next to three activation stages (npad * cin <= 8 stages of 16 KB: yolo-voc L13 / L15,
+    // 512 -> 256) it is loaded once and stays resident, which halves that traffic.  Otherwise (L19: 1024 -> 512)
+    // the streaming one-tap pair kernel measured 21.0 us against 20.1 of the slab kernel, so it is only used when
+    // asked for (Y2_CONV_VARIANT=pair; tests).
+    const int resident_stages = (d->npad / kPairN) * (d->cin / kPairBK);
+    const char *forced = getenv("Y2_CONV_VARIANT");
+    const bool forced_pair = forced && !strcmp(forced, "pair");
+    const bool resident = taps == 1 && resident_stages <= 8 && !getenv("Y2_PAIR_NO_RESIDENT");
+    if (taps == 1 && !resident && !forced_pair) return Y2_EINVAL;
+    // small layers stay on the single-CTA kernels, which have more CTAs to spread over
+    if (taps == 1 && resident && !forced_pair && total < 2ll * 256 * (sm_count() / 2)) return Y2_EINVAL;
     const int halo = taps == 9 ? wp + 1 : 0;
     const int slab_rows = 128 + 2 * halo;
     const int loads = (slab_rows + 255) / 256;
@@ -471,10 +499,18 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int slab_bytes = loads * box_rows * kPairRowBytes;
     const int aux = ((2 * kPairN * 8 + 512 + 1023) / 1024) * 1024 + 8 * 4096;  // alpha/beta, barriers | store staging
     const int budget = 227 * 1024 - 1024 - aux;
-    const int stages_a = taps == 9 ? 2 : kPairMaxStagesA;  // 1x1: a fresh A tile every K step
-    int stages_b = (budget - stages_a * slab_bytes) / kPairBHalfBytes;
-    if (stages_b > kPairMaxStagesB) stages_b = kPairMaxStagesB;
-    if (stages_b < 4) return Y2_EINVAL;
+    int stages_a = taps == 9 ? 2 : kPairMaxStagesA;  // 1x1: a fresh A tile every K step
+    int stages_b;
+    if (resident) {
+        stages_b = resident_stages;
+        stages_a = (budget - stages_b * kPairBHalfBytes) / slab_bytes;
+        if (stages_a > kPairMaxStagesA) stages_a = kPairMaxStagesA;
+        if (stages_a < 2) return Y2_EINVAL;
+    } else {
+        stages_b = (budget - stages_a * slab_bytes) / kPairBHalfBytes;
+        if (stages_b > kPairMaxStagesB) stages_b = kPairMaxStagesB;
+        if (stages_b < 4) return Y2_EINVAL;
+    }
     const int sms = sm_count();
     if (sms < 2) return Y2_EINVAL;
     const int ktot = taps * d->cin;
@@ -506,6 +542,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     p.couple = 0;
     p.tma_store = 0;
     p.dbg = getenv("Y2_PAIR_DBG") ? atoi(getenv("Y2_PAIR_DBG")) : 0;
+    p.b_resident = resident ? 1 : 0;
     memset(&pl->tm_out, 0, sizeof(pl->tm_out));
     if (d->out_mode == Y2_OUT_BF16_PADDED && d->cout % 64 == 0 && !getenv("Y2_SLAB_NO_TMA_STORE")) {
         rc = encode_2d_bf16(&pl->tm_out, d->out, (uint64_t)d->cout, (uint64_t)total, (uint64_t)d->out_cs * 2, 64u, 32u, 64);
@@ -529,7 +566,8 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     std::vector<int4> work;
     int stride = 0;
     const char *bal = getenv("Y2_PAIR_BALANCE");
-    pair_schedule(p.tiles_m, d->npad / 64, pairs, !(bal && atoi(bal) == 0), work, stride);
+    // resident weights are laid out per 256-filter tile: whole tiles only
+    pair_schedule(p.tiles_m, d->npad / 64, pairs, !(bal && atoi(bal) == 0) && !resident, work, stride);
     Y2_CUDA_CHECK(cudaMalloc(&pl->work_buf, work.size() * sizeof(int4)));
     Y2_CUDA_CHECK(cudaMemcpy(pl->work_buf, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice));
     p.work = (const int4 *)pl->work_buf;

@@ -44,6 +44,7 @@ struct SlabParams {
     int reverse;           // slab kernel: walk the position tiles last-to-first (see slab_plan_init)
     const int4 *work;      // pair kernel: per-pair lists of pieces (m_tile, n0, ncols, -), ncols == 0 terminates
     int work_stride;       // entries per pair in `work`
+    int b_resident;        // pair kernel, 1x1: the CTA's half of the whole weight matrix stays in shared memory
     int dbg;               // pair kernel, timing experiments only (Y2_PAIR_DBG): bit 0 = skip the weight loads of odd taps (WRONG results)
     const float *alpha;
     const float *beta;
