@@ -478,18 +478,18 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // 1x1 layers: only bf16 tensors through the TMA-store epilogue, and only when there is enough work to
     // fill the pairs (small layers stay on the single-CTA kernels, which have more CTAs to spread over)
     if (taps == 1 && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;
-    // 1x1 layers are bound by L2 -> shared-memory operand traffic (no tap reuse).  When the CTA's half of the WHOLE
-    // weight matrix fits next to three activation stages (npad * cin <= 8 stages of 16 KB: yolo-voc L13 / L15,
-    // 512 -> 256) it is loaded once and stays resident, which halves that traffic.  Otherwise (L19: 1024 -> 512)
-    // the streaming one-tap pair kernel measured 21.0 us against 20.1 of the slab kernel, so it is only used when
-    // asked for (Y2_CONV_VARIANT=pair; tests).
+    // 1x1 layers: the one-tap form of this kernel measured 21.0 us (L19, 1024 -> 512) against 20.1 of the slab kernel,
+    // so it is only used when asked for (Y2_CONV_VARIANT=pair; tests).  Y2_PAIR_RESIDENT=1 additionally keeps the CTA's
+    // half of the WHOLE weight matrix in shared memory when it fits next to two activation stages (npad * cin <= 8
+    // stages of 16 KB: yolo-voc L13 / L15, 512 -> 256): that halves the L2 -> shared traffic (ncu: 106 -> 68 MB) and
+    // still loses, 18.2 us against 16.5 of the slab kernel (profiles/r2o_resident.txt) - with three activation stages
+    // left the K loop of a 1x1 layer (8 steps of 512 clk per tile) is latency-bound, not traffic-bound.
     const int resident_stages = (d->npad / kPairN) * (d->cin / kPairBK);
     const char *forced = getenv("Y2_CONV_VARIANT");
     const bool forced_pair = forced && !strcmp(forced, "pair");
-    const bool resident = taps == 1 && resident_stages <= 8 && !getenv("Y2_PAIR_NO_RESIDENT");
-    if (taps == 1 && !resident && !forced_pair) return Y2_EINVAL;
-    // small layers stay on the single-CTA kernels, which have more CTAs to spread over
-    if (taps == 1 && resident && !forced_pair && total < 2ll * 256 * (sm_count() / 2)) return Y2_EINVAL;
+    const char *res_env = getenv("Y2_PAIR_RESIDENT");
+    const bool resident = taps == 1 && resident_stages <= 8 && res_env && atoi(res_env) != 0;
+    if (taps == 1 && !forced_pair && !(resident && total >= 2ll * 256 * (sm_count() / 2))) return Y2_EINVAL;
     const int halo = taps == 9 ? wp + 1 : 0;
     const int slab_rows = 128 + 2 * halo;
     const int loads = (slab_rows + 255) / 256;

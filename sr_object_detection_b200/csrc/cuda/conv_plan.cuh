@@ -45,7 +45,8 @@ struct SlabParams {
     const int4 *work;      // pair kernel: per-pair lists of pieces (m_tile, n0, ncols, -), ncols == 0 terminates
     int work_stride;       // entries per pair in `work`
     int b_resident;        // pair kernel, 1x1: the CTA's half of the whole weight matrix stays in shared memory
-    int dbg;               // pair kernel, timing experiments only (Y2_PAIR_DBG): bit 0 = skip the weight loads of odd taps (WRONG results)
+    int dbg;               // timing experiments only, WRONG results (Y2_PAIR_DBG / Y2_SLAB_DBG): 1 = pair kernel skips the weight
+                           // loads of odd taps, 2 = slab kernel skips the epilogue math and stores, 4 = slab kernel issues no MMAs
     const float *alpha;
     const float *beta;
     void *out;

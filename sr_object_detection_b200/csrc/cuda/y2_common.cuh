@@ -43,8 +43,12 @@ int sm_count();
 // allocate TMEM and prefetch WEIGHT tiles (which do not depend on layer i) while layer i's last wave drains, and
 // only the warp that loads ACTIVATIONS blocks in pdl_wait() until layer i has completed and its stores are visible.
 // Without the attribute both instructions are no-ops.  Y2_NO_PDL=1 launches everything the plain way.
+// Only the persistent convolution kernels use it.  Measured (profiles/r2q_pdl_small.txt, A/B in one box): with the
+// pool / reorg / shortcut / region / NMS kernels launched the same way the step gets SLOWER (yolo-voc 1.655 -> 1.68 ms,
+// resnet50 2.51 -> 2.60, tiny-yolo-voc 0.673 -> 0.698): once all blocks of such a grid have started, the next
+// convolution's CTAs (227 KB of shared memory, 59 k registers each) take over the SMs one by one and sit in
+// griddepcontrol.wait while the small kernel's tail runs on what is left.
 bool pdl_enabled();
-
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args... args)
@@ -315,13 +319,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar)
                      "r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  Default semantics (release at CTA scope, the
+// form cutlass::arch::ClusterBarrier::arrive uses): the explicit .release.cluster costs a MEMBAR.ALL.CTA + ERRBAR per
+// arrival (19 % of the samples of a short kernel, profiles/r2p_*), and what the arrival publishes here - "this thread's
+// tcgen05.ld of the accumulator has completed" - is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
 {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
 }
