@@ -138,7 +138,7 @@ __device__ __forceinline__ void slab_affine_pack(const uint32_t (&v)[32], const 
 // copy engine writes full 128-byte lines, the LSU sees 8 shared-memory stores per thread instead of 8
 // global stores that touch 32 different lines each.
 __device__ __forceinline__ void slab_store_tma(const void *tm_out, uint4 *stage, const uint4 (&w)[8], int lane,
-                                               int p_first, int ch0)
+                                               int p_first, int ch0, bool issue = true)
 {
     // the previous box of this warp must have been read out of the staging tile
     if (lane == 0) tma_store_wait_read();
@@ -147,7 +147,7 @@ __device__ __forceinline__ void slab_store_tma(const void *tm_out, uint4 *stage,
     for (int c = 0; c < 8; ++c) stage[lane * 8 + (c ^ (lane & 7))] = w[c];
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && issue) {
         tma_store_2d(tm_out, stage, ch0, p_first);
         tma_store_commit();
     }

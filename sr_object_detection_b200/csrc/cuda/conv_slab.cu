@@ -316,7 +316,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             slab_affine_pack<Y2_ACT_LOGISTIC>(v0, sab, col0 + c, valid, w);
                             slab_affine_pack<Y2_ACT_LOGISTIC>(v1, sab, col0 + c + 32, valid, w + 4);
                         }
-                        slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + col0 + c);
+                        slab_store_tma(&tm_out, s_stage + (warp - 3) * 256, w, lane, p - lane, n0 + col0 + c, !(prm.dbg & 8));
                     } else if (prm.act == Y2_ACT_LEAKY) {
                         slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v0, sab, col0 + c, n0, p, b, y, x, in_range, valid);
                         slab_epilogue_chunk<Y2_ACT_LEAKY>(prm, v1, sab, col0 + c + 32, n0, p, b, y, x, in_range, valid);
