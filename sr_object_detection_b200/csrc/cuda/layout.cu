@@ -648,6 +648,56 @@ __global__ void shortcut_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
     }
 }
 
+// The common case of the above (every block of resnet50 but the first of a stage): `add` has the running tensor's
+// extent and at least its channels, the activation maps 0 to 0 (linear / leaky).  Pad positions of all operands
+// hold zeros (the producers store them, fp32 streams are allocated zeroed and only ever written here), so
+// act(0 + 0) = 0 is what belongs there and the kernel is a flat elementwise pass over 8-channel groups: no
+// coordinates, no divisions (the general kernel spends four 64-bit divisions per group and reaches 4.6 TB/s).
+// ---------------------------------------------------------------------------------
+template <bool ADD32, bool OUT32, bool LEAKY>
+__global__ void shortcut_same_kernel(const __nv_bfloat16 *__restrict__ in, int in_cs,
+                                     const __nv_bfloat16 *__restrict__ add, int add_cs, __nv_bfloat16 *__restrict__ out,
+                                     int out_cs, int c8, int c8_shift, unsigned total,
+                                     const float *__restrict__ add32, int add32_cs, float *__restrict__ out32)
+{
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        unsigned p, g;
+        if (c8_shift >= 0) {
+            p = t >> c8_shift;
+            g = t & (unsigned)(c8 - 1);
+        } else {
+            p = t / (unsigned)c8;
+            g = t - p * (unsigned)c8;
+        }
+        const uint4 vi = __ldg(reinterpret_cast<const uint4 *>(in + (size_t)p * in_cs + g * 8));
+        const __nv_bfloat16 *hi = reinterpret_cast<const __nv_bfloat16 *>(&vi);
+        float f[8], a[8];
+        if (ADD32) {
+            const float4 *pa = reinterpret_cast<const float4 *>(add32 + (size_t)p * add32_cs + g * 8);
+            const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        } else {
+            const uint4 va = __ldg(reinterpret_cast<const uint4 *>(add + (size_t)p * add_cs + g * 8));
+            const __nv_bfloat16 *ha = reinterpret_cast<const __nv_bfloat16 *>(&va);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = __bfloat162float(ha[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            f[q] = __bfloat162float(hi[q]) + a[q];
+            if (LEAKY) f[q] = (f[q] > 0.f) ? f[q] : 0.1f * f[q];
+        }
+        if (OUT32) {
+            float4 *po = reinterpret_cast<float4 *>(out32 + (size_t)p * (c8 * 8) + g * 8);
+            po[0] = make_float4(f[0], f[1], f[2], f[3]);
+            po[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        *reinterpret_cast<uint4 *>(out + (size_t)p * out_cs + g * 8) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // connected layer input (connected_layer.c:122-155 reads state.input as a flat vector): the tensor of the layer
 // before it, or a vector, as ONE padded-NHWC position per image ([B][2][2][kpad], h = w = 1), so that the layer is a
@@ -767,6 +817,26 @@ extern "C" int y2_shortcut(const void *in, int in_cs, const void *add, int add_c
         return Y2_EINVAL;
     }
     const long long total = (long long)batch * (out_h + 1) * (out_w + 1) * (out_cpad / 8);
+    if (add_h == out_h && add_w == out_w && add_c >= out_c && out_c == out_cpad && act != Y2_ACT_LOGISTIC &&
+        total < 0x7fffffffLL && !getenv("Y2_SHORTCUT_GENERAL")) {
+        const int c8 = out_cpad / 8;
+        int shift = -1;
+        if ((c8 & (c8 - 1)) == 0)
+            for (shift = 0; (1 << shift) < c8; ++shift) {}
+        const int grid = grid_for(total, 256);
+        const bool leaky = act == Y2_ACT_LEAKY;
+#define Y2_SC(A, O, L)                                                                                           \
+    shortcut_same_kernel<A, O, L><<<grid, 256, 0, to_stream(s)>>>(                                              \
+        (const __nv_bfloat16 *)in, in_cs, (const __nv_bfloat16 *)add, add_cs, (__nv_bfloat16 *)out, out_cs, c8, \
+        shift, (unsigned)total, add_f32, add_f32_cs, out_f32)
+        if (add_f32 && out_f32) { if (leaky) Y2_SC(true, true, true); else Y2_SC(true, true, false); }
+        else if (add_f32) { if (leaky) Y2_SC(true, false, true); else Y2_SC(true, false, false); }
+        else if (out_f32) { if (leaky) Y2_SC(false, true, true); else Y2_SC(false, true, false); }
+        else { if (leaky) Y2_SC(false, false, true); else Y2_SC(false, false, false); }
+#undef Y2_SC
+        Y2_LAUNCH_CHECK();
+        return Y2_OK;
+    }
     shortcut_kernel<<<grid_for(total, 256), 256, 0, to_stream(s)>>>(
         (const __nv_bfloat16 *)in, in_cs, (const __nv_bfloat16 *)add, add_cs, add_c, add_h, add_w,
         (__nv_bfloat16 *)out, out_cs, out_cpad / 8, out_c, out_h, out_w, batch, act, add_f32, add_f32_cs, out_f32);

@@ -612,3 +612,55 @@ def test_im2col_ongpu_helper_matches_unfold():
     lib.im2col_ongpu(dx.data_ptr(), c, h, w, k, stride, pad, col.data_ptr())
     torch.cuda.synchronize()
     assert torch.equal(col.cpu(), want)
+
+
+def _shortcut_reference(x, add, act):
+    """shortcut_layer.c:39-59 -> blas.c:57-81 (shortcut_cpu) + activate_array, on NCHW fp32 tensors."""
+    b, c2, h2, w2 = x.shape
+    _, c1, h1, w1 = add.shape
+    stride, sample = max(w1 // w2, 1), max(w2 // w1, 1)
+    minw, minh, minc = min(w1, w2), min(h1, h2), min(c1, c2)
+    out = x.clone()
+    out[:, :minc, 0:minh * sample:sample, 0:minw * sample:sample] += add[:, :minc, 0:minh * stride:stride, 0:minw * stride:stride]
+    if act == ACT_LEAKY:
+        out = torch.where(out > 0, out, 0.1 * out)
+    return out
+
+
+@pytest.mark.parametrize("case", [
+    # (out_c, out_h, out_w, add_c, add_h, add_w, act, fp32 stream in, fp32 stream out)
+    (256, 16, 16, 256, 16, 16, ACT_LEAKY, True, True),     # resnet50's common block: the division-free kernel
+    (256, 16, 16, 256, 16, 16, ACT_LEAKY, False, True),
+    (192, 9, 13, 192, 9, 13, ACT_LINEAR, True, False),     # 24 channel groups: not a power of two
+    (64, 8, 8, 128, 8, 8, ACT_LEAKY, False, False),        # `from` has more channels than the running tensor
+    (256, 16, 16, 64, 16, 16, ACT_LEAKY, False, True),     # first block of a stage: 64 channels into 256 (general)
+    (128, 8, 8, 64, 16, 16, ACT_LEAKY, True, True),        # downsampling block: stride 2 (general)
+], ids=lambda c: "c%d_%dx%d_from_c%d_%dx%d_a%d_%d%d" % c)
+def test_shortcut_matches_reference(case, monkeypatch):
+    out_c, oh, ow, add_c, ah, aw, act, in32, out32 = case
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch = 3
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = (torch.randn(batch, out_c, oh, ow, generator=g)).to(dev).to(torch.bfloat16).float()
+    add_f = torch.randn(batch, add_c, ah, aw, generator=g).to(dev)
+    add_b = add_f.to(torch.bfloat16)
+    x_p, add_p = G.to_padded_nhwc(x), G.to_padded_nhwc(add_b.float())
+    add32_p = torch.zeros(batch, ah + 1, aw + 1, add_c, device=dev)
+    add32_p[:, :ah, :aw, :] = add_f.permute(0, 2, 3, 1)
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("Y2_SHORTCUT_GENERAL", "1")
+        out = torch.full((batch, oh + 1, ow + 1, out_c), 3.0, dtype=torch.bfloat16, device=dev)
+        o32 = torch.zeros(batch, oh + 1, ow + 1, out_c, device=dev) if out32 else None
+        _lib.check(lib.y2_shortcut(x_p.data_ptr(), out_c, add_p.data_ptr(), add_c, add_c, ah, aw, out.data_ptr(), out_c,
+                                   out_c, out_c, oh, ow, batch, act, add32_p.data_ptr() if in32 else None, add_c,
+                                   o32.data_ptr() if out32 else None, _stream()))
+        torch.cuda.synchronize()
+        ref = _shortcut_reference(x, add_f if in32 else add_b.float(), act)
+        got = G.from_padded_nhwc(out, out_c, oh, ow)
+        assert torch.equal(got, ref.to(torch.bfloat16).float()), f"general={general}"
+        assert out[:, oh].abs().max().item() == 0 and out[:, :, ow].abs().max().item() == 0   # pads stay zero
+        if out32:
+            assert torch.equal(o32[:, :oh, :ow, :].permute(0, 3, 1, 2), ref)
+            assert o32[:, oh].abs().max().item() == 0 and o32[:, :, ow].abs().max().item() == 0
