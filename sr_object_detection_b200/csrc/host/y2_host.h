@@ -32,6 +32,7 @@ typedef struct y2_layer_rt {
     size_t own_bytes;
     int placed_in;      /* route layer index whose concat buffer holds this output, or -1 */
     int copy_needed;    /* route: bitmask of inputs that need an explicit copy */
+    int packed_concat;  /* route: inputs carry padding channels, their real channels are packed by copies */
     /* convolution */
     y2_conv_plan *plan;
     void *wt_dev;       /* bf16 [npad][ktot] */

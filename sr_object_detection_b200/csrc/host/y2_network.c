@@ -930,17 +930,28 @@ void y2_plan_network(network *net)
         }
         case ROUTE: {
             r->out_kind = Y2_KIND_BF16_PADDED;
-            int total = 0;
+            int total = 0, total_real = 0, padded = 0;
             for (int k = 0; k < l->n; ++k) {
                 y2_layer_rt *ir = (y2_layer_rt *)net->layers[l->input_layers[k]].b200;
+                const int real_c = net->layers[l->input_layers[k]].out_c;
                 if (ir->out_kind != Y2_KIND_BF16_PADDED) unsupported(i, "route from a flat layer");
-                if (l->n > 1 && ir->cpad != net->layers[l->input_layers[k]].out_c)
-                    unsupported(i, "concat of channel-padded tensors");
+                if (l->n > 1 && ir->cpad != real_c) padded = 1;
                 total += ir->cpad;
+                total_real += real_c;
             }
             if (!l->out_w || !l->out_h) unsupported(i, "route over mismatched extents");
             r->cpad = total;
-            if (l->n > 1) {
+            if (padded) {
+                /* an input stores more channels than it has (48 -> 64): the reference's concat has no holes
+                 * (route_layer.c:73-86), so the real channels are packed next to each other by copies instead of
+                 * being written in place; the tail of the buffer up to the storage granularity stays zero */
+                for (int k = 0; k < l->n; ++k)
+                    if (net->layers[l->input_layers[k]].out_c % 8)
+                        unsupported(i, "concat of tensors whose channel count is not a multiple of 8");
+                r->cpad = storage_channels(total_real);
+                r->packed_concat = 1;
+                r->copy_needed = (1 << l->n) - 1;
+            } else if (l->n > 1) {
                 /* claim the producers: they will write into this layer's concat buffer */
                 for (int k = 0; k < l->n; ++k) {
                     int src = l->input_layers[k];
@@ -1303,12 +1314,13 @@ void forward_route_layer_gpu(layer l, network_state state)
     for (int k = 0; k < l.n; ++k) {
         layer src = state.net.layers[l.input_layers[k]];
         y2_layer_rt *ir = y2_lrt(src);
+        const int nch = r->packed_concat ? src.out_c : ir->cpad;  /* packed: real channels only */
         if (r->copy_needed & (1 << k)) {
             Y2_CHECK(y2_copy_channels(ir->out, ir->out_cs, (char *)r->out + (size_t)off * 2, r->out_cs, l.batch,
-                                      ir->cpad, l.out_h, l.out_w, net_stream(state.net)));
+                                      nch, l.out_h, l.out_w, net_stream(state.net)));
             count_launch(state.net, 1);
         }
-        off += ir->cpad;
+        off += nch;
     }
 }
 

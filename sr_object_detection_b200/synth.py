@@ -142,6 +142,18 @@ def mini_dense_cfg(batch=2, w=64, h=64, classes=4, num=3):
     return s + _region(anchors, classes, num)
 
 
+def mini_dense_odd_cfg(batch=2, w=64, h=64, classes=4, num=3):
+    """The same pattern with channel counts that are not whole storage groups (48, 80, 24 filters: stored as 64,
+    128, 32 channels): the concat has no holes in the reference (route_layer.c:73-86), so the real channels have
+    to be packed next to each other by copies; one concat is itself an input of the next."""
+    s = _net(batch, w, h) + _conv(48, 3) + _maxpool()                                   # 0-1: 48
+    s += _conv(80, 1) + _conv(24, 3) + "[route]\nlayers=-1,-3\n\n"                      # 2-4: 24 + 48 = 72
+    s += _conv(64, 1) + _conv(40, 3) + "[route]\nlayers=-1,-3\n\n"                      # 5-7: 40 + 72 = 112
+    s += _maxpool() + _conv(64, 3) + _conv(num * (classes + 5), 1, bn=0, act="linear")  # 8-10
+    anchors = ",".join(f"{0.6 + 0.7 * i:.2f},{0.8 + 0.5 * i:.2f}" for i in range(num))
+    return s + _region(anchors, classes, num)
+
+
 EXACT_ANCHORS = "1.0,1.5, 2.5,2.0, 4.0,5.0"
 
 
@@ -310,7 +322,7 @@ def mini_alexnet_cfg(batch=2, w=32, h=32, classes=10):
 CFGS = {
     "mini-alexnet": mini_alexnet_cfg,
     "mini-reorg-reverse": mini_reorg_reverse_cfg,
-    "mini-dense": mini_dense_cfg,
+    "mini-dense": mini_dense_cfg, "mini-dense-odd": mini_dense_odd_cfg,
     "mini-yolo": mini_yolo_cfg,
     "mini-resnet": mini_resnet_cfg,
     "tiny-yolo-voc": tiny_yolo_voc_cfg,

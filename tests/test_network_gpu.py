@@ -38,6 +38,8 @@ def _setup(tmp_path, name, batch, w=416, h=416, **kw):
                                              ("tiny-yolo-voc", 2, (480, 352)), ("yolo-voc", 1, (416, 288)),
                                              # nested routes (a route that concatenates another route's output)
                                              ("mini-dense", 3, 64),
+                                             # concat inputs with padding channels (48 / 24 / 40 filters): packed by copies
+                                             ("mini-dense-odd", 3, 64),
                                              # classifier cfgs: connected / dropout layers, relu / elu / tanh
                                              ("mini-alexnet", 3, 32),
                                              # depth-to-space: a reorg layer with reverse=1
