@@ -321,9 +321,23 @@ def main() -> int:
     dets_np = np.ctypeslib.as_array(dets)
     counts_np = np.ctypeslib.as_array(counts)
 
-    def step_device():
+    def step_device():  # synchronous form: the host waits for every step's detections before launching the next
         lib.network_forward_device(net)
         lib.network_detect_device(net, THRESH, NMS, dets, counts, MAX_DET)
+
+    # `value`: the same work with the batch resident in HBM and two steps in flight, so that the device does not idle
+    # while the host picks up a step's detection lists (459 KB D2H + a stream sync per step in the synchronous form).
+    # Both slots of the pipeline get the batch once, before the timed region.
+    for s in (0, 1):
+        _lib.check(lib.y2_memcpy_h2d(lib.network_pipeline_input_device(net, s), staging, images.nbytes, stream))
+    _lib.check(lib.y2_stream_sync(stream))
+
+    def run_device(steps):
+        lib.network_detect_submit_resident(net, THRESH, NMS, MAX_DET)
+        for _ in range(1, steps):
+            lib.network_detect_submit_resident(net, THRESH, NMS, MAX_DET)
+            lib.network_detect_wait(net, dets, counts, MAX_DET)
+        lib.network_detect_wait(net, dets, counts, MAX_DET)
 
     gathered = {"images": 0, "detections": 0}
 
@@ -385,23 +399,25 @@ def main() -> int:
             return float(t.item())
         return ms.value
 
-    for _ in range(args.warmup):
+    for _ in range(3):
         step_device()
     torch.cuda.synchronize()
     launches_fwd = lib.network_launch_count(net)
+    ms_dev_sync = timed(step_device, args.steps)
+    run_device(args.warmup)
+    torch.cuda.synchronize()
     det_per_image = float(np.mean([min(c, MAX_DET) for c in counts]))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps)
+    ms_dev = timed(lambda: run_device(args.steps), 1)
     sampling = "nvidia-smi -lms 100 over the timed region"
     if ms_dev < 400.0:
         # a short timed region (--steps given by the caller): nvidia-smi samples every 100 ms, so keep the same
         # step running (untimed) for ~1.5 s more so that the clock record really is taken under this load
         t_probe = time.time()
         while time.time() - t_probe < 1.5:
-            for _ in range(10):
-                step_device()
+            run_device(10)
         torch.cuda.synchronize()
         sampling += " + 1.5 s of the same step repeated (the timed region itself was shorter than 0.4 s)"
     clocks = sampler.stop() if rank == 0 else None
@@ -542,7 +558,11 @@ def main() -> int:
                    "weights": f"random-init synthetic .weights (seed 1234), detection head scaled x{HEAD_GAIN:g} so "
                               "that decode / NMS / pick have candidates to work on",
                    "detections_per_image": round(det_per_image, 2),
-                   "schedule": "CUDA graph replay",
+                   "schedule": "CUDA graph replay; batch resident in HBM, two steps in flight (network_detect_submit_resident / "
+                               "network_detect_wait): every step's detection lists are read back to the host",
+                   "sync_value": round(total_images / (ms_dev_sync / 1000.0), 1),
+                   "sync_schedule": "network_forward_device + network_detect_device: the host waits for each step's "
+                                    "detections before it launches the next",
                    "host_thread_cpus": cpus_bound or "unbound (PCI topology not visible)",
                    "algorithmic_gflop_per_image": round(flops_img / 1e9, 3),
                    "regime": ("sustained: timed region of %.2f s under the 1 kW power cap" % (ms_dev / 1000.0))

@@ -381,6 +381,10 @@ float *network_pipeline_staging(network net, int slot);
 int network_pipeline_next_slot(network net); /* slot the next network_detect_submit will use */
 int network_detect_submit(network net, const float *input, float thresh, float nms, int max_det);
 int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det);
+/* the same with the batch already resident in the slot's DEVICE input (fp32 planar, written there by the caller -
+ * another kernel, a peer copy, one upload for many passes): no host -> device copy at all */
+float *network_pipeline_input_device(network net, int slot);
+int network_detect_submit_resident(network net, float thresh, float nms, int max_det);
 /* The same calls fed with raw decoded images: uint8 interleaved RGB [batch][h][w][3] at the network's
  * resolution.  Each byte becomes (float)(byte / 255.) on the device exactly as the reference's loaders
  * do on the host (yolo_v2_class.cpp:129-149 load_image_stb; yolo_v2_class.hpp mat_to_image), so the

@@ -243,12 +243,14 @@ static void pipe_init(network net)
     if (rt->pipe_ready) return;
     Y2_CHECK(y2_set_device(rt->device));
     Y2_CHECK(y2_stream_create(&rt->copy_stream));
+    Y2_CHECK(y2_stream_create(&rt->d2h_stream));
     rt->pipe[0].in_dev = rt->in_dev;
     rt->pipe[0].in_pinned = rt->in_pinned;
     Y2_CHECK(y2_malloc((void **)&rt->pipe[1].in_dev, rt->in_bytes));
     Y2_CHECK(y2_host_alloc((void **)&rt->pipe[1].in_pinned, rt->in_bytes));
     for (int s = 0; s < 2; ++s) {
         Y2_CHECK(y2_event_create(&rt->pipe[s].ev_h2d));
+        Y2_CHECK(y2_event_create(&rt->pipe[s].ev_tail));
         Y2_CHECK(y2_event_create(&rt->pipe[s].ev_done));
         rt->pipe[s].busy = 0;
     }
@@ -327,7 +329,8 @@ static void pipe_reserve_frames(y2_net_rt *rt, int s, size_t bytes)
 }
 
 /* input: fp32 planar [B][c][h][w] (u8 == 0), uint8 interleaved RGB [B][h][w][3] at the network's
- * resolution (u8 == 1), or uint8 interleaved RGB frames [B][fh][fw][3] of any size (u8 == 2) */
+ * resolution (u8 == 1), uint8 interleaved RGB frames [B][fh][fw][3] of any size (u8 == 2), or nothing: the slot's
+ * device input already holds the batch (u8 == 3, network_detect_submit_resident) */
 static int submit_common(network net, const void *input, int u8, int fw, int fh, float thresh, float nms,
                          int max_det)
 {
@@ -355,13 +358,15 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
         const size_t bytes = (size_t)B * net.h * net.w * 3;
         if (input && input != ps->in_u8_pinned) memcpy(ps->in_u8_pinned, input, bytes);
         Y2_CHECK(y2_memcpy_h2d(ps->in_u8_dev, ps->in_u8_pinned, bytes, rt->copy_stream));
-    } else {
+    } else if (u8 == 0) {
         const size_t bytes = (size_t)B * net.inputs * sizeof(float);
         if (input && input != ps->in_pinned) memcpy(ps->in_pinned, input, bytes);
         Y2_CHECK(y2_memcpy_h2d(ps->in_dev, ps->in_pinned, bytes, rt->copy_stream));
     }
-    Y2_CHECK(y2_event_record(ps->ev_h2d, rt->copy_stream));
-    Y2_CHECK(y2_stream_wait_event(rt->stream, ps->ev_h2d));
+    if (u8 != 3) {
+        Y2_CHECK(y2_event_record(ps->ev_h2d, rt->copy_stream));
+        Y2_CHECK(y2_stream_wait_event(rt->stream, ps->ev_h2d));
+    }
     if (u8 == 2) /* byte/255. + resize_image on the device, into the slot's fp32 input */
         Y2_CHECK(y2_resize_u8_to_f32(ps->frames_dev, ps->in_dev, B, fw, fh, net.w, net.h, rt->stream));
     if (u8 == 1) {
@@ -374,9 +379,13 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
         y2_run_forward_from(net, ps->in_dev, &ps->graph, &ps->graph_valid);
     }
     detect_tail(rt, l, net.layers[net.n - 2].b200, thresh, nms, ps->det_dev, ps->cnt_dev, ps->det_cap);
-    Y2_CHECK(y2_memcpy_d2h(ps->cnt_pinned, ps->cnt_dev, (size_t)B * sizeof(int), rt->stream));
-    Y2_CHECK(y2_memcpy_d2h(ps->det_pinned, ps->det_dev, (size_t)B * ps->det_cap * sizeof(y2_det), rt->stream));
-    Y2_CHECK(y2_event_record(ps->ev_done, rt->stream));
+    /* the detection lists travel on their own stream: the next batch's forward pass (same compute stream) does
+     * not wait behind the device -> host copies of this one */
+    Y2_CHECK(y2_event_record(ps->ev_tail, rt->stream));
+    Y2_CHECK(y2_stream_wait_event(rt->d2h_stream, ps->ev_tail));
+    Y2_CHECK(y2_memcpy_d2h(ps->cnt_pinned, ps->cnt_dev, (size_t)B * sizeof(int), rt->d2h_stream));
+    Y2_CHECK(y2_memcpy_d2h(ps->det_pinned, ps->det_dev, (size_t)B * ps->det_cap * sizeof(y2_det), rt->d2h_stream));
+    Y2_CHECK(y2_event_record(ps->ev_done, rt->d2h_stream));
     ps->busy = 1;
     rt->pipe_inflight++;
     return s;
@@ -390,6 +399,21 @@ int network_detect_submit(network net, const float *input, float thresh, float n
 int network_detect_submit_u8(network net, const unsigned char *input_hwc, float thresh, float nms, int max_det)
 {
     return submit_common(net, input_hwc, 1, 0, 0, thresh, nms, max_det);
+}
+
+/* The batch is already in the slot's device input (network_pipeline_input_device(net, slot), e.g. written by another
+ * kernel or uploaded once): forward + decode + NMS + pick without any host -> device copy, pipelined like the others. */
+int network_detect_submit_resident(network net, float thresh, float nms, int max_det)
+{
+    return submit_common(net, 0, 3, 0, 0, thresh, nms, max_det);
+}
+
+float *network_pipeline_input_device(network net, int slot)
+{
+    y2_net_rt *rt = y2_rt(net);
+    if (!rt || slot < 0 || slot > 1) error("network_pipeline_input_device: bad slot or unplanned network");
+    pipe_init(net);
+    return rt->pipe[slot].in_dev;
 }
 
 int network_detect_wait(network net, y2_detection *dets, int *counts, int max_det)

@@ -105,7 +105,7 @@ typedef struct y2_net_rt {
         y2_det *det_dev, *det_pinned;
         int *cnt_dev, *cnt_pinned;
         int det_cap;
-        y2_event_t ev_h2d, ev_done;
+        y2_event_t ev_h2d, ev_tail, ev_done;
         int busy;
         /* raw uint8 HWC input of the same slot (network_detect_submit_u8) */
         unsigned char *in_u8_dev, *in_u8_pinned;
@@ -115,7 +115,8 @@ typedef struct y2_net_rt {
         unsigned char *frames_dev, *frames_pinned;
         size_t frames_cap;
     } pipe[2];
-    y2_stream_t copy_stream;
+    y2_stream_t copy_stream; /* host -> device uploads of the pipeline */
+    y2_stream_t d2h_stream;  /* detection lists back to the host, under the next batch's forward pass */
     int pipe_ready, pipe_head, pipe_inflight;
     int input_u8;        /* the forward pass being issued reads uint8 HWC images (first-layer kernel only) */
     int defer_region;    /* softmax-tree region layer: its dense forward is not part of the schedule, it runs when

@@ -1485,10 +1485,13 @@ static void pipe_free(y2_net_rt *rt)
         y2_host_free(rt->pipe[s].cnt_pinned);
         if (rt->pipe[s].ev_h2d) y2_event_destroy(rt->pipe[s].ev_h2d);
         if (rt->pipe[s].ev_done) y2_event_destroy(rt->pipe[s].ev_done);
+        if (rt->pipe[s].ev_tail) y2_event_destroy(rt->pipe[s].ev_tail);
     }
     if (rt->copy_stream) y2_stream_destroy(rt->copy_stream);
+    if (rt->d2h_stream) y2_stream_destroy(rt->d2h_stream);
     memset(rt->pipe, 0, sizeof(rt->pipe));
     rt->copy_stream = 0;
+    rt->d2h_stream = 0;
     rt->pipe_ready = 0;
 }
 

@@ -149,6 +149,8 @@ def lib() -> C.CDLL:
         "network_pipeline_next_slot": (i, [Network]),
         "network_detect_submit": (i, [Network, fp, f, f, i]),
         "network_detect_wait": (i, [Network, C.POINTER(Detection), _ip, i]),
+        "network_detect_submit_resident": (i, [Network, f, f, i]),
+        "network_pipeline_input_device": (C.c_void_p, [Network, i]),
         "network_pipeline_staging_u8": (C.POINTER(C.c_ubyte), [Network, i]),
         "network_detect_submit_u8": (i, [Network, C.POINTER(C.c_ubyte), f, f, i]),
         "network_detect_batch_u8": (None, [Network, C.POINTER(C.c_ubyte), f, f, C.POINTER(Detection), _ip, i]),

@@ -189,6 +189,25 @@ def test_pipelined_submit_wait_equals_synchronous_detect(tmp_path):
     lib.network_detect_wait(net, dets, counts, max_det)
     got.append(as_list(dets, counts))
     assert got == want
+
+    # the same with the batches already resident in the slots' DEVICE inputs (network_detect_submit_resident): two
+    # different batches uploaded once, then alternated without any host -> device copy
+    from sr_object_detection_b200 import _lib
+    stream = C.c_void_p(lib.network_stream(net))
+    for slot in (0, 1):
+        C.memmove(stage[slot], batches[slot].ctypes.data, batches[slot].nbytes)
+        _lib.check(lib.y2_memcpy_h2d(lib.network_pipeline_input_device(net, slot), stage[slot], batches[slot].nbytes, stream))
+    _lib.check(lib.y2_stream_sync(stream))
+    got = []
+    assert lib.network_detect_submit_resident(net, thresh, nms, max_det) == lib.network_pipeline_next_slot(net) ^ 1
+    for i in range(1, 6):
+        lib.network_detect_submit_resident(net, thresh, nms, max_det)
+        lib.network_detect_wait(net, dets, counts, max_det)
+        got.append(as_list(dets, counts))
+    lib.network_detect_wait(net, dets, counts, max_det)
+    got.append(as_list(dets, counts))
+    first = lib.network_pipeline_next_slot(net)  # six submissions: the next slot is the one the first one used
+    assert got == [want[(first + i) & 1] for i in range(6)]
     dn.free_network(net)
 
 
