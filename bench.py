@@ -399,13 +399,9 @@ def main() -> int:
             return float(t.item())
         return ms.value
 
-    for _ in range(3):
-        step_device()
-    torch.cuda.synchronize()
-    launches_fwd = lib.network_launch_count(net)
-    ms_dev_sync = timed(step_device, args.steps)
     run_device(args.warmup)
     torch.cuda.synchronize()
+    launches_fwd = lib.network_launch_count(net)
     det_per_image = float(np.mean([min(c, MAX_DET) for c in counts]))
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -423,6 +419,9 @@ def main() -> int:
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["sampling"] = sampling
+    for _ in range(3):
+        step_device()
+    ms_dev_sync = timed(step_device, args.steps)
 
     # the same pipeline fed with raw uint8 RGB images (what an image decoder hands over): a quarter of the upload
     u8_images = np.random.default_rng(SEED_X + lo).integers(0, 256, size=(B, SIDE, SIDE, 3), dtype=np.uint8)

@@ -354,7 +354,7 @@ static int submit_common(network net, const void *input, int u8, int fw, int fh,
         pipe_reserve_frames(rt, s, bytes);
         if (input && input != ps->frames_pinned) memcpy(ps->frames_pinned, input, bytes);
         Y2_CHECK(y2_memcpy_h2d(ps->frames_dev, ps->frames_pinned, bytes, rt->copy_stream));
-    } else if (u8) {
+    } else if (u8 == 1) {
         const size_t bytes = (size_t)B * net.h * net.w * 3;
         if (input && input != ps->in_u8_pinned) memcpy(ps->in_u8_pinned, input, bytes);
         Y2_CHECK(y2_memcpy_h2d(ps->in_u8_dev, ps->in_u8_pinned, bytes, rt->copy_stream));
