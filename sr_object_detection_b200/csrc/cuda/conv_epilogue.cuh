@@ -98,7 +98,10 @@ __device__ __forceinline__ void slab_store_f32_staged(const SlabParams &prm, uin
         if (fr >= 0 && ch < prm.cout) {
             float *o = out + fr * prm.out_cs + ch;
             if (ch + 4 <= prm.cout) {
-                *reinterpret_cast<uint4 *>(o) = q;
+                // streaming store: 2 GB of head output per yolo9000 step must not push the 58 MB weight matrix (read
+                // again for every position tile) out of the L2
+                if (prm.dbg & 16) *reinterpret_cast<uint4 *>(o) = q;
+                else __stcs(reinterpret_cast<uint4 *>(o), q);
             } else {  // the last filters of a head whose count is not a multiple of 4
                 o[0] = __uint_as_float(q.x);
                 if (ch + 1 < prm.cout) o[1] = __uint_as_float(q.y);

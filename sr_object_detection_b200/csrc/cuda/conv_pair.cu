@@ -320,7 +320,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tc_fence_before();
                     mbar_arrive_cluster(&tempty_bar[buf], 0);
                 }
-                if (prm.tma_store) {  // bf16 tensor: staged, one TMA store per warp and 64 channels
+                if (prm.tma_store == 2) {  // fp32 flat head: staged, row-contiguous 16-byte stores
+                    const long long fr = valid ? ((long long)b * prm.h + y) * prm.w + x : -1ll;
+                    uint4 *st = s_stage + (warp - 3) * 256;
+                    if (prm.act == Y2_ACT_LINEAR) {
+                        slab_store_f32_staged<Y2_ACT_LINEAR>(prm, st, v0, sab, c, n0, fr, lane);
+                        slab_store_f32_staged<Y2_ACT_LINEAR>(prm, st, v1, sab, c + 32, n0, fr, lane);
+                    } else if (prm.act == Y2_ACT_LEAKY) {
+                        slab_store_f32_staged<Y2_ACT_LEAKY>(prm, st, v0, sab, c, n0, fr, lane);
+                        slab_store_f32_staged<Y2_ACT_LEAKY>(prm, st, v1, sab, c + 32, n0, fr, lane);
+                    } else {
+                        slab_store_f32_staged<Y2_ACT_LOGISTIC>(prm, st, v0, sab, c, n0, fr, lane);
+                        slab_store_f32_staged<Y2_ACT_LOGISTIC>(prm, st, v1, sab, c + 32, n0, fr, lane);
+                    }
+                } else if (prm.tma_store) {  // bf16 tensor: staged, one TMA store per warp and 64 channels
                     uint4 w[8];
                     if (prm.act == Y2_ACT_LEAKY) {
                         slab_affine_pack<Y2_ACT_LEAKY>(v0, sab, c, valid, w);
@@ -346,7 +359,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (has_next) s_ab[(buf ^ 1) * kPairN + et] = ab_next;
         }
-        if (prm.tma_store && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
+        if (prm.tma_store == 1 && lane == 0) tma_store_wait_all();  // the copies read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -475,9 +488,12 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const int taps = d->ksize * d->ksize;
     const int hp = d->h + 1, wp = d->w + 1;
     const long long total = (long long)d->batch * hp * wp;
-    // 1x1 layers: only bf16 tensors through the TMA-store epilogue, and only when there is enough work to
-    // fill the pairs (small layers stay on the single-CTA kernels, which have more CTAs to spread over)
-    if (taps == 1 && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;
+    // wide fp32 heads (yolo9000: 28 269 filters over 1024 channels, a third of that network's step): one-tap form
+    // with the staged row-contiguous fp32 stores of conv_epilogue.cuh
+    const bool f32_head = taps == 1 && d->out_mode == Y2_OUT_F32_FLAT && d->cout >= 1024 && d->out_cs % 4 == 0 &&
+                          ((uintptr_t)d->out & 15) == 0 && !getenv("Y2_SLAB_NO_F32_STAGE") && !getenv("Y2_PAIR_NO_F32_HEAD");
+    // other 1x1 layers: only bf16 tensors through the TMA-store epilogue
+    if (taps == 1 && !f32_head && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;
     // 1x1 layers: the one-tap form of this kernel measured 21.0 us (L19, 1024 -> 512) against 20.1 of the slab kernel,
     // so it is only used when asked for (Y2_CONV_VARIANT=pair; tests).  Y2_PAIR_RESIDENT=1 additionally keeps the CTA's
     // half of the WHOLE weight matrix in shared memory when it fits next to two activation stages (npad * cin <= 8
@@ -489,7 +505,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const bool forced_pair = forced && !strcmp(forced, "pair");
     const char *res_env = getenv("Y2_PAIR_RESIDENT");
     const bool resident = taps == 1 && resident_stages <= 8 && res_env && atoi(res_env) != 0;
-    if (taps == 1 && !forced_pair && !(resident && total >= 2ll * 256 * (sm_count() / 2))) return Y2_EINVAL;
+    if (taps == 1 && !forced_pair && !f32_head && !(resident && total >= 2ll * 256 * (sm_count() / 2))) return Y2_EINVAL;
     const int halo = taps == 9 ? wp + 1 : 0;
     const int slab_rows = 128 + 2 * halo;
     const int loads = (slab_rows + 255) / 256;
@@ -549,6 +565,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
         if (rc != Y2_OK) return rc;
         p.tma_store = 1;
     }
+    if (f32_head) p.tma_store = 2;
     p.alpha = d->alpha;
     p.beta = d->beta;
     p.out = d->out;

@@ -136,6 +136,34 @@ def test_conv_f32_flat_head_125(conv_variant):
     assert err <= 1e-4, f"max err / max|ref| = {err:.3e}"
 
 
+@pytest.mark.parametrize("cout,batch,hw", [(1101, 3, 17), (2050, 9, 13)])
+def test_conv_f32_flat_wide_head(conv_variant, cout, batch, hw):
+    """Wide 1x1 linear head written as fp32 [B][H*W][cs] with staged row-contiguous stores (yolo9000's 28 269-filter
+    head in small): filter counts that are not multiples of 4 / 64 / 256, row stride padded to 4 floats, the
+    one-tap CTA-pair kernel by default and the slab / per-tap kernels under their variants."""
+    dev = torch.device("cuda:0")
+    cin, h, w = 128, hw, hw
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.rand(batch, cin, h, w, generator=g).to(dev) * 2 - 1
+    wt = (torch.rand(cout, cin, 1, 1, generator=g).to(dev) * 2 - 1) * (2.0 / cin) ** 0.5
+    npad = (cout + 255) // 256 * 256
+    cs = (cout + 3) // 4 * 4
+    alpha = torch.ones(npad, device=dev)
+    beta = torch.zeros(npad, device=dev)
+    alpha[:cout] = torch.rand(cout, generator=g).to(dev) + 0.5
+    beta[:cout] = torch.rand(cout, generator=g).to(dev) - 0.5
+    x_p = G.to_padded_nhwc(x)
+    wt_p = G.pack_weights(wt, cin, npad)
+    out = torch.full((batch, h * w, cs), 7.0, dtype=torch.float32, device=dev)
+    G.run_conv(x_p, cin, cin, batch, h, w, 1, wt_p, cout, npad, 256, 64, alpha, beta, ACT_LINEAR, out, cs, OUT_F32)
+    ref = _ref_conv(x, wt, alpha[:cout], beta[:cout], ACT_LINEAR, 1)
+    got = out[:, :, :cout].view(batch, h, w, cout).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 1e-4, f"max err / max|ref| = {err:.3e}"
+    if cs > cout:  # the row padding is nobody's to write
+        assert (out[:, :, cout:] == 7.0).all()
+
+
 def test_conv_channel_slice_in_concat_buffer(conv_variant):
     """Output written at a channel offset of a wider buffer (in-place route) and input read
     from a channel slice; neighbouring channels must be untouched."""
