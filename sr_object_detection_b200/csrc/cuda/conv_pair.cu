@@ -31,6 +31,11 @@
 // are bit-identical to whole tiles, nothing is parked or joined (the stream-K schedule this replaces needed fp32
 // partial sums in global scratch and lost at the power cap).  Y2_PAIR_BALANCE=0 restores whole
 // tiles round-robin (same kernel, different list).
+//
+// One-tap form (TAPS = 1, 1x1 layers).  Used by default only for wide fp32 heads (yolo9000's 28 269 filters over 1024
+// channels: 1263 -> 985 us at batch 64 against the single-CTA slab kernel, whose 128 x 256 MMAs are operand-fetch
+// bound); for the bf16 1x1 layers of the detectors it measured no faster than the slab kernel and is opt-in
+// (pair_plan_init).
 #include "conv_epilogue.cuh"
 
 #include <stdlib.h>
