@@ -495,7 +495,7 @@ int pair_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     const long long total = (long long)d->batch * hp * wp;
     // wide fp32 heads (yolo9000: 28 269 filters over 1024 channels, a third of that network's step): one-tap form
     // with the staged row-contiguous fp32 stores of conv_epilogue.cuh
-    const bool f32_head = taps == 1 && d->out_mode == Y2_OUT_F32_FLAT && d->cout >= 1024 && d->out_cs % 4 == 0 &&
+    const bool f32_head = taps == 1 && d->out_mode == Y2_OUT_F32_FLAT && d->cout >= 512 && d->out_cs % 4 == 0 &&
                           ((uintptr_t)d->out & 15) == 0 && !getenv("Y2_SLAB_NO_F32_STAGE") && !getenv("Y2_PAIR_NO_F32_HEAD");
     // other 1x1 layers: only bf16 tensors through the TMA-store epilogue
     if (taps == 1 && !f32_head && (d->out_mode != Y2_OUT_BF16_PADDED || d->cout % 64)) return Y2_EINVAL;

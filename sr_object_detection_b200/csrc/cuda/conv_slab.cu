@@ -440,8 +440,8 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
         if (rc != Y2_OK) return rc;
         p.tma_store = 1;
     }
-    // wide fp32 heads (>= 1024 filters, 16-byte aligned rows): staged row-contiguous stores (conv_epilogue.cuh)
-    const bool f32_staged = d->out_mode == Y2_OUT_F32_FLAT && bn == 256 && d->cout >= 1024 && d->out_cs % 4 == 0 &&
+    // wide fp32 heads (>= 512 filters, 16-byte aligned rows): staged row-contiguous stores (conv_epilogue.cuh)
+    const bool f32_staged = d->out_mode == Y2_OUT_F32_FLAT && bn == 256 && d->cout >= 512 && d->out_cs % 4 == 0 &&
                             ((uintptr_t)d->out & 15) == 0 && !getenv("Y2_SLAB_NO_F32_STAGE");
     if (f32_staged) p.tma_store = 2;
     p.cblocks = d->cin / bk;
