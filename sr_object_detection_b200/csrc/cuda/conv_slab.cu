@@ -440,8 +440,9 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
         if (rc != Y2_OK) return rc;
         p.tma_store = 1;
     }
-    // wide fp32 heads (>= 512 filters, 16-byte aligned rows): staged row-contiguous stores (conv_epilogue.cuh)
-    const bool f32_staged = d->out_mode == Y2_OUT_F32_FLAT && bn == 256 && d->cout >= 512 && d->out_cs % 4 == 0 &&
+    // fp32 heads with 16-byte aligned rows: staged row-contiguous stores (conv_epilogue.cuh) instead of 32 scalar
+    // stores per lane and chunk
+    const bool f32_staged = d->out_mode == Y2_OUT_F32_FLAT && bn >= 128 && d->out_cs % 4 == 0 &&
                             ((uintptr_t)d->out & 15) == 0 && !getenv("Y2_SLAB_NO_F32_STAGE");
     if (f32_staged) p.tma_store = 2;
     p.cblocks = d->cin / bk;
@@ -487,7 +488,7 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // 1x1 layers: the 256-position tiles pay off only while every SM still gets two or more of them and
     // the output is the bf16 tensor (measured on B200: L5/L9/L13 +5..15%, the 13x13 layers and the fp32
     // head are faster on the per-tap kernel's 128-position tiles)
-    if (taps == 1 && (tiles < 2 * sms || (d->out_mode != Y2_OUT_BF16_PADDED && !f32_staged)) && !getenv("Y2_CONV_VARIANT"))
+    if (taps == 1 && !f32_staged && (tiles < 2 * sms || d->out_mode != Y2_OUT_BF16_PADDED) && !getenv("Y2_CONV_VARIANT"))
         return Y2_EINVAL;
     pl->grid = tiles < sms ? tiles : sms;
     pl->taps = taps;

@@ -1077,8 +1077,8 @@ void y2_plan_network(network *net)
             r->out_cs = r->cpad;
         } else if (r->out_kind == Y2_KIND_F32_FLAT) {
             const int oh = l->type == REGION ? l->h : l->out_h, ow = l->type == REGION ? l->w : l->out_w;
-            /* wide conv heads: rows padded to 16 bytes so that the epilogue can store them with 16-byte accesses */
-            r->out_cs = (l->type == CONVOLUTIONAL && r->cpad >= 512) ? round_up(r->cpad, 4) : r->cpad;
+            /* conv heads: rows padded to 16 bytes so that the epilogue can store them with 16-byte accesses */
+            r->out_cs = (l->type == CONVOLUTIONAL) ? round_up(r->cpad, 4) : r->cpad;
             r->own_bytes = (size_t)B * oh * ow * r->out_cs * sizeof(float);
         } else {
             r->own_bytes = (size_t)B * r->cpad * sizeof(float);
