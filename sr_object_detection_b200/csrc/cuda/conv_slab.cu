@@ -488,7 +488,9 @@ int slab_plan_init(y2_conv_plan *pl, const y2_conv_desc *d)
     // 1x1 layers: the 256-position tiles pay off only while every SM still gets two or more of them and
     // the output is the bf16 tensor (measured on B200: L5/L9/L13 +5..15%, the 13x13 layers and the fp32
     // head are faster on the per-tap kernel's 128-position tiles)
-    if (taps == 1 && !f32_staged && (tiles < 2 * sms || d->out_mode != Y2_OUT_BF16_PADDED) && !getenv("Y2_CONV_VARIANT"))
+    int min_tiles = 2 * sms;
+    if (const char *e = getenv("Y2_SLAB_1X1_MIN_TILES")) min_tiles = atoi(e);
+    if (taps == 1 && !f32_staged && (tiles < min_tiles || d->out_mode != Y2_OUT_BF16_PADDED) && !getenv("Y2_CONV_VARIANT"))
         return Y2_EINVAL;
     pl->grid = tiles < sms ? tiles : sms;
     pl->taps = taps;
