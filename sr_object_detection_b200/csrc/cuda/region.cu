@@ -804,7 +804,17 @@ __global__ void avgpool_flat_kernel(const float *__restrict__ in, float *__restr
         const int b = (int)(t / c);
         const float *p = in + (size_t)b * hw * cs + ch;
         float s = 0.f;
-        for (int i = 0; i < hw; ++i) s += p[(size_t)i * cs];
+        int i = 0;
+        // sixteen loads in flight per thread, summed in the reference's order (the additions are one dependent chain
+        // either way; issued one at a time each of them waited for its own load)
+        for (; i + 16 <= hw; i += 16) {
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = __ldg(p + (size_t)(i + q) * cs);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) s += v[q];
+        }
+        for (; i < hw; ++i) s += __ldg(p + (size_t)i * cs);
         out[t] = s / hw;
     }
 }
@@ -842,6 +852,60 @@ __global__ void softmax_rows_kernel(const float *__restrict__ in, float *__restr
             for (int j = 0; j < cnt; ++j) sum = sum + __shfl_sync(0xffffffffu, e, j);
         }
         for (int i = lane; i < n; i += 32) oi[i] = oi[i] / sum;
+    }
+}
+
+// The same with a BLOCK per row, for wide rows (the 1000-way classifiers): the exps - double precision, the bulk of
+// the work - are spread over 256 threads and parked in shared memory, ONE thread then adds them in index order (the
+// reference's serial float sum: a dependent chain of n additions either way, but 4 clk each from shared memory
+// instead of a shuffle per term), everybody divides.  n <= 4096.
+__global__ void softmax_rows_block_kernel(const float *__restrict__ in, float *__restrict__ out, int rows, int n,
+                                          float temp)
+{
+    __shared__ float s_e[4096];
+    __shared__ float s_red[8];
+    __shared__ float s_sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float *xi = in + (size_t)r * n;
+        float *oi = out + (size_t)r * n;
+        float largest = -FLT_MAX;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float v = xi[i];
+            if (v > largest) largest = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, largest, d);
+            if (other > largest) largest = other;
+        }
+        if (lane == 0) s_red[warp] = largest;
+        __syncthreads();
+        largest = s_red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_red[w] > largest) largest = s_red[w];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float arg = xi[i] / temp - largest / temp;
+            s_e[i] = (float)exp((double)arg);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float sum = 0.f;
+            int i = 0;
+            for (; i + 8 <= n; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = s_e[i + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sum = sum + v[q];
+            }
+            for (; i < n; ++i) sum = sum + s_e[i];
+            s_sum = sum;
+        }
+        __syncthreads();
+        const float sum = s_sum;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) oi[i] = s_e[i] / sum;
+        __syncthreads();  // s_e / s_red are reused by the next row
     }
 }
 
@@ -1081,6 +1145,12 @@ extern "C" int y2_avgpool_flat(const float *in, float *out, int batch, int hw, i
 extern "C" int y2_softmax_rows(const float *in, float *out, int rows, int n, float temp, y2_stream_t s)
 {
     if (!in || !out) return Y2_EINVAL;
+    if (n >= 256 && n <= 4096 && rows <= 8 * sm_count() && !getenv("Y2_SOFTMAX_WARP_ROWS")) {
+        // few wide rows: a warp per row leaves the device empty (64 rows = 64 warps)
+        softmax_rows_block_kernel<<<rows, 256, 0, to_stream(s)>>>(in, out, rows, n, temp);
+        Y2_LAUNCH_CHECK();
+        return Y2_OK;
+    }
     softmax_rows_kernel<<<grid_cap(((long long)rows * 32 + 255) / 256, 8), 256, 0, to_stream(s)>>>(in, out, rows,
                                                                                                    n, temp);
     Y2_LAUNCH_CHECK();

@@ -692,3 +692,40 @@ def test_shortcut_matches_reference(case, monkeypatch):
         if out32:
             assert torch.equal(o32[:, :oh, :ow, :].permute(0, 3, 1, 2), ref)
             assert o32[:, oh].abs().max().item() == 0 and o32[:, :, ow].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rows,n", [(64, 1000), (3, 257), (5, 4096), (2, 100)])
+def test_softmax_rows_bit_exact_in_both_forms(rows, n, monkeypatch):
+    """softmax_layer.c:49-61 -> blas.c:205-221: exp in double rounded to float, float sum in index order, divide.
+    The block-per-row kernel (wide rows) and the warp-per-row kernel must both reproduce that sequence bit for bit."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(rows, n, generator=g) * 3).contiguous()
+    xn = x.numpy()
+    largest = xn.max(axis=1, keepdims=True)
+    e = np.exp((xn / np.float32(1.0) - largest / np.float32(1.0)).astype(np.float64)).astype(np.float32)
+    s = np.cumsum(e, axis=1, dtype=np.float32)[:, -1:]   # sequential float accumulation
+    ref = e / s
+    xd = x.to(dev)
+    for force_warp in (False, True):
+        if force_warp:
+            monkeypatch.setenv("Y2_SOFTMAX_WARP_ROWS", "1")
+        out = torch.zeros(rows, n, device=dev)
+        _lib.check(lib.y2_softmax_rows(xd.data_ptr(), out.data_ptr(), rows, n, 1.0, _stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32)), f"warp form: {force_warp}"
+
+
+def test_avgpool_flat_sequential_sum():
+    """avgpool_layer.c:40-55: per (image, channel) a sequential float sum over h*w, then / (h*w)."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    batch, hw, c, cs = 3, 196, 1000, 1000
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x = torch.randn(batch, hw, cs, generator=g).contiguous()
+    ref = (np.cumsum(x.numpy()[:, :, :c], axis=1, dtype=np.float32)[:, -1, :] / np.float32(hw)).astype(np.float32)
+    out = torch.zeros(batch, c, device=dev)
+    _lib.check(lib.y2_avgpool_flat(x.to(dev).data_ptr(), out.data_ptr(), batch, hw, c, cs, _stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
