@@ -243,12 +243,18 @@ __global__ void gather_patches_bf16_kernel(const __nv_bfloat16 *__restrict__ in,
     for (int rowi = blockIdx.x; rowi < rows; rowi += gridDim.x) {
         const int b = rowi / ohp, oy = rowi - b * ohp;
         __nv_bfloat16 *drow = dst + (size_t)rowi * owp * per_pos * 8;
-        for (int t = threadIdx.x; t < per_row; t += blockDim.x) {
-            const int ox = t / per_pos, rem = t - ox * per_pos;
-            const int tap = rem / c8, g = rem - tap * c8;
+        // (ox, tap, g) advance by a constant stride: carried instead of divided per 16-byte element
+        const int bd = (int)blockDim.x;
+        const int d_ox = bd / per_pos, d_tap = (bd - d_ox * per_pos) / c8, d_g = bd - d_ox * per_pos - d_tap * c8;
+        const unsigned inv_k = (65536u + (unsigned)ksize - 1u) / (unsigned)ksize;  // tap / ksize for tap < 256
+        int ox = (int)threadIdx.x / per_pos, tap = ((int)threadIdx.x - ox * per_pos) / c8,
+            g = (int)threadIdx.x - ox * per_pos - tap * c8;
+        for (int t = threadIdx.x; t < per_row; t += bd, g += d_g, tap += d_tap, ox += d_ox) {
+            if (g >= c8) { g -= c8; ++tap; }
+            if (tap >= kk) { tap -= kk; ++ox; }
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (ox < ow && oy < oh) {
-                const int ty = tap / ksize;
+                const int ty = (int)(((unsigned)tap * inv_k) >> 16);
                 const int yy = oy * stride + ty - pad, xx = ox * stride + (tap - ty * ksize) - pad;
                 if (yy >= 0 && yy < h && xx >= 0 && xx < w)
                     v = __ldg(reinterpret_cast<const uint4 *>(in + (((size_t)b * hp + yy) * wp + xx) * in_cs + g * 8));
