@@ -60,6 +60,8 @@ CONV_CASES = [
     (64, 256, 13, 13, 512, 3, 256, 64, ACT_LEAKY),
     (64, 128, 13, 13, 1024, 3, 256, 64, ACT_LINEAR),
     (48, 192, 13, 13, 768, 3, 256, 64, ACT_LEAKY),
+    # balanced pieces with a filter count that is not a multiple of 64: direct (non-TMA) stores, clipped last piece
+    (64, 128, 13, 13, 456, 3, 256, 64, ACT_LEAKY),
     # wide 1x1 layers (yolo-voc L13, L19): slab kernel by default, one-tap pair kernel under the "pair" variant
     (64, 512, 26, 26, 256, 1, 256, 64, ACT_LEAKY),
     (64, 1024, 13, 13, 512, 1, 256, 64, ACT_LEAKY),
@@ -136,7 +138,7 @@ def test_conv_f32_flat_head_125(conv_variant):
     assert err <= 1e-4, f"max err / max|ref| = {err:.3e}"
 
 
-@pytest.mark.parametrize("cout,batch,hw", [(1101, 3, 17), (2050, 9, 13)])
+@pytest.mark.parametrize("cout,batch,hw", [(1101, 3, 17), (2050, 9, 13), (1101, 64, 13)])
 def test_conv_f32_flat_wide_head(conv_variant, cout, batch, hw):
     """Wide 1x1 linear head written as fp32 [B][H*W][cs] with staged row-contiguous stores (yolo9000's 28 269-filter
     head in small): filter counts that are not multiples of 4 / 64 / 256, row stride padded to 4 floats, the
