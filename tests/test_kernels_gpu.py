@@ -101,7 +101,7 @@ def test_conv_bf16_matches_fp32_reference(case, conv_variant):
     x_p = G.to_padded_nhwc(x)
     wt_p = G.pack_weights(wt, cin, npad)
     out = torch.full((batch, h + 1, w + 1, cout), 7.0, dtype=torch.bfloat16, device=dev)
-    # three launches of the same plan: scratch flags of the stream-K schedule must come back clean
+    # three launches of the same plan: nothing a launch leaves behind (work lists, barriers) may change the next one
     G.run_conv(x_p, cin, cin, batch, h, w, ksize, wt_p, cout, npad, block_n, block_k, alpha, beta, act,
                out, cout, OUT_BF16, repeat=3)
     got = G.from_padded_nhwc(out, cout, h, w)

@@ -343,7 +343,7 @@ def test_networks_at_serving_batches(tmp_path, name, side, batch):
     """Whole networks at batch sizes where every CTA walks many tiles (the parity tests above use batches the
     CPU reference finishes in seconds): must complete - an epilogue race in the conv+pool kernel once hung
     tiny-yolo-voc at batch 64 - and EVERY image's output must equal what the batch-1 network computes for that
-    image up to bf16 roundings (kernel variant, stream-K split and tile order change with the batch; against the
+    image up to bf16 roundings (kernel variant, work distribution and tile order change with the batch; against the
     reference itself these batch sizes are checked in test_baseline_batches_gpu.py)."""
     text1 = synth.CFGS[name](batch=1, w=side, h=side)
     textb = synth.CFGS[name](batch=batch, w=side, h=side)

@@ -4,7 +4,7 @@
 For every (cfg, side, batch): parse, load seeded weights, network_predict on seeded images, then check that
 the output is finite and that image 0's row equals (to 5e-3 of the row maximum) the row a batch-1 network
 produces for the same image - kernels pick different tilings, schedules and tile orders per batch size; the
-result per image may only move by bf16 roundings (a stream-K split sums the same products in another order).  Also runs the batched detect call.  Prints one line per case."""
+result per image may only move by bf16 roundings (another kernel variant may sum the same products in another order).  Also runs the batched detect call.  Prints one line per case."""
 import sys
 import tempfile
 import time
