@@ -188,7 +188,8 @@ void forward_network_gpu(network net, network_state state);        /* network_ke
 float *get_network_output(network net);                            /* network.c:173-181 */
 float *get_network_output_gpu(network net);                        /* network_kernels.cu:378-390 */
 float *get_network_output_layer(network net, int i);               /* network.c:466 */
-float *get_network_output_gpu_layer(network net, int i);
+float *get_network_output_gpu_layer(network net, int i);          /* the name network.h:84 declares ... */
+float *get_network_output_layer_gpu(network net, int i);          /* ... and the one network_kernels.cu:378 defines */
 int get_network_output_size(network net);                          /* network.c:167-171 */
 int get_network_output_size_layer(network net, int i);
 int get_network_input_size(network net);

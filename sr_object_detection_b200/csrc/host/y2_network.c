@@ -1677,6 +1677,12 @@ float *get_network_output_gpu_layer(network net, int i)
     return export_layer(net, i);
 }
 
+/* the reference's header and definition disagree on the name (network.h:84 vs network_kernels.cu:378): both exist */
+float *get_network_output_layer_gpu(network net, int i)
+{
+    return export_layer(net, i);
+}
+
 float *get_network_output_layer(network net, int i)
 {
     if (net.b200) return export_layer(net, i);
