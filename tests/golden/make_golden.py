@@ -337,5 +337,71 @@ def classifier_front():
         np.savez_compressed(OUT / "classifier_front.npz", **out)
 
 
+def voc_eval_golden():
+    """scripts/voc_eval.py of the reference (a Python 2 file) run on a synthetic VOC-style data set: annotations with
+    difficult objects, detections with duplicates, misses, ties and images without objects.  The script's text is
+    read where it lies, made importable under Python 3 / numpy 2 in memory (print statements, cPickle, np.bool, pickle
+    file modes - nothing else) and executed; the fixture holds the inputs and the (recall, precision, AP) it
+    returned, for tools/voc_eval.py to reproduce (tests/test_voc_eval.py)."""
+    import re
+    src = Path("/root/reference/scripts/voc_eval.py").read_text()
+    src = src.replace("import cPickle", "import pickle as cPickle")
+    src = re.sub(r"print '([^']*)'\.format\(\s*([^)]*)\)", r"print('\1'.format(\2))", src, flags=re.S)
+    src = src.replace("np.bool", "bool").replace("open(cachefile, 'w')", "open(cachefile, 'wb')")
+    src = src.replace("open(cachefile, 'r')", "open(cachefile, 'rb')")
+    ns = {}
+    exec(compile(src, "reference scripts/voc_eval.py", "exec"), ns)
+    rng = np.random.default_rng(2024)
+    classes = ["cat", "dog", "car"]
+    images = ["%06d" % i for i in range(40)]
+    truth = {}
+    for im in images:
+        objs = []
+        for _ in range(int(rng.integers(0, 5))):
+            x0, y0 = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+            w, h = int(rng.integers(20, 180)), int(rng.integers(20, 150))
+            objs.append({"name": classes[int(rng.integers(0, 3))], "difficult": int(rng.random() < 0.2),
+                         "bbox": [x0, y0, x0 + w, y0 + h]})
+        truth[im] = objs
+    dets = {c: [] for c in classes}
+    for im in images:
+        for o in truth[im]:
+            if rng.random() < 0.8:   # a hit, sometimes twice (duplicate), sometimes badly localised
+                for _ in range(1 + int(rng.random() < 0.25)):
+                    j = rng.normal(0, 12 if rng.random() < 0.7 else 60, 4)
+                    b = [o["bbox"][k] + j[k] for k in range(4)]
+                    dets[o["name"]].append((im, round(float(rng.random()), 2 if rng.random() < 0.3 else 6), *b))
+        for _ in range(int(rng.integers(0, 3))):  # false alarms
+            x0, y0 = rng.uniform(1, 300), rng.uniform(1, 200)
+            dets[classes[int(rng.integers(0, 3))]].append((im, float(rng.random()) * 0.6, x0, y0, x0 + rng.uniform(10, 150),
+                                                           y0 + rng.uniform(10, 150)))
+    out = {"classes": classes, "images": images, "truth": truth, "detections": {}, "results": {}}
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        (t / "ann").mkdir()
+        for im in images:
+            xml = "<annotation>" + "".join(
+                "<object><name>%s</name><difficult>%d</difficult><bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax>"
+                "<ymax>%d</ymax></bndbox></object>" % (o["name"], o["difficult"], *o["bbox"]) for o in truth[im]) + "</annotation>"
+            (t / "ann" / f"{im}.xml").write_text(xml)
+        (t / "set.txt").write_text("\n".join(images) + "\n")
+        for c in classes:
+            lines = ["%s %f %f %f %f %f" % d for d in dets[c]]   # the format print_detector_detections writes
+            (t / f"det_{c}.txt").write_text("\n".join(lines) + "\n")
+            out["detections"][c] = lines
+            for voc07 in (False, True):
+                for ov in (0.5, 0.7):
+                    cache = t / f"cache_{c}_{voc07}_{ov}"
+                    rec, prec, ap = ns["voc_eval"](str(t / "det_{}.txt"), str(t / "ann" / "{}.xml"), str(t / "set.txt"), c,
+                                                   str(cache), ov, voc07)
+                    out["results"][f"{c}|{int(voc07)}|{ov}"] = {"rec": [float(v) for v in rec],
+                                                               "prec": [float(v) for v in prec], "ap": float(ap)}
+    (OUT / "voc_eval_ref.json").write_text(json.dumps(out))
+    print("voc_eval_ref.json:", {k: round(v["ap"], 4) for k, v in out["results"].items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "voc_eval":
+        voc_eval_golden()
+    else:
+        main()
