@@ -277,6 +277,14 @@ float box_union(box a, box b);
 
 /* ---- detector.c:202-369: validation result writers (VOC per-class files, COCO json, ImageNet-detection) --- */
 void validate_detector(char *datacfg, char *cfgfile, char *weightfile);            /* detector.c:244-369 */
+void validate_detector_recall(char *datacfg, char *cfgfile, char *weightfile);     /* detector.c:371-450 */
+typedef struct {                                                                   /* data.h:69-73 */
+    int id;
+    float x, y, w, h;
+    float left, right, top, bottom;
+} box_label;
+box_label *read_boxes(char *filename, int *n);                                     /* data.c:135-159 */
+void find_replace(char *str, char *orig, char *rep, char *output);                 /* utils.c:158-172 */
 void print_detector_detections(FILE **fps, char *id, box *boxes, float **probs, int total, int classes, int w,
                                int h);                                             /* detector.c:202-221 */
 void print_imagenet_detections(FILE *fp, int id, box *boxes, float **probs, int total, int classes, int w,

@@ -265,3 +265,139 @@ void validate_detector(char *datacfg, char *cfgfile, char *weightfile)
     free(paths);
     free_network(net);
 }
+
+/* ---- validate_detector_recall (detector.c:371-450): proposals, mean best IoU and recall against label files ------ */
+
+/* utils.c:158-172: the FIRST occurrence of `orig` in `str` replaced by `rep`; `output` may be `str` itself */
+void find_replace(char *str, char *orig, char *rep, char *output)
+{
+    char copy[4096];
+    snprintf(copy, sizeof(copy), "%s", str);
+    char *hit = strstr(copy, orig);
+    if (!hit) {
+        snprintf(output, 4096, "%s", copy);
+        return;
+    }
+    *hit = 0;
+    snprintf(output, 4096, "%s%s%s", copy, rep, hit + strlen(orig));
+}
+
+/* data.c:135-159: "id x y w h" records until the first line that does not parse */
+box_label *read_boxes(char *filename, int *n)
+{
+    FILE *file = fopen(filename, "r");
+    if (!file) file_error(filename);
+    int count = 0, cap = 0, id;
+    float x, y, w, h;
+    box_label *out = (box_label *)calloc(1, sizeof(box_label));
+    while (fscanf(file, "%d %f %f %f %f", &id, &x, &y, &w, &h) == 5) {
+        if (count == cap) {
+            cap = cap ? 2 * cap : 8;
+            out = (box_label *)realloc(out, (size_t)cap * sizeof(box_label));
+        }
+        box_label b;
+        b.id = id;
+        b.x = x; b.y = y; b.w = w; b.h = h;
+        b.left = x - w / 2;
+        b.right = x + w / 2;
+        b.top = y - h / 2;
+        b.bottom = y + h / 2;
+        out[count++] = b;
+    }
+    fclose(file);
+    *n = count;
+    return out;
+}
+
+/* the label file that belongs to an image (detector.c:413-418) */
+static void label_path_of(char *image_path, char *out)
+{
+    find_replace(image_path, "images", "labels", out);
+    find_replace(out, "JPEGImages", "labels", out);
+    find_replace(out, ".jpg", ".txt", out);
+    find_replace(out, ".JPEG", ".txt", out);
+    find_replace(out, ".png", ".txt", out);
+}
+
+/* Objectness proposals of every image (get_region_boxes with only_objectness, do_nms over that one column at .4)
+ * against the ground-truth boxes of its label file: running proposal count, sum of the best IoU per truth box and
+ * the number of truth boxes matched above .5, one stderr line per image in the reference's format.  As in
+ * validate_detector a chunk of images shares one forward pass; the decode runs per image through the caller-facing
+ * calls, so the lines are identical whenever the network outputs are. */
+void validate_detector_recall(char *datacfg, char *cfgfile, char *weightfile)
+{
+    network net = parse_network_cfg(cfgfile);
+    if (weightfile) load_weights(&net, weightfile);
+    int chunk = 16;
+    if (getenv("Y2_VALID_BATCH")) chunk = atoi(getenv("Y2_VALID_BATCH"));
+    if (chunk < 1) chunk = 1;
+    set_batch_network(&net, chunk);
+    fprintf(stderr, "Learning Rate: %g, Momentum: %g, Decay: %g\n", net.learning_rate, net.momentum, net.decay);
+
+    list *options = read_data_cfg(datacfg);
+    list *plist = get_paths(option_find_str(options, "valid", "data/train.txt"));
+    char **paths = (char **)list_to_array(plist);
+    layer l = net.layers[net.n - 1];
+    if (l.type != REGION) error("validate_detector_recall: the last layer is not a region layer");
+    const int nboxes = l.w * l.h * l.n;
+    box *boxes = (box *)calloc(nboxes, sizeof(box));
+    float **probs = (float **)calloc(nboxes, sizeof(float *));
+    for (int j = 0; j < nboxes; ++j) probs[j] = (float *)calloc(l.classes, sizeof(float));
+
+    const float thresh = .2, iou_thresh = .5, nms = .4;
+    int total = 0, correct = 0, proposals = 0;
+    float avg_iou = 0;
+    const int m = plist->size;
+    const size_t per_image = (size_t)net.w * net.h * net.c;
+    float *X = (float *)calloc((size_t)chunk * per_image, sizeof(float));
+    for (int i0 = 0; i0 < m; i0 += chunk) {
+        const int n = m - i0 < chunk ? m - i0 : chunk;
+        memset(X, 0, (size_t)chunk * per_image * sizeof(float));
+        for (int t = 0; t < n; ++t) {
+            image orig = load_image_color(paths[i0 + t], 0, 0);
+            image sized = resize_image(orig, net.w, net.h);
+            memcpy(X + (size_t)t * per_image, sized.data, per_image * sizeof(float));
+            free_image(orig);
+            free_image(sized);
+        }
+        network_predict(net, X);
+        l = net.layers[net.n - 1];
+        for (int t = 0; t < n; ++t) {
+            const int i = i0 + t;
+            layer lt = l;
+            lt.output = l.output + (size_t)t * l.outputs;
+            get_region_boxes(lt, 1, 1, thresh, probs, boxes, 1, 0);
+            if (nms) do_nms(boxes, probs, nboxes, 1, nms);
+
+            char labelpath[4096];
+            label_path_of(paths[i], labelpath);
+            int num_labels = 0;
+            box_label *truth = read_boxes(labelpath, &num_labels);
+            for (int k = 0; k < nboxes; ++k)
+                if (probs[k][0] > thresh) ++proposals;
+            for (int j = 0; j < num_labels; ++j) {
+                ++total;
+                box tb = {truth[j].x, truth[j].y, truth[j].w, truth[j].h};
+                float best_iou = 0;
+                for (int k = 0; k < nboxes; ++k) {
+                    const float iou = box_iou(boxes[k], tb);
+                    if (probs[k][0] > thresh && iou > best_iou) best_iou = iou;
+                }
+                avg_iou += best_iou;
+                if (best_iou > iou_thresh) ++correct;
+            }
+            fprintf(stderr, "%5d %5d %5d\tRPs/Img: %.2f\tIOU: %.2f%%\tRecall:%.2f%%\n", i, correct, total,
+                    (float)proposals / (i + 1), avg_iou * 100 / total, 100. * correct / total);
+            free(truth);
+        }
+    }
+    free(X);
+    for (int j = 0; j < nboxes; ++j) free(probs[j]);
+    free(probs);
+    free(boxes);
+    free(paths);
+    free_list_contents(plist);
+    free_list(plist);
+    free_network(net);
+}
+

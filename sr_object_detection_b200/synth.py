@@ -222,6 +222,32 @@ def write_validation_set(root, kind, w=16, h=12):
     return stems
 
 
+def write_recall_set(root, n_images=7, w=16, h=12, classes=4):
+    """Everything validate_detector_recall (detector.c:371-450) reads, under `root` (run with cwd = root): the exactly
+    representable detector, images/*.png (binary PPM bytes under a .png name: the label path is derived by replacing
+    "images" -> "labels" and ".png" -> ".txt"; both loaders decode by content), labels/*.txt with 1-3 truth boxes per
+    image ("id x y w h", relative units), valid.list and data.cfg."""
+    root = Path(root)
+    (root / "images").mkdir(parents=True, exist_ok=True)
+    (root / "labels").mkdir(exist_ok=True)
+    cfg_text = exact_detector_cfg(batch=1, w=w, h=h, classes=classes, num=3)
+    (root / "net.cfg").write_text(cfg_text)
+    write_exact_weights(root / "net.weights", cfg_text, seed=23, classes=classes, num=3)
+    rng = np.random.default_rng(77)
+    stems = [f"frame_{i:03d}" for i in range(n_images)]
+    for i, stem in enumerate(stems):
+        binary_ppm(root / "images" / f"{stem}.png", w, h, seed=500 + i)
+        lines = []
+        for _ in range(int(rng.integers(1, 4))):
+            bw, bh = rng.uniform(0.2, 0.9), rng.uniform(0.2, 0.9)
+            lines.append("%d %.6f %.6f %.6f %.6f" % (int(rng.integers(0, classes)), rng.uniform(0.2, 0.8),
+                                                      rng.uniform(0.2, 0.8), bw, bh))
+        (root / "labels" / f"{stem}.txt").write_text("\n".join(lines) + "\n")
+    (root / "valid.list").write_text("".join(f"images/{s}.png\n" for s in stems))
+    (root / "data.cfg").write_text(f"classes={classes}\nvalid=valid.list\n")
+    return stems
+
+
 def write_exact_weights(path, cfg_text, seed=5, classes=4, num=3):
     """weights m/32 (m/256 for the tw/th filters, so that boxes stay a few cells wide), biases m/64, |m| <= 32"""
     (sp,) = conv_specs_from_cfg(cfg_text)

@@ -265,6 +265,22 @@ def validation_golden():
     np.savez_compressed(OUT / "validate_ref.npz", **out)
 
 
+def recall_golden():
+    """oracle/_ref/ref_validate recall = the reference's validate_detector_recall (detector.c:371-450) on its CPU path
+    over synth.write_recall_set; its per-image stderr lines (running proposals per image, mean best IoU, recall) are
+    the golden tests/golden/recall_ref.json."""
+    exe = ROOT / "oracle" / "_ref" / "ref_validate"
+    with tempfile.TemporaryDirectory() as t:
+        t = Path(t)
+        synth.write_recall_set(t)
+        r = subprocess.run([str(exe), "recall", "data.cfg", "net.cfg", "net.weights"], cwd=t, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise SystemExit("ref_validate recall failed:\n" + r.stderr[-2000:])
+        lines = [l for l in r.stderr.splitlines() if "RPs/Img" in l]
+    (OUT / "recall_ref.json").write_text(json.dumps({"lines": lines}))
+    print("recall", lines)
+
+
 def demo_golden():
     """oracle/_ref/ref_demo: network_predict -> 3-frame mean -> get_region_boxes -> do_nms(.4) per frame (demo.c:71-107)
     on the exactly representable detector and frames of 0 / 255 bytes."""
@@ -403,5 +419,7 @@ def voc_eval_golden():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "voc_eval":
         voc_eval_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "recall":
+        recall_golden()
     else:
         main()

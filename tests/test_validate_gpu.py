@@ -44,3 +44,48 @@ def test_validation_files_equal_the_reference_files(tmp_path, monkeypatch, kind,
             raise AssertionError(f"{kind}/{name}: {len(a)} lines vs {len(b)}; first difference at line {first}: "
                                  f"{a[first:first + 1]} vs {b[first:first + 1]}")
     assert sum(len(v) for v in want.values()) > 10000  # not vacuous
+
+
+class _CaptureStderr:
+    """file descriptor 2 of this process into a file (the library prints from C)"""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        import sys
+        sys.stderr.flush()
+        self.saved = os.dup(2)
+        self.fd = os.open(self.path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        os.dup2(self.fd, 2)
+        return self
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 2)
+        os.close(self.saved)
+        os.close(self.fd)
+
+
+@pytest.mark.parametrize("chunk", [None, "3"])
+def test_recall_lines_equal_the_reference_lines(tmp_path, monkeypatch, chunk):
+    """validate_detector_recall (detector.c:371-450): objectness proposals (get_region_boxes with only_objectness,
+    do_nms at .4) against label files; the per-image lines - running proposals per image, mean best IoU, recall - must
+    be the ones the REFERENCE's own function printed on its CPU path (tests/golden/recall_ref.json)."""
+    import json
+    want = json.loads((GOLDEN.parent / "recall_ref.json").read_text())["lines"]
+    synth.write_recall_set(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    if chunk:
+        monkeypatch.setenv("Y2_VALID_BATCH", chunk)
+    else:
+        monkeypatch.delenv("Y2_VALID_BATCH", raising=False)
+    lib = dn.lib()
+    dn.set_gpu_index(0)
+    lib.cuda_set_device(0)
+    lib.validate_detector_recall.restype = None
+    lib.validate_detector_recall.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    with _CaptureStderr(str(tmp_path / "stderr.txt")):
+        lib.validate_detector_recall(b"data.cfg", b"net.cfg", b"net.weights")
+    got = [l for l in (tmp_path / "stderr.txt").read_text().splitlines() if "RPs/Img" in l]
+    assert got == want
+    assert len(want) == 7 and any("Recall:0.00%" not in l for l in want)  # not vacuous
