@@ -295,3 +295,33 @@ def test_classifier_front_end_matches_reference_golden():
         idx = (C.c_int * k)()
         lib.top_k(_fp(a), a.size, k, idx)
         assert list(idx) == d[f"topk_{k}"].tolist()
+
+
+def test_find_replace_and_read_boxes_follow_the_reference(tmp_path):
+    """utils.c:158-172 (first occurrence only, output may alias the input) and data.c:135-159 ("id x y w h" records,
+    corners derived in float, reading stops at the first record that does not parse)."""
+    import ctypes as C
+    lib = dn.lib()
+    lib.find_replace.restype = None
+    lib.find_replace.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    out = C.create_string_buffer(4096)
+    lib.find_replace(b"data/images/images_01.png", b"images", b"labels", out)
+    assert out.value == b"data/labels/images_01.png"
+    lib.find_replace(out, b".png", b".txt", out)          # in place, like detector.c:413-418
+    assert out.value == b"data/labels/images_01.txt"
+    lib.find_replace(out, b".jpg", b".txt", out)          # no occurrence: unchanged
+    assert out.value == b"data/labels/images_01.txt"
+
+    class BoxLabel(C.Structure):
+        _fields_ = [("id", C.c_int)] + [(k, C.c_float) for k in ("x", "y", "w", "h", "left", "right", "top", "bottom")]
+
+    lib.read_boxes.restype = C.POINTER(BoxLabel)
+    lib.read_boxes.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    p = tmp_path / "l.txt"
+    p.write_text("3 0.5 0.25 0.2 0.1\n7 0.125 0.75 0.5 0.5\nnot a record\n1 0.1 0.1 0.1 0.1\n")
+    n = C.c_int()
+    b = lib.read_boxes(str(p).encode(), C.byref(n))
+    assert n.value == 2
+    assert (b[0].id, b[0].x, b[0].y, b[0].w, b[0].h) == (3, 0.5, 0.25, np.float32(0.2), np.float32(0.1))
+    assert b[0].left == np.float32(0.5) - np.float32(0.2) / 2 and b[0].bottom == np.float32(0.25) + np.float32(0.1) / 2
+    assert (b[1].id, b[1].left, b[1].right, b[1].top, b[1].bottom) == (7, -0.125, 0.375, 0.5, 1.0)
